@@ -1,0 +1,237 @@
+"""ctypes binding of the CPU oracle (oracle/ddz_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (doudizhu-rl_b200/) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libddz_oracle.so")
+_lib = None
+
+MAX_LEGAL = 512
+NUNIVERSE = 13551
+NACTIONS_CARD_PY = 13527
+VARIANT_CHANNELS = (4, 7, 9, 6)
+DEFAULT_REWARDS = (50, 100, 50)  # role 0 up, 1 lord, 2 down (reference game.py:13-14)
+
+
+class RefEnv(C.Structure):
+    _fields_ = [("hand", (C.c_int8 * 15) * 3), ("hist", (C.c_int8 * 15) * 3), ("recent", (C.c_int8 * 15) * 3),
+                ("cur", C.c_int8), ("done", C.c_int8), ("winner", C.c_int8), ("err", C.c_int8),
+                ("games", C.c_int32)]
+
+
+ENV_DTYPE = np.dtype([("hand", np.int8, (3, 15)), ("hist", np.int8, (3, 15)), ("recent", np.int8, (3, 15)),
+                      ("cur", np.int8), ("done", np.int8), ("winner", np.int8), ("err", np.int8),
+                      ("games", np.int32)], align=True)
+assert ENV_DTYPE.itemsize == C.sizeof(RefEnv)
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("ddz_oracle.c", "ddz_oracle.h")]
+    if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libddz_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        i8p, i32p, i64p, u64p, f32p, u8p, u32p = (C.POINTER(t) for t in (
+            C.c_int8, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_uint8, C.c_uint32))
+        ip = C.POINTER(C.c_int)
+        envp = C.c_void_p
+        L.ddz_ref_universe_size.restype = C.c_int
+        L.ddz_ref_universe_get.argtypes = [C.c_int, i8p, ip, ip, ip, ip]
+        L.ddz_ref_classify.argtypes = [i8p, ip, ip, ip]
+        L.ddz_ref_bigger_than.argtypes = [C.c_int] * 6
+        L.ddz_ref_get_moves.argtypes = [i8p, i8p, i8p, C.c_int]
+        L.ddz_ref_get_moves_fast.argtypes = [i8p, i8p, i8p, C.c_int]
+        L.ddz_ref_count_moves_fast.argtypes = [i8p, i8p]
+        L.ddz_ref_env_clear.argtypes = [envp]
+        L.ddz_ref_env_clear.restype = None
+        L.ddz_ref_env_deal.argtypes = [envp, i8p, C.c_int]
+        L.ddz_ref_env_last.argtypes = [envp, i8p]
+        L.ddz_ref_env_last.restype = None
+        L.ddz_ref_env_legal.argtypes = [envp, i8p, C.c_int, C.c_int]
+        L.ddz_ref_env_step.argtypes = [envp, i8p, i32p, ip, ip, ip, f32p]
+        L.ddz_ref_state_prob.argtypes = [envp, f32p]
+        L.ddz_ref_state_prob.restype = None
+        L.ddz_ref_state_prob_manual.argtypes = [i32p, C.c_int, C.c_int, f32p]
+        L.ddz_ref_state_prob_manual.restype = None
+        L.ddz_ref_env_face.argtypes = [envp, C.c_int, f32p]
+        L.ddz_ref_encode_actions.argtypes = [i8p, C.c_int, f32p]
+        L.ddz_ref_encode_actions.restype = None
+        L.ddz_ref_pack.argtypes = [i8p]
+        L.ddz_ref_pack.restype = C.c_uint64
+        L.ddz_ref_unpack.argtypes = [C.c_uint64, i8p]
+        L.ddz_ref_unpack.restype = None
+        L.ddz_ref_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        L.ddz_ref_philox.restype = C.c_uint32
+        L.ddz_ref_batch_observe.argtypes = [envp, C.c_int, C.c_int, C.c_int, i32p, u64p, f32p, C.c_int64, f32p]
+        L.ddz_ref_batch_observe.restype = C.c_int64
+        L.ddz_ref_batch_step.argtypes = [envp, C.c_int, i32p, u64p, i32p, C.c_int, C.c_uint64, C.c_uint64,
+                                         C.c_uint32, i32p, i8p, u8p, i8p, f32p, i64p]
+        L.ddz_ref_batch_deal.argtypes = [envp, C.c_int, i8p, i8p, C.c_int, C.c_int]
+        L.ddz_ref_batch_export.argtypes = [envp, C.c_int, u64p, u32p]
+        L.ddz_ref_batch_export.restype = None
+        L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p]
+        L.ddz_ref_rollout.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _i8(a):
+    return np.ascontiguousarray(a, dtype=np.int8)
+
+
+# ---------------------------------------------------------------- rules
+def universe():
+    """(counts int8[U,15], cat, len, val, is_extra) in canonical order."""
+    L = lib()
+    n = L.ddz_ref_universe_size()
+    counts = np.zeros((n, 15), np.int8)
+    meta = np.zeros((n, 4), np.int32)
+    c, l, v, x = (C.c_int() for _ in range(4))
+    for i in range(n):
+        L.ddz_ref_universe_get(i, _ptr(counts[i], C.c_int8), C.byref(c), C.byref(l), C.byref(v), C.byref(x))
+        meta[i] = (c.value, l.value, v.value, x.value)
+    return counts, meta[:, 0], meta[:, 1], meta[:, 2], meta[:, 3]
+
+
+def classify(counts):
+    c, l, v = C.c_int(), C.c_int(), C.c_int()
+    a = _i8(counts)
+    idx = lib().ddz_ref_classify(_ptr(a, C.c_int8), C.byref(c), C.byref(l), C.byref(v))
+    return idx, c.value, l.value, v.value
+
+
+def bigger_than(a, g):
+    return bool(lib().ddz_ref_bigger_than(*[int(x) for x in a], *[int(x) for x in g]))
+
+
+def get_moves(hand, last, fast=False):
+    """r.get_moves(hand15, last15) -> int8[N,15]"""
+    h, l = _i8(hand), _i8(last)
+    out = np.zeros((MAX_LEGAL, 15), np.int8)
+    f = lib().ddz_ref_get_moves_fast if fast else lib().ddz_ref_get_moves
+    n = f(_ptr(h, C.c_int8), _ptr(l, C.c_int8), _ptr(out, C.c_int8), MAX_LEGAL)
+    if n < 0 or n > MAX_LEGAL:
+        raise ValueError("get_moves failed: %d" % n)
+    return out[:n].copy()
+
+
+def pack(counts):
+    a = _i8(counts)
+    if a.ndim == 1:
+        return int(lib().ddz_ref_pack(_ptr(a, C.c_int8)))
+    sh = (np.arange(15, dtype=np.uint64) * np.uint64(4))
+    return (a.astype(np.uint64) << sh).sum(axis=-1, dtype=np.uint64)
+
+
+def unpack(packed):
+    p = np.asarray(packed, dtype=np.uint64)
+    sh = (np.arange(15, dtype=np.uint64) * np.uint64(4))
+    return ((p[..., None] >> sh) & np.uint64(15)).astype(np.int8)
+
+
+def philox(seed, env, step):
+    return int(lib().ddz_ref_philox(int(seed), int(env), int(step)))
+
+
+def state_prob_manual(known60, size1, size2):
+    k = np.ascontiguousarray(known60, dtype=np.int32).reshape(60)
+    out = np.zeros(120, np.float32)
+    lib().ddz_ref_state_prob_manual(_ptr(k, C.c_int32), int(size1), int(size2), _ptr(out, C.c_float))
+    return out
+
+
+# ---------------------------------------------------------------- batched env
+class RefBatch:
+    """B oracle envs driven in lock-step; mirrors the product's batched API for parity tests."""
+
+    def __init__(self, B, variant=2, rewards=DEFAULT_REWARDS):
+        self.B, self.variant = int(B), int(variant)
+        self.C = VARIANT_CHANNELS[variant]
+        self.envs = np.zeros(self.B, ENV_DTYPE)
+        self.envs["winner"] = -1
+        self.envs["cur"] = 1
+        self.rewards = np.asarray(rewards, np.int32)
+        self.stats = np.zeros(16, np.int64)
+        self.offsets = np.zeros(self.B + 1, np.int32)
+        self.actions_u64 = np.zeros(0, np.uint64)
+
+    @property
+    def _p(self):
+        return self.envs.ctypes.data_as(C.c_void_p)
+
+    def clear(self):
+        for b in range(self.B):
+            lib().ddz_ref_env_clear(C.c_void_p(self.envs.ctypes.data + b * ENV_DTYPE.itemsize))
+
+    def deal(self, perm, lord_pile=None, only_done=False, pool_games=1):
+        perm = _i8(perm)
+        lp = None if lord_pile is None else _i8(lord_pile)
+        rc = lib().ddz_ref_batch_deal(self._p, self.B, _ptr(perm, C.c_int8), _ptr(lp, C.c_int8),
+                                      int(only_done), int(pool_games))
+        if rc != 0:
+            raise ValueError("bad deal")
+
+    def observe(self, fast=True, want_f32=True, want_face=True):
+        cap = self.B * MAX_LEGAL
+        offsets = np.zeros(self.B + 1, np.int32)
+        # first pass for the count keeps the buffers tight
+        total = lib().ddz_ref_batch_observe(self._p, self.B, self.variant, int(fast), _ptr(offsets, C.c_int32),
+                                            None, None, 0, None)
+        if total < 0:
+            raise ValueError("observe failed")
+        au = np.zeros(total, np.uint64)
+        af = np.zeros((total, 15, 4), np.float32) if want_f32 else None
+        face = np.zeros((self.B, self.C, 15, 4), np.float32) if want_face else None
+        lib().ddz_ref_batch_observe(self._p, self.B, self.variant, int(fast), _ptr(offsets, C.c_int32),
+                                    _ptr(au, C.c_uint64), _ptr(af, C.c_float), total,
+                                    _ptr(face, C.c_float))
+        self.offsets, self.actions_u64 = offsets, au
+        return offsets, au, af, face
+
+    def step(self, choice=None, mode=0, seed=0, env0=0, step=0):
+        ch = None if choice is None else np.ascontiguousarray(choice).view(np.int32)
+        r = np.zeros(self.B, np.int8)
+        done = np.zeros(self.B, np.uint8)
+        cat = np.zeros(self.B, np.int8)
+        rew = np.zeros((self.B, 3), np.float32)
+        lib().ddz_ref_batch_step(self._p, self.B, _ptr(self.offsets, C.c_int32), _ptr(self.actions_u64, C.c_uint64),
+                                 _ptr(ch, C.c_int32), int(mode), int(seed), int(env0), int(step),
+                                 _ptr(self.rewards, C.c_int32), _ptr(r, C.c_int8), _ptr(done, C.c_uint8),
+                                 _ptr(cat, C.c_int8), _ptr(rew, C.c_float), _ptr(self.stats, C.c_int64))
+        return r, done, cat, rew
+
+    def export(self):
+        f = np.zeros((9, self.B), np.uint64)
+        meta = np.zeros(self.B, np.uint32)
+        lib().ddz_ref_batch_export(self._p, self.B, _ptr(f, C.c_uint64), _ptr(meta, C.c_uint32))
+        return f, meta
+
+
+def rollout(B, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads):
+    """CPU baseline: returns (env_steps, stats int64[16], checksum)."""
+    perm_pool = _i8(perm_pool)
+    lp = None if lord_pool is None else _i8(lord_pool)
+    stats = np.zeros(16, np.int64)
+    cs = C.c_uint64(0)
+    n = lib().ddz_ref_rollout(int(B), int(steps), int(variant), int(seed), _ptr(perm_pool, C.c_int8),
+                              _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64), C.byref(cs))
+    return int(n), stats, int(cs.value)

@@ -1,0 +1,164 @@
+"""CPU: pin the oracle to the reference's own golden vectors (tests/golden/, made by make_golden.py from
+rule_based/utils/card.py, server/rule_utils/utils.py, server/mcts/get_moves.py and the unmodified envi.py)."""
+import numpy as np
+import pytest
+
+
+def test_universe_is_card_py_action_space_plus_24(oracle, golden):
+    cnt, cat, ln, val, extra = oracle.universe()
+    g = golden.card_space
+    assert len(cnt) == 13551 and int(extra.sum()) == 24
+    keep = extra == 0
+    assert np.array_equal(cnt[keep], g["counts"])                      # card.py:34-159, same order
+    assert np.array_equal(np.stack([cat, ln, val], 1)[keep], g["attrs"])  # card.py:372-527 type/len/value
+    # Category2Range (card.py:31) == first/last index of each category in the 13 527 list
+    c = cat[keep]
+    for k, (lo, hi) in enumerate(g["cat_range"]):
+        assert (c[lo:hi] == k).all() and (lo == 0 or c[lo - 1] != k) and (hi == len(c) or c[hi] != k)
+    assert len(set(oracle.pack(cnt).tolist())) == 13551                # duplicate-free universe
+    assert int(cnt.sum(axis=1).max()) == 20
+
+
+def test_extras_are_the_24_rocket_kicker_moves(oracle, golden):
+    cnt, cat, ln, val, extra = oracle.universe()
+    mine = {tuple(r) for r in cnt[extra == 1].tolist()}
+    ref = {tuple(r) for r in golden.rocket24["counts"].tolist()}      # server/mcts/get_moves.py:22-34
+    assert mine == ref
+    ls = golden.legal_sets
+    for c, (t, l, v) in zip(golden.rocket24["counts"], ls["extra_attrs"]):
+        idx, mc, ml, mv = oracle.classify(c)
+        assert idx >= 0 and (mc, ml, mv) == (t, l, v)                  # reference to_cardgroup agrees
+
+
+def test_bigger_than_matches_card_py(oracle, golden):
+    g = golden.beats
+    attrs = golden.card_space["attrs"]
+    a, b = attrs[g["pairs"][:, 0]], attrs[g["pairs"][:, 1]]
+    mine = np.array([oracle.bigger_than(x, y) for x, y in zip(a, b)], np.uint8)
+    assert np.array_equal(mine, g["beats"])
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_legal_sets_match_get_mask_onehot60(oracle, golden, fast):
+    g = golden.legal_sets
+    assert np.array_equal(g["universe"], oracle.universe()[0])
+    off = g["legal_off"]
+    for i, (h, last) in enumerate(zip(g["hands"], g["lasts"])):
+        want = g["universe"][g["legal_idx"][off[i]:off[i + 1]]]
+        got = oracle.get_moves(h, last, fast=fast)
+        assert np.array_equal(got, want), (i, h, last)
+
+
+def test_known_answers(oracle):
+    z = np.zeros(15, np.int8)
+    # 20-card hand 333444 5..A 22 *$ -> 167 lead moves; vs 9995 -> only rocket (+ pass)
+    h = np.array([3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1], np.int8)
+    assert h.sum() == 20
+    # card.py space gives 167; the oracle additionally emits 333444+*$ (rocket-kicker extra) -> 168
+    moves = oracle.get_moves(h, z)
+    extra = np.array([3, 3] + [0] * 11 + [1, 1], np.int8)
+    assert len(moves) == 168 and any((m == extra).all() for m in moves)
+    last = np.zeros(15, np.int8); last[6] = 3; last[2] = 1   # 999 + 5
+    got = oracle.get_moves(h, last)
+    assert len(got) == 2 and not got[0].any() and got[1][13] == 1 and got[1][14] == 1
+    worst = np.array([1, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0], np.int8)
+    assert len(oracle.get_moves(worst, z)) == 497               # SURVEY.md App. B worst lead hand
+    assert len(oracle.get_moves(z, z)) == 0                      # empty hand, lead: nothing
+    assert oracle.get_moves(z, worst * 0 + np.eye(15, dtype=np.int8)[0]).shape == (1, 15)  # follow: pass only
+
+
+def test_fast_equals_definitional_random(oracle):
+    rng = np.random.default_rng(123)
+    deck = np.array([i // 4 for i in range(52)] + [13, 14])
+    z = np.zeros(15, np.int8)
+    for it in range(4000):
+        h = np.bincount(rng.permutation(deck)[:rng.integers(1, 21)], minlength=15).astype(np.int8)
+        if it % 2:
+            o = np.bincount(rng.permutation(deck)[:rng.integers(1, 21)], minlength=15).astype(np.int8)
+            om = oracle.get_moves(o, z, fast=True)
+            last = om[rng.integers(len(om))]
+        else:
+            last = z
+        assert np.array_equal(oracle.get_moves(h, last), oracle.get_moves(h, last, fast=True))
+
+
+def _replay(oracle, golden, variant, key):
+    """Replay the recorded game (perms + choice stream) through the oracle's BATCHED driver and compare with what
+    the unmodified envi.py produced step by step."""
+    t = golden.envi_trace
+    games = t["game"]
+    faces = t[key]
+    fi = li = ai = 0
+    for g in range(len(t["perms"])):
+        rb = oracle.RefBatch(1, variant)
+        rb.deal(t["perms"][g][None], np.zeros(1, np.int8))
+        for s in np.flatnonzero(games == g):
+            off, au, af, face = rb.observe(fast=False)
+            n = int(t["n_legal"][s])
+            assert off[1] == n
+            assert np.array_equal(oracle.unpack(au), t["legal"][li:li + n])
+            assert np.array_equal(af, t["actions_f32"][ai:ai + n])
+            assert np.array_equal(face[0], faces[fi]), (g, s)
+            f, meta = rb.export()
+            assert (meta[0] & 3) == t["role"][s]
+            li += n; ai += n; fi += 1
+            r, done, cat, rew = rb.step(np.array([t["choice"][s]], np.int32), mode=0)
+            assert (r[0], done[0], cat[0]) == (t["r"][s], t["done"][s], t["cat"][s])
+            f, meta = rb.export()
+            hands = oracle.unpack(f[0:3, 0]); hist = oracle.unpack(f[3:6, 0]); rec = oracle.unpack(f[6:9, 0])
+            assert np.array_equal(hands.sum(1), t["left"][s])            # envi.py:39 left[role]
+            assert np.array_equal(hist, t["history"][s])                 # envi.py:41
+            assert np.array_equal(rec, t["recent"][s])                   # envi.py:42-43
+            assert np.array_equal(hist.sum(0), t["taken"][s])            # envi.py:40
+        # terminal face (game.py:121-122)
+        _, _, _, face = rb.observe()
+        assert np.array_equal(face[0], faces[fi])
+        fi += 1
+    assert fi == len(faces)
+
+
+@pytest.mark.parametrize("variant,key", [(0, "face_first"), (1, "face_complicated"),
+                                         (2, "face_cooperation"), (3, "face_simplify")])
+def test_envi_trace_replay(oracle, golden, variant, key):
+    _replay(oracle, golden, variant, key)
+
+
+def test_philox_stream_matches_trace(oracle, golden):
+    t = golden.envi_trace
+    seed = int(t["seed"])
+    for g in range(len(t["perms"])):
+        idx = np.flatnonzero(t["game"] == g)
+        for k, s in enumerate(idx):
+            assert oracle.philox(seed, g, k) % int(t["n_legal"][s]) == t["choice"][s]
+    # Philox4x32-10 known-answer (Random123 kat_vectors: counter=0, key=0 -> 6627e8d5 ...)
+    assert oracle.philox(0, 0, 0) == 0x6627E8D5
+
+
+def test_converters_golden(golden):
+    g = golden.converters
+    arrs, onehot = g["arrs"], g["onehot"]
+    therm = (np.arange(4)[None, None, :] < arrs[:, :, None]).astype(np.int8)   # envi.py:140-146
+    assert np.array_equal(therm, onehot)
+    for i, a in enumerate(arrs):
+        cards = g["cards_flat"][g["cards_off"][i]:g["cards_off"][i + 1]]
+        assert np.array_equal(np.repeat(np.arange(15) + 3, a), cards)           # envi.py:119-130
+
+
+def test_deal_rejects_bad_perm(oracle):
+    rb = oracle.RefBatch(1)
+    bad = np.zeros((1, 54), np.int8)
+    with pytest.raises(ValueError):
+        rb.deal(bad)
+
+
+def test_illegal_and_done_steps_are_noops(oracle):
+    rng = np.random.default_rng(5)
+    rb = oracle.RefBatch(2)
+    rb.deal(np.stack([rng.permutation(54), rng.permutation(54)]).astype(np.int8))
+    off, au, _, _ = rb.observe()
+    before = rb.export()
+    r, done, cat, rew = rb.step(np.array([off[1] - off[0], -1], np.int32))       # out of range both
+    after = rb.export()
+    assert (cat == -1).all() and (r == 0).all() and not done.any()
+    assert np.array_equal(before[0], after[0]) and rb.stats[7] == 2
+    assert ((after[1] >> 5) & 1).all()                                           # sticky error flag
