@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched Doudizhu env (legal moves + state/action encode + step + re-deal).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one fused env-step of every env of the rank's slice (ddz_rollout_step: apply the chosen move,
+re-deal finished envs, generate the legal moves of the new state, write face [B,9,15,4] and the action one-hots).
+Workload: BASELINE.json config 4's per-GPU slice -- 131 072 envs per GPU (weak scaling), EnvCooperation face
+(C=9, reference train.py:4-5), all three seats play uniformly random legal moves from the Philox index stream
+(config 2's lord-vs-random policy), synthetic random deals.  Inputs per step are ~0.5 GB of output traffic, i.e.
+larger than the 126 MB L2, so no flush between iterations is needed.
+
+--impl reference times the CPU restatement of the reference env (oracle/, kind "port": the reference's own native
+modules are not shipped) on all host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (legal moves + state encode)"
+UNIT = "env-steps/s"
+VARIANT, CHANNELS = 2, 9            # EnvCooperation
+STATE_BYTES = 76                    # 9 x uint64 + uint32 per env (include/ddz_b200.h)
+POOL_GAMES = 8
+SEED = 20260101
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=131072, help="envs per GPU")
+    ap.add_argument("--prefill", type=int, default=150, help="untimed env-steps that bring the games to their steady-state mix")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def bytes_per_env_step(nbar, C=CHANNELS):
+    """ALGORITHMIC bytes of one env-step: state read+write, face write, action one-hot + packed list write,
+    offset write, chosen-move gather + offsets read, r/done/cat/reward write, counts write+read."""
+    transition = 2 * STATE_BYTES + 8 + 8 + 15 + 4
+    emit = STATE_BYTES + 4 + 4 + 240 * C + 248 * nbar
+    return transition, emit
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_rollout(envs, warm, steps, threads):
+    import ddz_b200  # noqa: F401  (only for random_deals; pure numpy)
+    from oracle import ddz_oracle as O
+    perm, lord = ddz_b200.random_deals(envs, seed=SEED, pool_games=POOL_GAMES)
+    n, sec, stats, cs = O.rollout(envs, warm, steps, VARIANT, SEED, perm, lord, POOL_GAMES, threads)
+    return n, sec, stats
+
+
+def cpu_baseline(target_seconds):
+    """oracle port timed on this box's host cores over a bounded sample of the same workload."""
+    threads = os.cpu_count() or 1
+    envs = 512 * threads
+    n, sec, _ = cpu_rollout(envs, 100, 20, threads)                 # calibration
+    rate = n / max(sec, 1e-9)
+    steps = max(20, min(int(target_seconds * rate / envs), 4000))
+    n, sec, stats = cpu_rollout(envs, 100, steps, threads)
+    return {"value": n / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs x %d env-steps after 100 warm-up steps (%.1f s), C oracle (oracle/ddz_oracle.c), "
+                      "mean legal moves %.2f" % (envs, steps, sec, stats[8] / max(n, 1))}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path = oracle port on all host threads (its natives are absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs = 1024 * threads
+    warm_prefill = 100
+    # W warm-up steps then exactly K timed steps, each one env-step of the bounded sample of `envs` envs
+    n, sec, stats = cpu_rollout(envs, warm_prefill + args.warmup, args.steps, threads)
+    value = n / sec
+    nbar = stats[8] / max(n, 1)
+    sample = "%d envs (of the %d-per-GPU workload) x %d env-steps, C oracle port, %d threads" % (envs, args.envs, args.steps, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "lord-vs-random rollout, EnvCooperation C=9, %d envs per GPU" % args.envs,
+                       "sample_envs": envs, "mean_legal_moves": nbar, "prefill_steps": warm_prefill},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ddz_b200 as D
+
+    rank, local, world = D.sharding.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the env has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, K, W, G = args.envs, args.steps, args.warmup, POOL_GAMES
+    env0 = rank * B                                   # global env ids keep results independent of the GPU count
+    perm, lord = D.random_deals(B, seed=SEED + 1000 * rank, pool_games=G)
+    perm_d, lord_d = torch.as_tensor(perm).to(dev), torch.as_tensor(lord).to(dev)
+    env = D.BatchedEnvCooperation(B, seed=SEED, device=dev, env0=env0, max_actions_per_env=160)
+    env.prepare(perm_d, lord_d, pool_games=G)
+    env.observe()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    step_kw = dict(mode=D.native.CHOICE_PHILOX, perm=perm_d, lord_pile=lord_d, pool_games=G)
+    for _ in range(args.prefill + W):
+        env.rollout_step(**step_kw)
+    torch.cuda.synchronize(dev)
+    if int(env.stats[7].item()):
+        raise SystemExit("env reported errors during warm-up")
+
+    # ---------------- timed region: device-resident inputs, CUDA events on the launching (current) stream
+    stats0 = env.stats.clone()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev[0].record()
+    for k in range(K):
+        env.rollout_step(mid_event=ev[2 * k + 1], **step_kw)
+        ev[2 * k + 2].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[2 * K])
+    emit_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)) / K
+    trans_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)) / K
+    dstats_t = (env.stats - stats0).clone()
+    dstats = dstats_t.cpu().numpy()
+    if int(env.stats[7].item()):
+        raise SystemExit("env reported errors during the timed region")
+    local_steps = int(dstats[4])
+    assert local_steps == B * K, (local_steps, B * K)   # every env applied one move per step (finished ones re-dealt)
+    nbar = float(dstats[8]) / local_steps
+
+    # ---------------- e2e: same step through the public API with HOST buffers (pinned) every step
+    R = 4
+    perm_h = [torch.as_tensor(D.random_deals(B, seed=SEED + 77 + i + 1000 * rank)[0]).pin_memory() for i in range(R)]
+    lord_h = [torch.zeros(B, dtype=torch.int8).pin_memory() for _ in range(R)]
+    rng = np.random.default_rng(SEED + rank)
+    ent_h = [torch.as_tensor(rng.integers(0, 1 << 31, B, dtype=np.int64).astype(np.int32)).pin_memory() for _ in range(R)]
+    perm_e, lord_e = torch.empty_like(perm_h[0], device=dev), torch.empty_like(lord_h[0], device=dev)
+    ent_e = torch.empty_like(ent_h[0], device=dev)
+    out_h = {"r": torch.empty(B, dtype=torch.int8).pin_memory(), "done": torch.empty(B, dtype=torch.uint8).pin_memory(),
+             "cat": torch.empty(B, dtype=torch.int8).pin_memory(), "reward": torch.empty((B, 3), dtype=torch.float32).pin_memory()}
+
+    def e2e_step(i):
+        perm_e.copy_(perm_h[i % R], non_blocking=True)
+        lord_e.copy_(lord_h[i % R], non_blocking=True)
+        ent_e.copy_(ent_h[i % R], non_blocking=True)
+        env.rollout_step(choice=ent_e, mode=D.native.CHOICE_MOD, perm=perm_e, lord_pile=lord_e, pool_games=1)
+        out_h["r"].copy_(env.r, non_blocking=True)
+        out_h["done"].copy_(env.done, non_blocking=True)
+        out_h["cat"].copy_(env.cat, non_blocking=True)
+        out_h["reward"].copy_(env.reward, non_blocking=True)
+
+    for i in range(max(W, 3)):
+        e2e_step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = B * (54 + 1 + 4)
+    d2h = B * (1 + 1 + 1 + 12)
+    if int(env.stats[7].item()):
+        raise SystemExit("env reported errors during the e2e region")
+
+    # ---------------- reduce over ranks: MAX of the device times, SUM of the work
+    total_ms = D.sharding.max_over_ranks(total_ms, dev)
+    e2e_ms = D.sharding.max_over_ranks(e2e_ms, dev)
+    emit_ms = D.sharding.max_over_ranks(emit_ms, dev)
+    trans_ms = D.sharding.max_over_ranks(trans_ms, dev)
+    gstats = D.sharding.allreduce_stats(dstats_t, side_stream=torch.cuda.Stream(dev) if world > 1 else None)
+    torch.cuda.synchronize(dev)
+    all_steps = int(gstats[4].item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        tb, eb = bytes_per_env_step(nbar)
+        value = all_steps / (total_ms * 1e-3)
+        emit_gbs = B * eb / (emit_ms * 1e-3) / 1e9
+        step_gbs = (all_steps / world) * (tb + eb) / (total_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 per-GPU slice: %d envs/GPU, lord-vs-random rollout (all seats uniform "
+                                   "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % B,
+                       "envs_per_gpu": B, "face_channels": CHANNELS, "mean_legal_moves": nbar,
+                       "prefill_steps": args.prefill, "pool_games": G, "parallelism": "env-shard x%d" % world,
+                       "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * (tb + eb) / 1e6),
+                       "games_finished": int(gstats[0].item()),
+                       "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))},
+            "roofline": {"bound": "hbm", "kernel": "k_emit", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": emit_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env": eb, "ms_per_launch": emit_ms,
+                         "step_achieved": step_gbs, "step_frac": step_gbs / peak, "step_bytes_per_env": tb + eb,
+                         "transition_ms_per_launch": trans_ms},
+            "e2e": {"value": B * K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+            "gpu_launches": 2 * K,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""doudizhu-rl_b200 -- B200-native batched Doudizhu environment (drop-in for the rollout path of
+charleschen003/doudizhu-rl: envi.py + its absent native modules `env` and `r`).
+
+The directory name carries a hyphen, so import it as `ddz_b200` (the alias module at the repo root) or with
+importlib.import_module("doudizhu-rl_b200").
+"""
+from . import _native as native  # raises ImportError when libddz_b200.so has not been built
+from . import sharding
+from .env import (BatchedEnv, BatchedEnvComplicated, BatchedEnvCooperation, BatchedEnvCooperationSimplify,
+                  Env, EnvComplicated, EnvCooperation, EnvCooperationSimplify,
+                  get_moves, pack_counts, unpack_counts, default_deals, random_deals,
+                  VARIANT_CHANNELS, DEFAULT_REWARDS)
+
+__all__ = ["native", "sharding", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
+           "Env", "EnvComplicated", "EnvCooperation", "EnvCooperationSimplify", "get_moves", "pack_counts",
+           "unpack_counts", "default_deals", "random_deals", "VARIANT_CHANNELS", "DEFAULT_REWARDS"]

@@ -1,0 +1,61 @@
+"""ctypes binding of libddz_b200.so -- the C-ABI declared in include/ddz_b200.h.
+
+There is no CPU fallback: if the library is missing this module raises at import, and every launcher
+raises when the CUDA runtime reports an error (e.g. no device)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libddz_b200.so")
+
+E_ARG, E_CUDA = -1, -2
+FACE_FIRST, FACE_COMPLICATED, FACE_COOPERATION, FACE_SIMPLIFY = range(4)
+CHOICE_INDEX, CHOICE_MOD, CHOICE_PHILOX, CHOICE_MOVE = range(4)
+MAX_LEGAL = 512
+ABI_VERSION = 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). The batched env has no CPU fallback." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+_vp, _i, _i64, _u64, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32
+
+lib.ddz_abi_version.restype = _i
+lib.ddz_face_channels.argtypes = [_i]
+lib.ddz_state_bytes.argtypes = [_i]
+lib.ddz_state_bytes.restype = C.c_size_t
+lib.ddz_workspace_bytes.argtypes = [_i]
+lib.ddz_workspace_bytes.restype = C.c_size_t
+lib.ddz_last_error.restype = C.c_char_p
+lib.ddz_reset.argtypes = [_vp, _vp, _vp, _i, _i, _vp, _i, _vp]
+lib.ddz_observe.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
+lib.ddz_step.argtypes = [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.ddz_rollout_step.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _i,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
+lib.ddz_rollout_step_begin.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _i,
+                                       _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.ddz_rollout_step_end.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
+lib.ddz_legal_moves.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]
+lib.ddz_encode_actions.argtypes = [_vp, _i64, _vp, _vp]
+lib.ddz_encode_face.argtypes = [_vp, _i, _vp, _i, _vp]
+
+EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
+           "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_rollout_step_begin", "ddz_rollout_step_end", "ddz_legal_moves", "ddz_encode_actions",
+           "ddz_encode_face")
+
+if lib.ddz_abi_version() != ABI_VERSION:
+    raise ImportError("libddz_b200.so ABI %d != binding %d: rebuild" % (lib.ddz_abi_version(), ABI_VERSION))
+
+
+class DdzError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc == E_CUDA:
+        raise DdzError("%s: CUDA failure: %s" % (what, lib.ddz_last_error().decode()))
+    raise DdzError("%s: bad argument (code %d)" % (what, rc))

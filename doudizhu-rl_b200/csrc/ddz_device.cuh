@@ -1,0 +1,389 @@
+// ddz_device.cuh -- device-side Doudizhu rules for sm_100a: rank masks, move classification, legal-move
+// counting (closed form) and enumeration (canonical order), deal, state transition, Philox.
+//
+// Representation.  A hand / move is 15 per-rank counts packed as nibbles in a uint64 ("packed").  All rule
+// logic runs on four dense 15-bit rank masks g1..g4 (bit r of gk <=> count[r] >= k), i.e. the thermometer
+// planes of the reference's one-hot (envi.py:140-146).  Sets of ranks are then popc / shift-AND / ffs work:
+//   runs (straights, pair-straights, airplanes)  = shift-AND chains over a mask,
+//   kicker choices                               = lexicographic k-subsets of a mask,
+//   counts                                       = popc x binomial table.
+// Canonical order of the move list = index order of the reference's action space
+// (rule_based/utils/card.py:34-159), pass first when following, the 24 rocket-kicker moves of
+// server/mcts/get_moves.py:22-34 where unfiltered itertools.combinations would put them.
+#pragma once
+#include <cstdint>
+
+#define DDZ_DEV __device__ __forceinline__
+
+namespace ddz {
+
+constexpr uint64_t kDeckPacked = 0x0114444444444444ull;  // 4 of ranks 0..12, one of each joker
+constexpr uint32_t kLineMask = 0x0FFFu;                  // ranks 3..A may appear in sequences (card.py:86-130)
+constexpr uint32_t kRocket = 0x6000u;
+
+struct Masks { uint32_t g1, g2, g3, g4; };
+
+// bits at 0,4,..,28 of a 32-bit word -> dense 8 bits
+DDZ_DEV uint32_t compress8(uint32_t s) {
+    s = (s | (s >> 3)) & 0x03030303u;
+    s = (s | (s >> 6)) & 0x000F000Fu;
+    s = (s | (s >> 12)) & 0xFFu;
+    return s;
+}
+// dense 8 bits -> bits at 0,4,..,28
+DDZ_DEV uint32_t spread8(uint32_t x) {
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
+}
+DDZ_DEV uint32_t plane15(uint32_t lo, uint32_t hi, int bit) {
+    return compress8((lo >> bit) & 0x11111111u) | (compress8((hi >> bit) & 0x11111111u) << 8);
+}
+DDZ_DEV Masks masks_of(uint64_t packed) {
+    uint32_t lo = (uint32_t)packed, hi = (uint32_t)(packed >> 32);
+    uint32_t b0 = plane15(lo, hi, 0), b1 = plane15(lo, hi, 1), b2 = plane15(lo, hi, 2);
+    Masks m;
+    m.g4 = b2;                 // counts are 0..4: 4 = 0b100
+    m.g3 = b2 | (b1 & b0);
+    m.g2 = b2 | b1;
+    m.g1 = b2 | b1 | b0;
+    return m;
+}
+// packed move = mult x (one per rank of `main`) + kmult x (one per rank of `kick`)
+DDZ_DEV uint64_t pack_move(uint32_t main, uint32_t mult, uint32_t kick, uint32_t kmult) {
+    uint32_t lo = spread8(main & 0xFFu) * mult + spread8(kick & 0xFFu) * kmult;
+    uint32_t hi = spread8(main >> 8) * mult + spread8(kick >> 8) * kmult;
+    return ((uint64_t)hi << 32) | lo;
+}
+DDZ_DEV int card_count(uint64_t packed) {  // sum of the 15 nibbles (<= 20)
+    uint64_t x = (packed & 0x0F0F0F0F0F0F0F0Full) + ((packed >> 4) & 0x0F0F0F0F0F0F0F0Full);
+    return (int)((x * 0x0101010101010101ull) >> 56);
+}
+DDZ_DEV uint32_t above(int v) { return ~((1u << v) - 1u); }  // ranks >= v, v in 0..31
+
+// what has to be beaten: category / length / main rank of the last non-pass hand-out
+// (CardGroup type/len/value, card.py:372-527); cat 0 = free lead
+struct Trick { int cat, len, val; };
+
+DDZ_DEV Trick classify(uint64_t move) {
+    Trick t; t.cat = 0; t.len = 1; t.val = 0;
+    if (move == 0) return t;
+    Masks a = masks_of(move);
+    int n = __popc(a.g1) + __popc(a.g2) + __popc(a.g3) + __popc(a.g4);
+    if (a.g4) { t.val = __ffs(a.g4) - 1; t.cat = (n == 4) ? 4 : (n == 6 ? 13 : 14); }
+    else if (a.g3) {
+        int k = __popc(a.g3); t.val = __ffs(a.g3) - 1; t.len = k;
+        if (n == 3 * k) t.cat = (k == 1) ? 3 : 9;
+        else if (n == 4 * k) t.cat = (k == 1) ? 5 : 10;
+        else t.cat = (k == 1) ? 6 : 11;
+    } else if (a.g2) {
+        int k = __popc(a.g2); t.val = __ffs(a.g2) - 1; t.len = k; t.cat = (k == 1) ? 2 : 8;
+    } else {
+        t.val = __ffs(a.g1) - 1;
+        if (n == 1) t.cat = 1;
+        else if (n == 2) t.cat = 12;
+        else { t.cat = 7; t.len = n; }
+    }
+    return t;
+}
+
+// the trick the player to move must beat: previous player's hand-out, else the one before (envi.py:103-110)
+DDZ_DEV uint64_t last_move(uint64_t rec_prev, uint64_t rec_prevprev) { return rec_prev ? rec_prev : rec_prevprev; }
+
+// C(n, k) for n <= 15, k <= 5 (kicker choices)
+__constant__ uint16_t kBinom[16][6] = {
+    {1, 0, 0, 0, 0, 0},      {1, 1, 0, 0, 0, 0},       {1, 2, 1, 0, 0, 0},        {1, 3, 3, 1, 0, 0},
+    {1, 4, 6, 4, 1, 0},      {1, 5, 10, 10, 5, 1},     {1, 6, 15, 20, 15, 6},     {1, 7, 21, 35, 35, 21},
+    {1, 8, 28, 56, 70, 56},  {1, 9, 36, 84, 126, 126}, {1, 10, 45, 120, 210, 252}, {1, 11, 55, 165, 330, 462},
+    {1, 12, 66, 220, 495, 792}, {1, 13, 78, 286, 715, 1287}, {1, 14, 91, 364, 1001, 2002},
+    {1, 15, 105, 455, 1365, 3003}};
+DDZ_DEV int binom(int n, int k) { return (n < 0 || k > n) ? 0 : (int)kBinom[n][k]; }
+
+// Which categories may be played on `t`, and from which main rank (CardGroup.bigger_than, card.py:307-325):
+// lead: everything but pass.  follow: pass, same category with same len and higher value, any bomb (a higher
+// one on a bomb), the rocket; nothing but pass on a rocket.
+struct Rule {
+    bool lead; int cat, len, val;
+    DDZ_DEV bool allowed(int c) const { return lead || (cat != 12 && (c == cat || c == 4 || c == 12)); }
+    DDZ_DEV uint32_t from(int c) const { return (!lead && c == cat) ? above(val + 1) : 0xFFFFFFFFu; }
+    DDZ_DEV bool len_ok(int c, int L) const { return lead || c != cat || L == len; }
+};
+DDZ_DEV Rule rule_of(uint64_t last) {
+    Trick t = classify(last);
+    Rule r; r.lead = (last == 0); r.cat = t.cat; r.len = t.len; r.val = t.val;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// number of legal moves, closed form (popc x binomial); must equal what enumerate() emits
+// ------------------------------------------------------------------------------------------------
+template <int LMIN, int LMAX>
+DDZ_DEV int count_lines(uint32_t src, const Rule& ru, int cat) {
+    uint32_t R = src & kLineMask, t = R, from = ru.from(cat);
+    int n = 0;
+#pragma unroll
+    for (int L = 2; L <= LMAX; L++) {
+        t &= R >> (L - 1);
+        if (L >= LMIN && ru.len_ok(cat, L)) n += __popc(t & from);
+    }
+    return n;
+}
+template <int LMAX>
+DDZ_DEV int count_planes(uint32_t g3, int nkick, const Rule& ru, int cat) {
+    uint32_t R = g3 & kLineMask, t = R, from = ru.from(cat);
+    int n = 0;
+#pragma unroll
+    for (int L = 2; L <= LMAX; L++) {
+        t &= R >> (L - 1);
+        if (ru.len_ok(cat, L)) n += __popc(t & from) * binom(nkick - L, L);
+    }
+    return n;
+}
+DDZ_DEV int count_legal(const Masks& m, uint64_t last) {
+    if (m.g1 == 0) return last ? 1 : 0;  // empty hand (finished env): pass only / nothing
+    Rule ru = rule_of(last);
+    int n = ru.lead ? 0 : 1;             // pass
+    int n1 = __popc(m.g1), n2 = __popc(m.g2);
+    if (ru.allowed(1)) n += __popc(m.g1 & ru.from(1));
+    if (ru.allowed(2)) n += __popc(m.g2 & ru.from(2));
+    if (ru.allowed(3)) n += __popc(m.g3 & ru.from(3));
+    if (ru.allowed(4)) n += __popc(m.g4 & ru.from(4));
+    if (ru.allowed(5)) n += __popc(m.g3 & ru.from(5)) * (n1 - 1);
+    if (ru.allowed(6)) n += __popc(m.g3 & ru.from(6)) * (n2 - 1);
+    if (ru.allowed(7)) n += count_lines<5, 12>(m.g1, ru, 7);
+    if (ru.allowed(8)) n += count_lines<3, 10>(m.g2, ru, 8);
+    if (ru.allowed(9)) n += count_lines<2, 6>(m.g3, ru, 9);
+    if (ru.allowed(10)) n += count_planes<5>(m.g3, n1, ru, 10);
+    if (ru.allowed(11)) n += count_planes<4>(m.g3, n2, ru, 11);
+    if (ru.allowed(12)) n += ((m.g1 & kRocket) == kRocket);
+    if (ru.allowed(13)) n += __popc(m.g4 & ru.from(13)) * binom(n1 - 1, 2);
+    if (ru.allowed(14)) n += __popc(m.g4 & ru.from(14)) * binom(n2 - 1, 2);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// enumeration in canonical order; f(packed_move) is called once per legal move
+// ------------------------------------------------------------------------------------------------
+// lexicographic successor of the k-subset c of S (the order itertools.combinations yields, card.py:115);
+// returns 0 when c was the last one
+DDZ_DEV uint32_t next_combo(uint32_t c, uint32_t S) {
+    uint32_t U = S & ~c;
+    if (U == 0) return 0;
+    int pu = 31 - __clz(U);
+    uint32_t top = ~((2u << pu) - 1u);
+    uint32_t rest = c & ~top;
+    if (rest == 0) return 0;
+    int j = __popc(c & top);
+    int q = 31 - __clz(rest);
+    uint32_t up = S & ~((2u << q) - 1u);
+    uint32_t nb = up & (0u - up);
+    uint32_t out = (rest & ~(1u << q)) | nb;
+    uint32_t rem = up & ~nb;
+    for (int i = 0; i < j; i++) { out |= rem & (0u - rem); rem &= rem - 1; }
+    return out;
+}
+DDZ_DEV uint32_t first_combo(uint32_t S, int k) {
+    uint32_t c = 0;
+    for (int i = 0; i < k; i++) { c |= S & (0u - S); S &= S - 1; }
+    return c;
+}
+template <class F>
+DDZ_DEV void each_kicker_set(uint32_t main, uint32_t mult, uint32_t S, int k, uint32_t kmult, F& f) {
+    if (__popc(S) < k) return;
+    uint64_t base = pack_move(main, mult, 0, 0);
+    for (uint32_t c = first_combo(S, k); c; c = next_combo(c, S)) f(base + pack_move(c, kmult, 0, 0));
+}
+template <int MULT, class F>
+DDZ_DEV void each_rank(uint32_t mask, F& f) {
+    while (mask) { uint32_t b = mask & (0u - mask); mask ^= b; f(pack_move(b, MULT, 0, 0)); }
+}
+template <int MULT, int LMIN, int LMAX, class F>
+DDZ_DEV void each_line(uint32_t src, const Rule& ru, int cat, F& f) {
+    uint32_t R = src & kLineMask;
+    // starts of runs of at least LMIN
+    uint32_t t = R;
+#pragma unroll
+    for (int L = 2; L <= LMIN; L++) t &= R >> (L - 1);
+    t &= ru.from(cat);
+    while (t) {
+        int s = __ffs(t) - 1; t &= t - 1;
+        uint32_t run = ((1u << LMIN) - 1u) << s;
+        for (int L = LMIN; L <= LMAX; L++) {
+            if ((R & run) != run) break;
+            if (ru.len_ok(cat, L)) f(pack_move(run, MULT, 0, 0));
+            run |= run << 1;
+        }
+    }
+}
+template <int LMAX, int KMULT, class F>
+DDZ_DEV void each_plane(uint32_t g3, uint32_t kicksrc, const Rule& ru, int cat, F& f) {
+    uint32_t R = g3 & kLineMask;
+    uint32_t t = R & (R >> 1) & ru.from(cat);
+    while (t) {
+        int s = __ffs(t) - 1; t &= t - 1;
+        uint32_t run = 3u << s;
+        for (int L = 2; L <= LMAX; L++) {
+            if ((R & run) != run) break;
+            if (ru.len_ok(cat, L)) each_kicker_set(run, 3, kicksrc & ~run, L, KMULT, f);
+            run |= run << 1;
+        }
+    }
+}
+template <class F>
+DDZ_DEV void enumerate_legal(const Masks& m, uint64_t last, F& f) {
+    if (m.g1 == 0) { if (last) f(0ull); return; }
+    Rule ru = rule_of(last);
+    if (!ru.lead) f(0ull);
+    if (ru.allowed(1)) each_rank<1>(m.g1 & ru.from(1), f);
+    if (ru.allowed(2)) each_rank<2>(m.g2 & ru.from(2), f);
+    if (ru.allowed(3)) each_rank<3>(m.g3 & ru.from(3), f);
+    if (ru.allowed(4)) each_rank<4>(m.g4 & ru.from(4), f);
+    if (ru.allowed(5)) {
+        uint32_t mains = m.g3 & ru.from(5);
+        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 3, m.g1 & ~b, 1, 1, f); }
+    }
+    if (ru.allowed(6)) {
+        uint32_t mains = m.g3 & ru.from(6);
+        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 3, m.g2 & ~b, 1, 2, f); }
+    }
+    if (ru.allowed(7)) each_line<1, 5, 12>(m.g1, ru, 7, f);
+    if (ru.allowed(8)) each_line<2, 3, 10>(m.g2, ru, 8, f);
+    if (ru.allowed(9)) each_line<3, 2, 6>(m.g3, ru, 9, f);
+    if (ru.allowed(10)) each_plane<5, 1>(m.g3, m.g1, ru, 10, f);
+    if (ru.allowed(11)) each_plane<4, 2>(m.g3, m.g2, ru, 11, f);
+    if (ru.allowed(12) && (m.g1 & kRocket) == kRocket) f(pack_move(kRocket, 1, 0, 0));
+    if (ru.allowed(13)) {
+        uint32_t mains = m.g4 & ru.from(13);
+        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 4, m.g1 & ~b, 2, 1, f); }
+    }
+    if (ru.allowed(14)) {
+        uint32_t mains = m.g4 & ru.from(14);
+        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 4, m.g2 & ~b, 2, 2, f); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter (env_lo, env_hi, step, 0), key (seed_lo, seed_hi): the action-index stream
+// ------------------------------------------------------------------------------------------------
+DDZ_DEV uint32_t philox(uint64_t seed, uint64_t env, uint32_t step) {
+    uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32), c2 = step, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-env state in registers
+// ------------------------------------------------------------------------------------------------
+struct Env {
+    uint64_t hand[3], hist[3], recent[3];
+    uint32_t meta;
+    DDZ_DEV int cur() const { return meta & 3; }
+    DDZ_DEV bool done() const { return (meta >> 2) & 1; }
+};
+struct StateView {  // SoA arrays inside the caller's state buffer
+    uint64_t* f;    // [9][B]
+    uint32_t* meta; // [B]
+    int B;
+};
+DDZ_DEV StateView view_of(void* state, int B) {
+    StateView v; v.f = (uint64_t*)state; v.meta = (uint32_t*)(v.f + 9 * (size_t)B); v.B = B;
+    return v;
+}
+DDZ_DEV Env load_env(const StateView& v, int b) {
+    Env e;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        e.hand[q] = v.f[(size_t)q * v.B + b];
+        e.hist[q] = v.f[(size_t)(3 + q) * v.B + b];
+        e.recent[q] = v.f[(size_t)(6 + q) * v.B + b];
+    }
+    e.meta = v.meta[b];
+    return e;
+}
+DDZ_DEV void store_env(const StateView& v, int b, const Env& e) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        v.f[(size_t)q * v.B + b] = e.hand[q];
+        v.f[(size_t)(3 + q) * v.B + b] = e.hist[q];
+        v.f[(size_t)(6 + q) * v.B + b] = e.recent[q];
+    }
+    v.meta[b] = e.meta;
+}
+template <class T>
+DDZ_DEV T pick3(int i, T a, T b, T c) { return i == 0 ? a : (i == 1 ? b : c); }
+
+DDZ_DEV uint64_t hand_to_move(const Env& e) { int s = e.cur(); return pick3(s, e.hand[0], e.hand[1], e.hand[2]); }
+DDZ_DEV uint64_t trick_of(const Env& e) {
+    int s = e.cur();
+    uint64_t p1 = pick3((s + 2) % 3, e.recent[0], e.recent[1], e.recent[2]);
+    uint64_t p2 = pick3((s + 1) % 3, e.recent[0], e.recent[1], e.recent[2]);
+    return last_move(p1, p2);
+}
+
+// deal: returns false when perm is not a permutation of 0..53 or lord_pile is out of range
+DDZ_DEV bool deal(Env& e, const int8_t* __restrict__ perm, int lord_pile) {
+    uint64_t pile[4] = {0, 0, 0, 0}, seen = 0;
+    bool ok = (lord_pile >= 0 && lord_pile <= 2);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int n = (p < 3) ? 17 : 3;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            int id = perm[17 * p + i];
+            ok = ok && (id >= 0 && id < 54);
+            id = (id < 0) ? 0 : (id > 53 ? 53 : id);
+            seen |= 1ull << id;
+            int rank = id < 52 ? (id >> 2) : id - 39;
+            pile[p] += 1ull << (4 * rank);
+        }
+    }
+    ok = ok && (seen == (1ull << 54) - 1);
+    if (!ok) return false;
+    int lp = lord_pile;
+    e.hand[1] = pick3(lp, pile[0], pile[1], pile[2]) + pile[3];
+    e.hand[2] = pick3((lp + 1) % 3, pile[0], pile[1], pile[2]);
+    e.hand[0] = pick3((lp + 2) % 3, pile[0], pile[1], pile[2]);
+#pragma unroll
+    for (int q = 0; q < 3; q++) { e.hist[q] = 0; e.recent[q] = 0; }
+    uint32_t games = (e.meta >> 8) + 1;
+    e.meta = 1u | (e.meta & 0x20u) | (games << 8);  // lord to move, not done, keep sticky error
+    return true;
+}
+
+struct StepOut { int r, done, cat; float reward[3]; bool applied, pass; int winner; };
+
+// envi.py:38-43 _update + native step_manual: remove cards, record, terminal, rotate
+DDZ_DEV StepOut apply_move(Env& e, uint64_t move, const int32_t* rewards) {
+    StepOut o; o.r = 0; o.cat = classify(move).cat; o.applied = true; o.pass = (move == 0); o.winner = -1;
+    o.reward[0] = o.reward[1] = o.reward[2] = 0.f;
+    int s = e.cur();
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+        if (q == s) { e.hand[q] -= move; e.hist[q] += move; e.recent[q] = move; }
+    uint64_t h = pick3(s, e.hand[0], e.hand[1], e.hand[2]);
+    uint32_t meta = e.meta;
+    if (move != 0 && h == 0) {
+        meta |= 4u | ((uint32_t)s << 3);
+        o.r = (s == 1) ? -1 : 1; o.winner = s;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            bool win = (s == 1) ? (q == 1) : (q != 1);
+            o.reward[q] = win ? (float)rewards[q] : -(float)rewards[q];
+        }
+    }
+    meta = (meta & ~3u) | (uint32_t)((s + 1) % 3);
+    e.meta = meta;
+    o.done = (meta >> 2) & 1;
+    return o;
+}
+
+}  // namespace ddz

@@ -1,0 +1,475 @@
+"""Batched, GPU-resident Doudizhu env with the reference's Python env API.
+
+Mirrors reference envi.py:16-217 (classes Env / EnvComplicated / EnvCooperation / EnvCooperationSimplify):
+same verbs (reset, prepare, face, valid_actions, step_manual, step_random, step_auto), same tensor layouts
+(face float32 [C,15,4], actions float32 [N,15,4] thermometer one-hot), over a leading batch of B envs.
+`BatchedEnv*` are the batched classes; `Env*` are B=1 views with the exact single-env signatures so the
+reference's game.py / dqn.py / net.py loop runs on them unchanged.
+
+All arithmetic happens in hand-written sm_100a kernels behind the C-ABI of include/ddz_b200.h; PyTorch only
+owns the buffers and the stream.  There is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _native as N
+
+VARIANT_CHANNELS = (4, 7, 9, 6)
+DEFAULT_REWARDS = (50, 100, 50)          # role 0 up, 1 lord, 2 down  (reference game.py:13-14)
+DEAL_SEED0 = 20260101                    # default deal stream: PCG64(DEAL_SEED0 + game).permutation(54)
+_SHIFTS = None
+
+
+def _shifts(device):
+    return (torch.arange(15, device=device, dtype=torch.int64) * 4)
+
+
+def default_deals(first_game, n):
+    """The documented default shuffle stream: game g -> PCG64(20260101+g).permutation(54), lord_pile 0."""
+    perm = np.stack([np.random.Generator(np.random.PCG64(DEAL_SEED0 + first_game + i)).permutation(54)
+                     for i in range(n)]).astype(np.int8)
+    return perm, np.zeros(n, np.int8)
+
+
+def random_deals(n, seed, pool_games=1):
+    """Vectorised synthetic deals for large batches: int8 [pool_games*n, 54] permutations, random landlord pile."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    perm = rng.permuted(np.tile(np.arange(54, dtype=np.int8), (pool_games * n, 1)), axis=1)
+    lord = rng.integers(0, 3, size=pool_games * n, dtype=np.int8)
+    return perm, lord
+
+
+def pack_counts(counts):
+    """int [...,15] per-rank counts -> int64 packed nibbles (the library's uint64 move/hand format)."""
+    c = torch.as_tensor(counts)
+    return (c.to(torch.int64) << _shifts(c.device)).sum(-1)
+
+
+def unpack_counts(packed):
+    """int64 packed nibbles [...] -> int64 [...,15] per-rank counts."""
+    p = torch.as_tensor(packed)
+    return (p.unsqueeze(-1) >> _shifts(p.device)) & 15
+
+
+class BatchedEnv:
+    """B independent Doudizhu games on one GPU.  Reference: envi.py:16-157 (class Env, C=4 face)."""
+
+    VARIANT = N.FACE_FIRST
+
+    def __init__(self, num_envs=1, debug=False, seed=None, device=None, max_actions_per_env=None,
+                 rewards=DEFAULT_REWARDS, env0=0):
+        if not torch.cuda.is_available():
+            raise N.DdzError("BatchedEnv needs a CUDA device: the env runs as sm_100a kernels, there is no CPU path")
+        self.B = int(num_envs)
+        if self.B <= 0:
+            raise ValueError("num_envs must be positive")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.debug = debug
+        self.seed = int(seed) if seed else 0          # `if seed:` like envi.py:18 (seed=0 == unseeded)
+        self.env0 = int(env0)                          # global id of env 0 (multi-GPU sharding)
+        self.C = VARIANT_CHANNELS[self.VARIANT]
+        per_env = int(max_actions_per_env) if max_actions_per_env else N.MAX_LEGAL
+        self.cap = self.B * per_env
+        dev, B = self.device, self.B
+        with torch.cuda.device(dev):
+            self._state = torch.zeros(N.lib.ddz_state_bytes(B) // 4, dtype=torch.int32, device=dev)
+            self._ws = torch.zeros(max(1, N.lib.ddz_workspace_bytes(B) // 4), dtype=torch.int32, device=dev)
+            self._offsets = [torch.zeros(B + 1, dtype=torch.int32, device=dev) for _ in range(2)]
+            self._actions_u64 = [torch.zeros(self.cap, dtype=torch.int64, device=dev) for _ in range(2)]
+            self._actions_f32 = torch.empty((self.cap, 15, 4), dtype=torch.float32, device=dev)
+            self._face = torch.empty((B, self.C, 15, 4), dtype=torch.float32, device=dev)
+            self.r = torch.zeros(B, dtype=torch.int8, device=dev)
+            self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
+            self.cat = torch.zeros(B, dtype=torch.int8, device=dev)
+            self.reward = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+            self.stats = torch.zeros(16, dtype=torch.int64, device=dev)
+            self._rewards = torch.tensor(list(rewards), dtype=torch.int32, device="cpu")
+        self._cur = 0            # which ping-pong list describes the current state
+        self._fresh = False      # lists/face valid for the current state?
+        self._n_total = None
+        self._stepno = 0
+        self._games_dealt = 0
+        self._perm_dev = None
+        self._lord_dev = None
+        self.reset()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def _fields(self):
+        """int64 view [9,B] (hand[3], hist[3], recent[3]) and int32 meta [B] of the state buffer."""
+        B = self.B
+        f = self._state[: 18 * B].view(torch.int64).view(9, B)
+        meta = self._state[18 * B: 19 * B]
+        return f, meta
+
+    def _to_dev(self, a, dtype):
+        if a is None:
+            return None
+        t = torch.as_tensor(a)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self):
+        """envi.py:30-36 + CEnv.reset: clear the table (hands are empty until prepare())."""
+        self._state.zero_()
+        f, meta = self._fields()
+        meta.fill_(1)            # lord to move, not done, no deals consumed
+        self._fresh = False
+        self._stepno = 0
+
+    def prepare(self, perm=None, lord_pile=None, only_done=False, pool_games=1):
+        """CEnv.prepare (game.py:171): deal.  perm int8 [pool_games*B,54] host or device, lord_pile int8 [pool_games*B].
+        Without perm the documented default stream is used (default_deals)."""
+        B = self.B
+        if perm is None:
+            perm, lord_pile = default_deals(self._games_dealt, B)
+            pool_games = 1
+        perm_d = self._to_dev(perm, torch.int8)
+        if perm_d.numel() != pool_games * B * 54:
+            raise ValueError("perm must have shape [pool_games*B, 54]")
+        lord_d = self._to_dev(lord_pile, torch.int8)
+        if lord_d is not None and lord_d.numel() != pool_games * B:
+            raise ValueError("lord_pile must have shape [pool_games*B]")
+        self._perm_dev, self._lord_dev = perm_d, lord_d      # keep alive while the launch is in flight
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_reset(self._p(self._state), self._p(perm_d), self._p(lord_d), int(pool_games),
+                                    int(bool(only_done)), self._p(self.stats), B, self._stream()), "ddz_reset")
+        self._games_dealt += B
+        self._fresh = False
+        self._check_errors("prepare")
+
+    def observe(self):
+        """Run legal-move generation + encoders for the current state (the work behind env.face and
+        env.valid_actions(), envi.py:87-116)."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_observe(self._p(self._state), self._p(self._ws), self.VARIANT,
+                                      self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]),
+                                      self._p(self._actions_f32), self.cap, self._p(self._face),
+                                      self._p(self.stats), self.B, self._stream()), "ddz_observe")
+        self._fresh, self._n_total = True, None
+        return self
+
+    def _ensure(self):
+        if not self._fresh:
+            self.observe()
+
+    @property
+    def offsets(self):
+        self._ensure()
+        return self._offsets[self._cur]
+
+    @property
+    def num_actions(self):
+        """total number of legal moves over the batch (host int; synchronises)."""
+        self._ensure()
+        if self._n_total is None:
+            self._n_total = int(self._offsets[self._cur][self.B].item())
+            if self._n_total > self.cap:
+                raise N.DdzError("legal-move lists overflowed the action buffer (%d > cap %d)" % (self._n_total, self.cap))
+        return self._n_total
+
+    @property
+    def face(self):
+        """float32 [B,C,15,4] on the GPU (envi.py:87-96)."""
+        self._ensure()
+        return self._face
+
+    @property
+    def actions_packed(self):
+        self._ensure()
+        return self._actions_u64[self._cur][: self.num_actions]
+
+    def valid_actions(self, tensor=True):
+        """tensor=True: (float32 [sumN,15,4], int32 offsets [B+1]); False: per-env lists of 15-int lists (envi.py:98-116)."""
+        self._ensure()
+        n = self.num_actions
+        if tensor:
+            return self._actions_f32[:n], self._offsets[self._cur]
+        counts = unpack_counts(self._actions_u64[self._cur][:n]).cpu().numpy()
+        off = self._offsets[self._cur].cpu().numpy()
+        return [[[int(x) for x in row] for row in counts[off[b]:off[b + 1]]] for b in range(self.B)]
+
+    def _step(self, choice, mode):
+        self._ensure()
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_step(self._p(self._state), self._p(self._offsets[self._cur]),
+                                   self._p(self._actions_u64[self._cur]), self._p(choice), mode,
+                                   self.seed, self.env0, self._stepno, self._rewards.data_ptr(),
+                                   self._p(self.r), self._p(self.done), self._p(self.cat), self._p(self.reward),
+                                   self._p(self.stats), self.B, self._stream()), "ddz_step")
+        self._fresh = False
+        self._stepno += 1
+        self._check_errors("step")
+        return self.r, self.done, self.cat
+
+    def step(self, choice):
+        """apply legal move number choice[b] of every env (the index stream of the parity contract)."""
+        return self._step(self._to_dev(choice, torch.int32), N.CHOICE_INDEX)
+
+    def step_manual(self, onehot_cards):
+        """envi.py:63-70: onehot float/int [B,15,4] (a row of valid_actions per env) -> (r, done, cat)."""
+        oh = torch.as_tensor(onehot_cards, device=self.device)
+        moves = pack_counts(oh.reshape(self.B, 15, 4).sum(-1).round().to(torch.int64)).contiguous()
+        return self._step(moves, N.CHOICE_MOVE)
+
+    def step_random(self, entropy=None):
+        """envi.py:79-85: uniform random legal move.  entropy uint32/int32 [B] -> index = entropy % N (host-supplied
+        stream); None -> device Philox4x32-10 keyed (seed, env0+b, step number)."""
+        if entropy is None:
+            return self._step(None, N.CHOICE_PHILOX)
+        return self._step(self._to_dev(np.asarray(entropy).view(np.int32) if isinstance(entropy, np.ndarray)
+                                       else entropy, torch.int32), N.CHOICE_MOD)
+
+    def step_auto(self):
+        """envi.py:72-77: RHCP heuristic opponent -- out of scope for this build."""
+        raise NotImplementedError("step_auto (RHCP rule AI of the absent native env) is not part of the hot path")
+
+    def rollout_step(self, choice=None, mode=N.CHOICE_PHILOX, perm=None, lord_pile=None, pool_games=1, mid_event=None):
+        """One fused env-step: apply the chosen move, re-deal finished envs from perm (device int8 [pool*B,54]) when
+        given, and produce face + legal lists of the new state.  Two launches (ddz_rollout_step); mid_event, a
+        torch.cuda.Event, is recorded between them (bench.py times the dominant kernel with it)."""
+        self._ensure()
+        nxt = 1 - self._cur
+        if choice is not None:
+            choice = self._to_dev(choice, torch.int64 if mode == N.CHOICE_MOVE else torch.int32)
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            step_args = (self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]),
+                         self._p(choice), mode, self.seed, self.env0, self._stepno, self._rewards.data_ptr(),
+                         self._p(perm), self._p(lord_pile), int(pool_games),
+                         self._p(self.r), self._p(self.done), self._p(self.cat), self._p(self.reward))
+            emit_args = (self._p(self._offsets[nxt]), self._p(self._actions_u64[nxt]), self._p(self._actions_f32),
+                         self.cap, self._p(self._face), self._p(self.stats), self.B, st)
+            if mid_event is None:
+                N.check(N.lib.ddz_rollout_step(self._p(self._state), self._p(self._ws), self.VARIANT, *step_args,
+                                               *emit_args), "ddz_rollout_step")
+            else:
+                N.check(N.lib.ddz_rollout_step_begin(self._p(self._state), self._p(self._ws), *step_args,
+                                                     self._p(self.stats), self.B, st), "ddz_rollout_step_begin")
+                mid_event.record(torch.cuda.current_stream(self.device))
+                N.check(N.lib.ddz_rollout_step_end(self._p(self._state), self._p(self._ws), self.VARIANT, *emit_args),
+                        "ddz_rollout_step_end")
+        self._cur, self._fresh, self._n_total = nxt, True, None
+        self._stepno += 1
+        return self.r, self.done, self.cat
+
+    def _check_errors(self, what):
+        if self.debug:
+            err = int(self.stats[7].item())
+            if err:
+                raise N.DdzError("%s: %d env(s) flagged an error (illegal choice, bad permutation or list overflow)" % (what, err))
+
+    # ------------------------------------------------------------------ getters (native env getters, App. A)
+    def get_role_ID(self):
+        """1 = up, 2 = lord, 3 = down (envi.py:64) -> int64 [B]"""
+        return (self._fields()[1] & 3).to(torch.int64) + 1
+
+    def _role(self):
+        return (self._fields()[1] & 3).to(torch.int64)
+
+    def hands(self):
+        """int64 [B,3,15] counts of every role's hand."""
+        return unpack_counts(self._fields()[0][0:3].t().contiguous())
+
+    def get_curr_handcards(self):
+        """counts int64 [B,15] of the player to move (the reference returns card values 3..17; see Env view)."""
+        h = self.hands()
+        return h[torch.arange(self.B, device=self.device), self._role()]
+
+    def get_last_two_cards(self):
+        """int64 [B,2,15]: [previous player's hand-out, the one before]; zeros = pass (envi.py:103)."""
+        rec = self.recent_handout
+        s = self._role()
+        ar = torch.arange(self.B, device=self.device)
+        return torch.stack([rec[ar, (s + 2) % 3], rec[ar, (s + 1) % 3]], 1)
+
+    @property
+    def left(self):
+        """cards left per role int64 [B,3] (envi.py:23,39)."""
+        return self.hands().sum(-1)
+
+    @property
+    def history(self):
+        """int64 [B,3,15] (envi.py:25,41)."""
+        return unpack_counts(self._fields()[0][3:6].t().contiguous())
+
+    @property
+    def taken(self):
+        """int64 [B,15] (envi.py:22,40)."""
+        return self.history.sum(1)
+
+    @property
+    def recent_handout(self):
+        """int64 [B,3,15] (envi.py:26,42-43)."""
+        return unpack_counts(self._fields()[0][6:9].t().contiguous())
+
+    @property
+    def is_done(self):
+        return ((self._fields()[1] >> 2) & 1).to(torch.bool)
+
+    @property
+    def winner(self):
+        return ((self._fields()[1] >> 3) & 3).to(torch.int64)
+
+    def state_dict(self):
+        """Exact-resume checkpoint of the env (the reference never checkpoints env state)."""
+        return {"state": self._state.clone(), "stepno": self._stepno, "games_dealt": self._games_dealt,
+                "stats": self.stats.clone()}
+
+    def load_state_dict(self, sd):
+        self._state.copy_(sd["state"])
+        self.stats.copy_(sd["stats"])
+        self._stepno, self._games_dealt = int(sd["stepno"]), int(sd["games_dealt"])
+        self._fresh = False
+
+    # ------------------------------------------------------------------ converters (envi.py:118-157)
+    @classmethod
+    def arr2cards(cls, arr):
+        """counts[15] -> card values 3..17, ascending (envi.py:119-130)"""
+        arr = np.asarray(arr).astype(np.int64).reshape(15)
+        return np.repeat(np.arange(3, 18), arr)
+
+    @classmethod
+    def cards2arr(cls, cards):
+        """card values 3..17 -> counts[15] (envi.py:133-137)"""
+        cards = np.asarray(cards, dtype=np.int64).reshape(-1)
+        return np.bincount(cards - 3, minlength=15).astype(np.int64) if cards.size else np.zeros(15, np.int64)
+
+    @classmethod
+    def batch_arr2onehot(cls, batch_arr):
+        """counts [n,15] -> thermometer one-hot int [n,15,4]: res[i][rank][:count] = 1 (envi.py:140-146)"""
+        a = np.asarray(batch_arr).astype(np.int64).reshape(-1, 15)
+        return (np.arange(4)[None, None, :] < a[:, :, None]).astype(np.int64)
+
+    @classmethod
+    def onehot2arr(cls, onehot_cards):
+        """one-hot [15,4] -> counts[15] (row sums, envi.py:149-157)"""
+        if torch.is_tensor(onehot_cards):
+            onehot_cards = onehot_cards.detach().cpu().numpy()
+        return np.asarray(onehot_cards).reshape(15, 4).sum(-1).round().astype(np.int64)
+
+    @staticmethod
+    def encode_actions(packed):
+        """packed moves int64 [n] on the GPU -> float32 [n,15,4] (envi.py:113)."""
+        packed = packed.contiguous()
+        out = torch.empty((packed.numel(), 15, 4), dtype=torch.float32, device=packed.device)
+        with torch.cuda.device(packed.device):
+            N.check(N.lib.ddz_encode_actions(packed.data_ptr(), packed.numel(), out.data_ptr(),
+                                             torch.cuda.current_stream(packed.device).cuda_stream), "ddz_encode_actions")
+        return out
+
+
+class BatchedEnvComplicated(BatchedEnv):
+    """envi.py:160-178, C=7"""
+    VARIANT = N.FACE_COMPLICATED
+
+
+class BatchedEnvCooperation(BatchedEnv):
+    """envi.py:181-198, C=9"""
+    VARIANT = N.FACE_COOPERATION
+
+
+class BatchedEnvCooperationSimplify(BatchedEnv):
+    """envi.py:201-217, C=6"""
+    VARIANT = N.FACE_SIMPLIFY
+
+
+def get_moves(hands, lasts, device=None):
+    """Batched r.get_moves(hand15, last15) (envi.py:111): hands/lasts int [n,15] -> (packed int64 [sumN], offsets int32 [n+1])."""
+    if not torch.cuda.is_available():
+        raise N.DdzError("get_moves needs a CUDA device")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    h = pack_counts(torch.as_tensor(np.asarray(hands)).reshape(-1, 15).to(dev)).contiguous()
+    l = pack_counts(torch.as_tensor(np.asarray(lasts)).reshape(-1, 15).to(dev)).contiguous()
+    n = h.numel()
+    ws = torch.zeros(max(1, N.lib.ddz_workspace_bytes(n) // 4), dtype=torch.int32, device=dev)
+    offsets = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    cap = n * N.MAX_LEGAL
+    out = torch.zeros(cap, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ddz_legal_moves(h.data_ptr(), l.data_ptr(), ws.data_ptr(), offsets.data_ptr(), out.data_ptr(),
+                                      cap, None, n, torch.cuda.current_stream(dev).cuda_stream), "ddz_legal_moves")
+    return out[: int(offsets[n].item())], offsets
+
+
+# ---------------------------------------------------------------------- B = 1 views (exact reference signatures)
+class _RoleDict:
+    """history / recent_handout of the reference are dicts role -> float array[15] (envi.py:25-26)."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def __getitem__(self, role):
+        return self._fn()[0, int(role)].cpu().numpy().astype(np.float64)
+
+
+class Env(BatchedEnv):
+    """Single-env drop-in for reference envi.Env: same attribute names, shapes and return types."""
+
+    def __init__(self, debug=False, seed=None, device=None):
+        super().__init__(1, debug=debug, seed=seed, device=device)
+
+    @property
+    def face(self):
+        return BatchedEnv.face.fget(self)[0]
+
+    def valid_actions(self, tensor=True):
+        if tensor:
+            return super().valid_actions(True)[0]
+        return super().valid_actions(False)[0]
+
+    def step_manual(self, onehot_cards):
+        r, done, cat = super().step_manual(torch.as_tensor(onehot_cards, device=self.device).reshape(1, 15, 4))
+        return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
+
+    def step_random(self, entropy=None):
+        if entropy is not None:
+            entropy = np.asarray([entropy], dtype=np.uint32)
+        r, done, cat = super().step_random(entropy)
+        return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
+
+    def get_role_ID(self):
+        return int(super().get_role_ID()[0].item())
+
+    def get_curr_handcards(self):
+        return self.arr2cards(super().get_curr_handcards()[0].cpu().numpy())
+
+    def get_last_two_cards(self):
+        two = super().get_last_two_cards()[0].cpu().numpy()
+        return [list(self.arr2cards(two[0])), list(self.arr2cards(two[1]))]
+
+    @property
+    def left(self):
+        return BatchedEnv.left.fget(self)[0].cpu().numpy()
+
+    @property
+    def taken(self):
+        return BatchedEnv.taken.fget(self)[0].cpu().numpy().astype(np.float64)
+
+    @property
+    def history(self):
+        return _RoleDict(lambda: BatchedEnv.history.fget(self))
+
+    @property
+    def recent_handout(self):
+        return _RoleDict(lambda: BatchedEnv.recent_handout.fget(self))
+
+
+class EnvComplicated(Env):
+    VARIANT = N.FACE_COMPLICATED
+
+
+class EnvCooperation(Env):
+    VARIANT = N.FACE_COOPERATION
+
+
+class EnvCooperationSimplify(Env):
+    VARIANT = N.FACE_SIMPLIFY

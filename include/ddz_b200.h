@@ -1,0 +1,129 @@
+/*
+ * ddz_b200.h -- C-ABI of the B200-native batched Doudizhu environment (libddz_b200.so).
+ *
+ * This is the drop-in boundary for the rollout path of charleschen003/doudizhu-rl.  It replaces the two
+ * pre-compiled native modules the reference loads from precompiled/ (reference envi.py:10-13):
+ *   `env`  (class env.Env: reset / prepare / step_manual / get_* / get_state_prob)   and
+ *   `r`    (r.get_moves(hand15, last15))
+ * plus the per-decision Python loops of envi.py that sit directly on them (face, valid_actions,
+ * batch_arr2onehot, _update).  Every entry point below cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller (PyTorch) owns every buffer; the library never allocates device memory and keeps no
+ *     pointer after the call returns;
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default);
+ *   - return value: 0 ok, <0 error (DDZ_E_*); no exceptions, nothing printed;
+ *   - there is NO CPU fallback: without a CUDA device every launcher returns DDZ_E_CUDA.
+ *
+ * Data formats
+ *   counts   a hand / move / history is 15 per-rank counts, rank 0='3' ... 11='A', 12='2', 13=black joker,
+ *            14=red joker (reference config.py:16-18, envi.py:119-137), packed 4 bits per rank into a
+ *            uint64 (rank r in bits [4r, 4r+4)); a pass is 0.
+ *   state    opaque, ddz_state_bytes(B) bytes, 8-byte aligned, struct-of-arrays:
+ *            uint64 hand[3][B], hist[3][B], recent[3][B]  (role 0=up, 1=lord, 2=down, envi.py:24)
+ *            uint32 meta[B]: bits 0-1 role to move, bit 2 done, bits 3-4 winner, bit 5 sticky error,
+ *            bits 8-31 deals consumed.
+ *   legal    CSR: offsets int32[B+1], actions_u64[offsets[B]] packed counts in canonical order
+ *            (card.py action-space order, pass first when following), actions_f32[offsets[B]][15][4]
+ *            thermometer one-hot (envi.py:140-146), face float32[B][C][15][4] (envi.py:87-217).
+ *   stats    int64[16], accumulated (never cleared by the library):
+ *            0 games finished, 1 lord wins, 2 down wins, 3 up wins, 4 env-steps applied,
+ *            5 sum lord reward, 6 sum farmer reward (down+up), 7 errors, 8 legal moves emitted, 9 passes.
+ */
+#ifndef DDZ_B200_H
+#define DDZ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDZ_ABI_VERSION 1
+#define DDZ_MAX_LEGAL 512  /* upper bound of legal moves of one decision (worst known hand: 497) */
+
+#define DDZ_E_ARG -1     /* bad argument (NULL pointer, B <= 0, unknown variant/mode) */
+#define DDZ_E_CUDA -2    /* CUDA runtime error / no device */
+
+/* face variants = the reference's four Env classes */
+#define DDZ_FACE_FIRST 0          /* envi.py:87-96    Env                     C=4 */
+#define DDZ_FACE_COMPLICATED 1    /* envi.py:165-178  EnvComplicated          C=7 */
+#define DDZ_FACE_COOPERATION 2    /* envi.py:182-198  EnvCooperation          C=9 */
+#define DDZ_FACE_SIMPLIFY 3       /* envi.py:202-217  EnvCooperationSimplify  C=6 */
+
+/* how ddz_step / ddz_rollout_step pick the move of env b out of its N legal moves */
+#define DDZ_CHOICE_INDEX 0   /* choice[b] is the index (dqn.py:60,70 argmax / randint)                    */
+#define DDZ_CHOICE_MOD 1     /* (uint32)choice[b] % N  -- host-supplied entropy, envi.py:83 random.choice */
+#define DDZ_CHOICE_PHILOX 2  /* philox4x32-10(key=seed, ctr=(env0+b, stepno)) % N, no input buffer        */
+#define DDZ_CHOICE_MOVE 3    /* moves[b] is the packed move itself (envi.py:63-70 step_manual); must be legal */
+
+int ddz_abi_version(void);
+int ddz_face_channels(int variant);          /* 4 / 7 / 9 / 6, or DDZ_E_ARG */
+size_t ddz_state_bytes(int B);
+size_t ddz_workspace_bytes(int B);           /* scratch for observe / rollout_step / legal_moves (n <= B) */
+const char* ddz_last_error(void);            /* text of the last CUDA error seen by this thread */
+
+/* env.Env.reset() + prepare()  (envi.py:30-36, game.py:170-171) with host-chosen shuffles:
+ * perm int8[pool_games][B][54] card ids (0..51 -> rank id/4, 52/53 jokers), lord_pile int8[pool_games][B]
+ * (may be NULL = 0).  Env b takes row (deals_consumed % pool_games)*B + b.  only_done != 0 re-deals only
+ * finished envs.  Piles perm[0:17],[17:34],[34:51], bottom [51:54]; pile lord_pile(+bottom) -> lord,
+ * next pile -> down, next -> up; lord to move. */
+int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool_games, int only_done,
+              int64_t* stats, int B, void* stream);
+
+/* env.face + env.valid_actions() for all envs  (envi.py:87-116; r.get_moves envi.py:111;
+ * get_state_prob envi.py:94; batch_arr2onehot envi.py:140-146).
+ * offsets int32[B+1] and actions_u64[cap] are required; actions_f32 / face may be NULL (skipped).
+ * Finished envs have no legal move.  If the total exceeds cap the tail is dropped and stats[7] is bumped. */
+int ddz_observe(const void* state, void* workspace, int variant, int32_t* offsets, uint64_t* actions_u64,
+                float* actions_f32, int64_t cap, float* face, int64_t* stats, int B, void* stream);
+
+/* env.step_manual / step_random for all envs  (envi.py:63-70, 79-85, _update :38-43; terminal + sign
+ * rule_based/rule_play.py:14-28; rewards game.py:109-118 with magnitudes rewards[role]).
+ * offsets/actions_u64 must be the lists ddz_observe produced for the CURRENT state.
+ * Outputs (any may be NULL): r int8[B] (-1 lord won, +1 farmers won, 0), done uint8[B], cat int8[B]
+ * (card.py:13-28 category of the move, -1 if nothing was applied), reward float32[B][3].
+ * Finished envs and illegal choices are no-ops (illegal: sticky error bit + stats[7]). */
+int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, const void* choice,
+             int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno, const int32_t rewards[3],
+             int8_t* r, uint8_t* done, int8_t* cat, float* reward, int64_t* stats, int B, void* stream);
+
+/* One fused env-step = ddz_step, then ddz_reset(only_done=1) when perm != NULL, then ddz_observe of the
+ * new state, in two launches.  prev_* are the lists of the state being stepped, out_* receive the new
+ * lists (ping-pong; they must not alias). */
+int ddz_rollout_step(void* state, void* workspace, int variant,
+                     const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                     const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
+                     const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                     int8_t* r, uint8_t* done, int8_t* cat, float* reward,
+                     int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                     float* face, int64_t* stats, int B, void* stream);
+
+/* The two launches of ddz_rollout_step as separate calls, so a caller can record a CUDA event between them
+ * (bench.py times the dominant kernel this way).  _begin = apply move + re-deal + count; _end = offsets +
+ * move lists + encoders.  Calling _begin then _end with the same arguments IS ddz_rollout_step. */
+int ddz_rollout_step_begin(void* state, void* workspace,
+                           const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                           const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
+                           const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                           int8_t* r, uint8_t* done, int8_t* cat, float* reward, int64_t* stats, int B, void* stream);
+int ddz_rollout_step_end(const void* state, void* workspace, int variant,
+                         int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                         float* face, int64_t* stats, int B, void* stream);
+
+/* r.get_moves(hand15, last15) for n independent (hand, last) pairs  (envi.py:111, server/core.py:65):
+ * hands/lasts packed uint64[n]; last == 0 means lead.  Same CSR outputs as ddz_observe. */
+int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,
+                    uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream);
+
+/* Env.batch_arr2onehot over packed moves (envi.py:113,140-146): out float32[n][15][4] */
+int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream);
+
+/* env.face only (envi.py:87-217) */
+int ddz_encode_face(const void* state, int variant, float* face, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -9,8 +9,10 @@
  * reference has no C source at all; the rules are re-expressed from its
  * Python (rule_based/utils/card.py, envi.py, server/core.py, game.py).
  */
+#define _POSIX_C_SOURCE 200809L
 #include "ddz_oracle.h"
 #include <pthread.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,7 +57,7 @@ static void push(const int8_t c[15], int cat, int len, int val, int extra) {
  * (card.py:115,128,141,151) */
 typedef void (*combo_cb)(const int* pick, int k, void* ctx);
 static void combos(const int* pool, int n, int k, combo_cb cb, void* ctx) {
-    int idx[8], pick[8];
+    int idx[8], pick[8] = {0};
     if (k > n) return;
     for (int i = 0; i < k; i++) idx[i] = i;
     for (;;) {
@@ -520,10 +522,12 @@ void ddz_ref_batch_export(const ddz_ref_env* envs, int B, uint64_t* f, uint32_t*
 /* CPU baseline rollout                                                 */
 /* ------------------------------------------------------------------ */
 typedef struct {
-    int b0, b1, B, steps, variant, pool_games;
+    int b0, b1, B, steps, warm, variant, pool_games;
     uint64_t seed; const int8_t* perm; const int8_t* lord;
-    int64_t stats[16]; uint64_t checksum; int64_t nsteps;
+    int64_t stats[16]; uint64_t checksum; int64_t nsteps; double seconds;
+    pthread_barrier_t* bar;
 } job_t;
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static void* rollout_worker(void* arg) {
     job_t* j = (job_t*)arg;
@@ -540,7 +544,13 @@ static void* rollout_worker(void* arg) {
         size_t row = (size_t)(j->b0 + i);
         ddz_ref_env_deal(&envs[i], j->perm + 54 * row, j->lord ? j->lord[row] : 0);
     }
-    for (int t = 0; t < j->steps; t++) {
+    double t0 = 0;
+    for (int t = 0; t < j->warm + j->steps; t++) {
+        if (t == j->warm) {   /* warm-up steps bring the envs to the steady-state mix; only the rest is timed */
+            pthread_barrier_wait(j->bar);
+            t0 = now_s();
+            memset(j->stats, 0, sizeof j->stats); j->nsteps = 0;
+        }
         for (int i = 0; i < n; i++) {
             ddz_ref_env* e = &envs[i];
             int b = j->b0 + i;
@@ -561,14 +571,15 @@ static void* rollout_worker(void* arg) {
             }
         }
     }
+    j->seconds = now_s() - t0;
     j->checksum = cs;
     free(envs); free(moves); free(af); free(face);
     return 0;
 }
 
-int64_t ddz_ref_rollout(int B, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
                         const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
-                        uint64_t* checksum) {
+                        uint64_t* checksum, double* seconds) {
     ensure();
     if (nthreads < 1) nthreads = 1;
     if (nthreads > B) nthreads = B;
@@ -576,20 +587,26 @@ int64_t ddz_ref_rollout(int B, int steps, int variant, uint64_t seed, const int8
     if (ddz_ref_face_channels(variant) < 0) return -1;
     job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
     pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    pthread_barrier_t bar; pthread_barrier_init(&bar, 0, (unsigned)nthreads);
+    if (warm_steps < 0) warm_steps = 0;
     for (int i = 0; i < nthreads; i++) {
+        jobs[i].warm = warm_steps; jobs[i].bar = &bar;
         jobs[i].b0 = (int)((int64_t)B * i / nthreads); jobs[i].b1 = (int)((int64_t)B * (i + 1) / nthreads);
         jobs[i].B = B; jobs[i].steps = steps; jobs[i].variant = variant; jobs[i].pool_games = pool_games;
         jobs[i].seed = seed; jobs[i].perm = perm_pool; jobs[i].lord = lord_pool;
         pthread_create(&th[i], 0, rollout_worker, &jobs[i]);
     }
-    int64_t total = 0; uint64_t cs = 0;
+    int64_t total = 0; uint64_t cs = 0; double sec = 0;
     if (stats) memset(stats, 0, 16 * sizeof(int64_t));
     for (int i = 0; i < nthreads; i++) {
         pthread_join(th[i], 0);
         total += jobs[i].nsteps; cs += jobs[i].checksum;
+        if (jobs[i].seconds > sec) sec = jobs[i].seconds;
         if (stats) for (int k = 0; k < 16; k++) stats[k] += jobs[i].stats[k];
     }
     if (checksum) *checksum = cs;
+    if (seconds) *seconds = sec;
+    pthread_barrier_destroy(&bar);
     free(jobs); free(th);
     return total;
 }

@@ -88,7 +88,8 @@ def lib():
         L.ddz_ref_batch_deal.argtypes = [envp, C.c_int, i8p, i8p, C.c_int, C.c_int]
         L.ddz_ref_batch_export.argtypes = [envp, C.c_int, u64p, u32p]
         L.ddz_ref_batch_export.restype = None
-        L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p]
+        L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
+                                      C.POINTER(C.c_double)]
         L.ddz_ref_rollout.restype = C.c_int64
         _lib = L
     return _lib
@@ -226,12 +227,14 @@ class RefBatch:
         return f, meta
 
 
-def rollout(B, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads):
-    """CPU baseline: returns (env_steps, stats int64[16], checksum)."""
+def rollout(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads):
+    """CPU baseline: returns (timed env_steps, seconds, stats int64[16], checksum)."""
     perm_pool = _i8(perm_pool)
     lp = None if lord_pool is None else _i8(lord_pool)
     stats = np.zeros(16, np.int64)
     cs = C.c_uint64(0)
-    n = lib().ddz_ref_rollout(int(B), int(steps), int(variant), int(seed), _ptr(perm_pool, C.c_int8),
-                              _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64), C.byref(cs))
-    return int(n), stats, int(cs.value)
+    sec = C.c_double(0)
+    n = lib().ddz_ref_rollout(int(B), int(warm_steps), int(steps), int(variant), int(seed), _ptr(perm_pool, C.c_int8),
+                              _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64),
+                              C.byref(cs), C.byref(sec))
+    return int(n), float(sec.value), stats, int(cs.value)

@@ -1,0 +1,323 @@
+"""GPU parity: the CUDA path, called through the C-ABI (ddz_b200 -> ctypes -> libddz_b200.so), against the CPU oracle
+and the committed golden fixtures.  Everything is integer / exact-float work: comparisons are bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import ddz_b200
+    return ddz_b200
+
+
+def _rand_hands(rng, n, lo=1, hi=21):
+    deck = np.array([i // 4 for i in range(52)] + [13, 14])
+    return np.stack([np.bincount(rng.permutation(deck)[:rng.integers(lo, hi)], minlength=15) for _ in range(n)]).astype(np.int8)
+
+
+def _split(packed, offsets):
+    packed = packed.cpu().numpy().view(np.uint64)
+    off = offsets.cpu().numpy()
+    return [packed[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+# ------------------------------------------------------------------ legal moves (r.get_moves)
+def test_get_moves_golden_legal_sets(D, oracle, golden):
+    g = golden.legal_sets
+    packed, offsets = D.get_moves(g["hands"], g["lasts"])
+    lists = _split(packed, offsets)
+    off = g["legal_off"]
+    for i, got in enumerate(lists):
+        want = oracle.pack(g["universe"][g["legal_idx"][off[i]:off[i + 1]]])
+        assert np.array_equal(got, want), (i, g["hands"][i], g["lasts"][i])
+
+
+def test_get_moves_random_vs_oracle(D, oracle):
+    rng = np.random.default_rng(11)
+    n = 6000
+    hands = _rand_hands(rng, n)
+    z = np.zeros(15, np.int8)
+    lasts = np.zeros((n, 15), np.int8)
+    for i in range(n):
+        if i % 3:
+            om = oracle.get_moves(_rand_hands(rng, 1, 2, 21)[0], z, fast=True)
+            w = om.sum(1).astype(np.float64) ** 2
+            lasts[i] = om[rng.choice(len(om), p=w / w.sum())]
+    packed, offsets = D.get_moves(hands, lasts)
+    for i, got in enumerate(_split(packed, offsets)):
+        want = oracle.pack(oracle.get_moves(hands[i], lasts[i], fast=(i % 7 != 0)))
+        assert np.array_equal(got, np.atleast_1d(want)), (i, hands[i], lasts[i])
+
+
+def test_get_moves_adversarial_and_edges(D, oracle):
+    z = np.zeros(15, np.int8)
+    worst = np.array([1, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0], np.int8)
+    hands = np.stack([worst, z, z, np.array([4] * 5 + [0] * 10, np.int8),
+                      np.array([3, 3, 3, 3, 3, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0], np.int8)])
+    single = np.eye(15, dtype=np.int8)[3]
+    lasts = np.stack([z, z, single, z, z])
+    packed, offsets = D.get_moves(hands, lasts)
+    lists = _split(packed, offsets)
+    assert len(lists[0]) == 497 and len(lists[1]) == 0 and list(lists[2]) == [0]
+    for i in range(len(hands)):
+        assert np.array_equal(lists[i], np.atleast_1d(oracle.pack(oracle.get_moves(hands[i], lasts[i]))))
+
+
+def test_encode_actions_kernel(D, oracle):
+    cnt = oracle.universe()[0]
+    packed = torch.as_tensor(oracle.pack(cnt).view(np.int64)).cuda()
+    out = D.BatchedEnv.encode_actions(packed).cpu().numpy()
+    want = (np.arange(4)[None, None, :] < cnt[:, :, None]).astype(np.float32)
+    assert np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------ full rollouts
+def _compare_observation(env, ref, t, check_f32=True):
+    B = env.B
+    off, au, af, face = ref.observe(want_f32=check_f32)
+    assert np.array_equal(env.offsets.cpu().numpy(), off), "offsets, step %d" % t
+    assert np.array_equal(env.actions_packed.cpu().numpy().view(np.uint64), au), "legal lists, step %d" % t
+    if check_f32:
+        assert np.array_equal(env.valid_actions()[0].cpu().numpy(), af), "action one-hots, step %d" % t
+    assert np.array_equal(env.face.cpu().numpy(), face), "face, step %d" % t
+    return int(off[B])
+
+
+def _compare_state(env, ref, t):
+    f, meta = ref.export()
+    ef, emeta = env._fields()
+    assert np.array_equal(ef.cpu().numpy().view(np.uint64), f), "state fields, step %d" % t
+    assert np.array_equal(emeta.cpu().numpy().view(np.uint32), meta), "meta, step %d" % t
+
+
+@pytest.mark.parametrize("cls,variant", [("BatchedEnv", 0), ("BatchedEnvComplicated", 1),
+                                         ("BatchedEnvCooperation", 2), ("BatchedEnvCooperationSimplify", 3)])
+def test_fused_rollout_bit_exact(D, oracle, cls, variant):
+    """BASELINE config 2: 4096 envs, random play from the Philox index stream, >= 3 games per env; every legal list,
+    encoded tensor, return value and the full state compared with the oracle at every step."""
+    B, G, seed = 4096, 8, 20260101
+    steps = 220 if variant == 2 else 60
+    perm, lord = D.random_deals(B, seed=5, pool_games=G)
+    perm_d, lord_d = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = getattr(D, cls)(B, seed=seed, env0=1000)
+    env.prepare(perm_d, lord_d, pool_games=G)
+    ref = oracle.RefBatch(B, variant)
+    ref.deal(perm, lord, pool_games=G)
+    env.observe()
+    for t in range(steps):
+        _compare_observation(env, ref, t, check_f32=(t % 8 == 0))
+        r, done, cat = env.rollout_step(mode=D.native.CHOICE_PHILOX, perm=perm_d, lord_pile=lord_d, pool_games=G)
+        rr, rd, rc, rrew = ref.step(mode=2, seed=seed, env0=1000, step=t)
+        ref.deal(perm, lord, only_done=True, pool_games=G)
+        assert np.array_equal(r.cpu().numpy(), rr) and np.array_equal(done.cpu().numpy(), rd)
+        assert np.array_equal(cat.cpu().numpy(), rc) and np.array_equal(env.reward.cpu().numpy(), rrew)
+        if t % 16 == 0:
+            _compare_state(env, ref, t)
+    _compare_state(env, ref, steps)
+    stats = env.stats.cpu().numpy()
+    assert np.array_equal(stats[[0, 1, 2, 3, 4, 5, 6, 9]], ref.stats[[0, 1, 2, 3, 4, 5, 6, 9]])
+    assert stats[7] == 0
+    if variant == 2:
+        assert stats[0] >= 3 * B * 0.8                      # about 62 decisions per game
+        assert stats[1] + stats[2] + stats[3] == stats[0]
+
+
+def test_unfused_api_matches_oracle(D, oracle):
+    """reset / prepare / observe / step (index), step_random (host entropy), step_manual (one-hot) one by one."""
+    B = 512
+    rng = np.random.default_rng(3)
+    perm, lord = D.random_deals(B, seed=8)
+    env = D.BatchedEnvCooperation(B, debug=True)
+    env.prepare(perm, lord)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord)
+    for t in range(90):
+        n = _compare_observation(env, ref, t)
+        off = ref.offsets
+        cnt = np.diff(off)
+        kind = t % 3
+        if kind == 0:
+            choice = np.where(cnt > 0, rng.integers(0, 1 << 30, B) % np.maximum(cnt, 1), 0).astype(np.int32)
+            r, done, cat = env.step(choice)
+            rr, rd, rc, rrew = ref.step(choice, mode=0)
+        elif kind == 1:
+            ent = rng.integers(0, 1 << 32, B, dtype=np.uint64).astype(np.uint32)
+            r, done, cat = env.step_random(ent)
+            rr, rd, rc, rrew = ref.step(ent.view(np.int32), mode=1)
+        else:
+            choice = np.where(cnt > 0, rng.integers(0, 1 << 30, B) % np.maximum(cnt, 1), 0).astype(np.int32)
+            acts, offs = env.valid_actions()
+            idx = torch.as_tensor(off[:-1].astype(np.int64) + choice).cuda()
+            idx = torch.where(torch.as_tensor(cnt > 0).cuda(), idx, torch.zeros_like(idx))
+            onehot = acts[idx]
+            # finished envs have no list: give them an all-zero one-hot (ignored)
+            onehot = onehot * torch.as_tensor(cnt > 0).cuda()[:, None, None]
+            r, done, cat = env.step_manual(onehot)
+            rr, rd, rc, rrew = ref.step(choice, mode=0)
+        assert np.array_equal(r.cpu().numpy(), rr) and np.array_equal(done.cpu().numpy(), rd), t
+        assert np.array_equal(cat.cpu().numpy(), rc) and np.array_equal(env.reward.cpu().numpy(), rrew), t
+        _compare_state(env, ref, t)
+        # getters
+        if t % 10 == 0:
+            f, meta = ref.export()
+            assert np.array_equal(env.left.cpu().numpy(), oracle.unpack(f[0:3].T).sum(-1))
+            assert np.array_equal(env.history.cpu().numpy(), oracle.unpack(f[3:6].T))
+            assert np.array_equal(env.recent_handout.cpu().numpy(), oracle.unpack(f[6:9].T))
+            assert np.array_equal(env.get_role_ID().cpu().numpy(), (meta & 3) + 1)
+        if t == 70:   # re-deal the finished ones, keep the others
+            perm2, lord2 = D.random_deals(B, seed=9)
+            env.prepare(perm2, lord2, only_done=True)
+            ref.deal(perm2, lord2, only_done=True)
+
+
+def test_reference_api_views_replay_golden_trace(D, golden):
+    """The B=1 `Env*` views expose the reference's exact signatures; replay the golden envi.py trace through them."""
+    t = golden.envi_trace
+    classes = [(D.Env, "face_first"), (D.EnvComplicated, "face_complicated"),
+               (D.EnvCooperation, "face_cooperation"), (D.EnvCooperationSimplify, "face_simplify")]
+    for cls, key in classes:
+        faces = t[key]
+        env = cls(debug=True)
+        fi = li = 0
+        for g in range(4):
+            env.reset()
+            env.prepare(t["perms"][g][None], np.zeros(1, np.int8))
+            for s in np.flatnonzero(t["game"] == g):
+                n = int(t["n_legal"][s])
+                face = env.face
+                assert tuple(face.shape) == faces[fi].shape and face.dtype == torch.float32
+                assert np.array_equal(face.cpu().numpy(), faces[fi])
+                acts = env.valid_actions()
+                assert tuple(acts.shape) == (n, 15, 4)
+                assert np.array_equal(acts.cpu().numpy(), t["actions_f32"][li:li + n])
+                assert env.valid_actions(tensor=False) == t["legal"][li:li + n].tolist()
+                assert env.get_role_ID() - 1 == t["role"][s]
+                r, done, cat = env.step_manual(acts[int(t["choice"][s])])
+                assert (r, done, cat) == (int(t["r"][s]), bool(t["done"][s]), int(t["cat"][s]))
+                assert np.array_equal(env.left, t["left"][s]) and np.array_equal(env.taken, t["taken"][s])
+                for q in range(3):
+                    assert np.array_equal(env.history[q], t["history"][s][q])
+                    assert np.array_equal(env.recent_handout[q], t["recent"][s][q])
+                fi += 1
+                li += n
+            assert np.array_equal(env.face.cpu().numpy(), faces[fi])      # terminal face (game.py:121-122)
+            fi += 1
+
+
+def test_encode_face_standalone(D, oracle):
+    B = 300
+    perm, lord = D.random_deals(B, seed=21)
+    for variant, cls in enumerate([D.BatchedEnv, D.BatchedEnvComplicated, D.BatchedEnvCooperation, D.BatchedEnvCooperationSimplify]):
+        env = cls(B)
+        env.prepare(perm, lord)
+        ref = oracle.RefBatch(B, variant)
+        ref.deal(perm, lord)
+        for t in range(5):
+            env.rollout_step()
+            off, au, af, face = ref.observe()
+            ref.step(mode=2, seed=0, env0=0, step=t)
+        out = torch.empty_like(env._face)
+        D.native.check(D.native.lib.ddz_encode_face(env._state.data_ptr(), variant, out.data_ptr(), B, None), "ddz_encode_face")
+        torch.cuda.synchronize()
+        _, _, _, face = ref.observe()
+        assert np.array_equal(out.cpu().numpy(), face)
+
+
+def test_errors_are_flagged_not_silent(D):
+    B = 64
+    perm, lord = D.random_deals(B, seed=2)
+    env = D.BatchedEnv(B)
+    env.prepare(perm, lord)
+    before = env._state.clone()
+    bad = torch.full((B,), 10_000, dtype=torch.int32)
+    r, done, cat = env.step(bad)
+    torch.cuda.synchronize()
+    assert int(env.stats[7].item()) == B and (cat == -1).all() and (r == 0).all()
+    f0 = before[: 18 * B]
+    assert torch.equal(env._state[: 18 * B], f0)                       # cards untouched
+    assert ((env._fields()[1] >> 5) & 1).all()                         # sticky error bit
+    # a bad permutation is refused
+    env2 = D.BatchedEnv(B, debug=True)
+    badperm = perm.copy()
+    badperm[5, 0] = badperm[5, 1]
+    with pytest.raises(D.native.DdzError):
+        env2.prepare(badperm, lord)
+    # too small an action buffer is reported
+    env3 = D.BatchedEnv(B, max_actions_per_env=4)
+    env3.prepare(perm, lord)
+    with pytest.raises(D.native.DdzError):
+        env3.num_actions
+    # null / bad arguments come back as error codes, not crashes
+    assert D.native.lib.ddz_observe(None, None, 0, None, None, None, 0, None, None, B, None) == D.native.E_ARG
+    assert D.native.lib.ddz_reset(None, None, None, 1, 0, None, B, None) == D.native.E_ARG
+    assert D.native.lib.ddz_face_channels(7) == D.native.E_ARG
+
+
+def test_state_dict_resume_is_exact(D):
+    B = 256
+    perm, lord = D.random_deals(B, seed=4, pool_games=2)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    a = D.BatchedEnvCooperation(B, seed=77)
+    a.prepare(pd, ld, pool_games=2)
+    for _ in range(30):
+        a.rollout_step(perm=pd, lord_pile=ld, pool_games=2)
+    sd = a.state_dict()
+    b = D.BatchedEnvCooperation(B, seed=77)
+    b.load_state_dict(sd)
+    for _ in range(40):
+        a.rollout_step(perm=pd, lord_pile=ld, pool_games=2)
+        b.rollout_step(perm=pd, lord_pile=ld, pool_games=2)
+    assert torch.equal(a._state, b._state) and torch.equal(a.face, b.face) and torch.equal(a.stats, b.stats)
+
+
+def test_full_size_invariants(D, oracle):
+    """BASELINE config 4 slice: 131 072 envs on one GPU.  Size-independent properties + oracle spot checks."""
+    B, G, seed = 131072, 4, 7
+    perm, lord = D.random_deals(B, seed=1, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = D.BatchedEnvCooperation(B, seed=seed, max_actions_per_env=160)
+    env.prepare(pd, ld, pool_games=G)
+    deck = torch.tensor([4] * 13 + [1, 1], device="cuda")
+    sample = np.random.default_rng(0).choice(B, 512, replace=False)
+    ref = oracle.RefBatch(len(sample), 2)
+    ref.deal(perm.reshape(G, B, 54)[:, sample].reshape(-1, 54), lord.reshape(G, B)[:, sample].reshape(-1), pool_games=G)
+    for t in range(130):
+        env.observe() if t == 0 else None
+        off = env.offsets.to(torch.int64)
+        cnt = off[1:] - off[:-1]
+        assert (cnt >= 0).all() and int(off[0]) == 0
+        assert (cnt[~env.is_done] >= 1).all()
+        assert env.num_actions == int(off[B])
+        # cards are conserved: hands + everything played == one deck
+        total = env.hands().sum(1) + env.taken
+        assert (total == deck).all()
+        # every listed move fits in the mover's hand
+        if t % 20 == 0:
+            mv = D.unpack_counts(env.actions_packed)
+            owner = torch.repeat_interleave(torch.arange(B, device="cuda"), cnt)
+            assert (mv <= env.get_curr_handcards()[owner]).all()
+            # spot check against the oracle on the sample
+            o_off, o_au, _, o_face = ref.observe(want_f32=False)
+            lists = env.actions_packed.cpu().numpy().view(np.uint64)
+            offs = off.cpu().numpy()
+            got = np.concatenate([lists[offs[b]:offs[b + 1]] for b in sample])
+            assert np.array_equal(got, o_au)
+            assert np.array_equal(env.face[torch.as_tensor(sample).cuda()].cpu().numpy(), o_face)
+        else:
+            ref.observe(want_f32=False, want_face=False)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
+        # the oracle sample follows the same Philox stream: env ids are the sampled global ids
+        for i, b in enumerate(sample):
+            pass
+        ent = np.array([oracle.philox(seed, int(b), t) for b in sample], dtype=np.uint32)
+        ref.step(ent.view(np.int32), mode=1)
+        ref.deal(perm.reshape(G, B, 54)[:, sample].reshape(-1, 54), lord.reshape(G, B)[:, sample].reshape(-1),
+                 only_done=True, pool_games=G)
+    assert int(env.stats[7].item()) == 0
+    st = env.stats.cpu().numpy()
+    assert st[1] + st[2] + st[3] == st[0] and st[0] > B
