@@ -57,11 +57,11 @@ def peaks():
 
 
 def bytes_per_env_step(nbar, C=CHANNELS):
-    """ALGORITHMIC bytes of one env-step: state read+write, face write, action one-hot + packed list write,
-    offset write, chosen-move gather + offsets read, r/done/cat/reward write, counts write+read."""
-    transition = 2 * STATE_BYTES + 8 + 8 + 15 + 4
-    emit = STATE_BYTES + 4 + 4 + 240 * C + 248 * nbar
-    return transition, emit
+    """ALGORITHMIC bytes of one env-step = one env's share of one k_env launch: state read + write,
+    previous offsets (2 x 4) and chosen move (8) read, r/done/cat/reward (15) written, new offset (4), packed list
+    (8 N) and one-hot rows (240 N) written, face (240 C) written.  Deck permutations of re-dealt envs (55 B x ~1.6 %)
+    and the look-back words are not counted."""
+    return 2 * STATE_BYTES + 8 + 8 + 15 + 4 + 240 * C + 248 * nbar
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -121,10 +121,10 @@ def cpu_rollout(envs, warm, steps, threads):
 def cpu_baseline(target_seconds):
     """oracle port timed on this box's host cores over a bounded sample of the same workload."""
     threads = os.cpu_count() or 1
-    envs = 512 * threads
+    envs = 4096 * threads
     n, sec, _ = cpu_rollout(envs, 100, 20, threads)                 # calibration
     rate = n / max(sec, 1e-9)
-    steps = max(20, min(int(target_seconds * rate / envs), 4000))
+    steps = max(20, min(int(target_seconds * rate / envs), 20000))
     n, sec, stats = cpu_rollout(envs, 100, steps, threads)
     return {"value": n / sec, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d envs x %d env-steps after 100 warm-up steps (%.1f s), C oracle (oracle/ddz_oracle.c), "
@@ -190,19 +190,18 @@ def run_ours(args):
 
     # ---------------- timed region: device-resident inputs, CUDA events on the launching (current) stream
     stats0 = env.stats.clone()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     ev[0].record()
     for k in range(K):
-        env.rollout_step(mid_event=ev[2 * k + 1], **step_kw)
-        ev[2 * k + 2].record()
+        env.rollout_step(**step_kw)         # one launch: k_env<cooperation, step+observe>
+        ev[k + 1].record()
     barrier()
     clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[2 * K])
-    emit_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)) / K
-    trans_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)) / K
+    total_ms = ev[0].elapsed_time(ev[K])
+    kern_ms = sum(ev[k].elapsed_time(ev[k + 1]) for k in range(K)) / K   # the kernel's average launch duration
     dstats_t = (env.stats - stats0).clone()
     dstats = dstats_t.cpu().numpy()
     if int(env.stats[7].item()):
@@ -250,18 +249,16 @@ def run_ours(args):
     # ---------------- reduce over ranks: MAX of the device times, SUM of the work
     total_ms = D.sharding.max_over_ranks(total_ms, dev)
     e2e_ms = D.sharding.max_over_ranks(e2e_ms, dev)
-    emit_ms = D.sharding.max_over_ranks(emit_ms, dev)
-    trans_ms = D.sharding.max_over_ranks(trans_ms, dev)
+    kern_ms = D.sharding.max_over_ranks(kern_ms, dev)
     gstats = D.sharding.allreduce_stats(dstats_t, side_stream=torch.cuda.Stream(dev) if world > 1 else None)
     torch.cuda.synchronize(dev)
     all_steps = int(gstats[4].item())
 
     if rank == 0:
         peak, peak_src = peaks()
-        tb, eb = bytes_per_env_step(nbar)
+        eb = bytes_per_env_step(nbar)
         value = all_steps / (total_ms * 1e-3)
-        emit_gbs = B * eb / (emit_ms * 1e-3) / 1e9
-        step_gbs = (all_steps / world) * (tb + eb) / (total_ms * 1e-3) / 1e9
+        kern_gbs = B * eb / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -270,17 +267,15 @@ def run_ours(args):
                                    "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % B,
                        "envs_per_gpu": B, "face_channels": CHANNELS, "mean_legal_moves": nbar,
                        "prefill_steps": args.prefill, "pool_games": G, "parallelism": "env-shard x%d" % world,
-                       "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * (tb + eb) / 1e6),
+                       "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
                        "games_finished": int(gstats[0].item()),
                        "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))},
-            "roofline": {"bound": "hbm", "kernel": "k_emit", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": emit_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env": eb, "ms_per_launch": emit_ms,
-                         "step_achieved": step_gbs, "step_frac": step_gbs / peak, "step_bytes_per_env": tb + eb,
-                         "transition_ms_per_launch": trans_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env": eb, "ms_per_launch": kern_ms},
             "e2e": {"value": B * K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
-            "gpu_launches": 2 * K,
+            "gpu_launches": K,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

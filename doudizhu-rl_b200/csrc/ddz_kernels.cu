@@ -1,13 +1,19 @@
 // ddz_kernels.cu -- sm_100a kernels and the C-ABI launchers of libddz_b200.so (see include/ddz_b200.h).
 //
-// Kernels (one CTA = kEnvs consecutive envs, thread t owns env b0+t for the rule work, the whole CTA
-// cooperates on the stores):
-//   k_reset          deal from host-supplied permutations                      (reference: CEnv.prepare)
-//   k_transition     [apply the chosen move] [re-deal finished envs] count the legal moves of the new state
-//   k_emit           CSR offsets (block scan + prefix of the per-CTA totals), move enumeration into
-//                    actions_u64, then thermometer rows for actions_f32 and face as 128-bit coalesced stores
-//   k_encode_actions packed moves -> [n,15,4] float32
-// One env-step of a rollout = k_transition + k_emit (ddz_rollout_step).
+// k_env<V, MODE> is the whole env-step in ONE launch.  A CTA owns kEnvs consecutive envs (thread t <-> env b0+t for
+// the rule work, the whole CTA for the output):
+//   1. tile ticket (atomic) -> b0; load the packed state (SoA, coalesced)
+//   2. [MODE step] pick the move (index / entropy % N / Philox % N / explicit), apply it, terminal + rewards,
+//      [re-deal finished envs from the host-supplied permutation pool], store the state
+//   3. count legal moves (closed form), CTA-wide exclusive scan, publish the CTA total for the decoupled
+//      look-back that turns per-CTA totals into global CSR offsets without a second pass over the state
+//   4. face rows: the C count planes of every env go to shared memory; each thread expands one 240-byte row
+//      (15 x float4 through a 5-entry thermometer LUT) into a 128-row staging tile; one elected thread pushes the
+//      tile to HBM with a TMA bulk store (cp.async.bulk.global.shared::cta) while the CTA fills the other tile
+//   5. look-back (its latency is hidden behind 4) -> global base, offsets
+//   6. enumerate the legal moves in canonical order into shared memory (segments of < kMoveCap moves), write
+//      the packed list (coalesced) and the action rows (same tile + TMA path as the face)
+// Nothing is re-read from HBM: algorithmic bytes == DRAM traffic (profiles/).
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -18,34 +24,57 @@
 
 namespace ddz {
 
-constexpr int kEnvs = 128;     // envs per CTA == threads per CTA
+constexpr int kEnvs = 128;                       // envs per CTA == threads per CTA
 constexpr int kWarps = kEnvs / 32;
+constexpr int kTileRows = 128;                   // rows (240 B each) per staging tile, one per thread
+constexpr int kSegMoves = 1280;                  // a new segment of envs starts every kSegMoves legal moves ...
+constexpr int kMoveCap = kSegMoves + DDZ_MAX_LEGAL;  // ... so a segment never holds this many (an env has <= 512)
+constexpr int kMaxSegs = kEnvs * DDZ_MAX_LEGAL / kSegMoves + 2;
 
-struct Workspace {
-    int32_t* counts;   // [B]
-    int32_t* blk;      // [nblk] legal moves per CTA
-};
+enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
+
+// workspace: header (ticket, finished, epoch) + one look-back word per CTA.  Must be zero when first used.
+struct WsHeader { unsigned int ticket, finished, epoch, pad; };
+struct Workspace { WsHeader* h; unsigned long long* tile; };
 static inline int nblocks(int B) { return (B + kEnvs - 1) / kEnvs; }
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static inline Workspace ws_of(void* p, int B) {
-    Workspace w; w.counts = (int32_t*)p; w.blk = (int32_t*)((char*)p + align_up((size_t)B * 4, 256));
+static inline Workspace ws_of(void* p) {
+    Workspace w; w.h = (WsHeader*)p; w.tile = (unsigned long long*)((char*)p + 256);
     return w;
 }
+// look-back word: [63:34] epoch, [33:32] status (1 = CTA total, 2 = inclusive prefix), [31:0] value
+constexpr unsigned long long kAggregate = 1ull << 32, kInclusive = 2ull << 32;
 
 // ------------------------------------------------------------------------------------------------
-// block helpers
+// small PTX wrappers
 // ------------------------------------------------------------------------------------------------
-DDZ_DEV int warp_sum(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+DDZ_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DDZ_DEV void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {   // bytes % 16 == 0, both 16-B aligned
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+DDZ_DEV void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+DDZ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DDZ_DEV unsigned long long ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+DDZ_DEV void st_relaxed(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 DDZ_DEV long long warp_sum_ll(long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
-// exclusive scan of one int per thread over the CTA; *total = CTA sum.  smem: int[kWarps]
+DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {
+    v = warp_sum_ll(v);
+    if ((threadIdx.x & 31) == 0 && v != 0 && stats) atomicAdd((unsigned long long*)&stats[slot], (unsigned long long)v);
+}
+// exclusive scan of one int per thread over the CTA; *total = CTA sum.  smem: int[kWarps]; ends after a barrier
 DDZ_DEV int block_exclusive_scan(int v, int* smem, int* total) {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = v;
@@ -56,17 +85,12 @@ DDZ_DEV int block_exclusive_scan(int v, int* smem, int* total) {
     int base = 0, tot = 0;
 #pragma unroll
     for (int i = 0; i < kWarps; i++) { int s = smem[i]; if (i < w) base += s; tot += s; }
-    __syncthreads();
     *total = tot;
     return base + inc - v;
 }
-DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {
-    v = warp_sum_ll(v);
-    if ((threadIdx.x & 31) == 0 && v != 0 && stats) atomicAdd((unsigned long long*)&stats[slot], (unsigned long long)v);
-}
 
 // ------------------------------------------------------------------------------------------------
-// k_reset
+// deal
 // ------------------------------------------------------------------------------------------------
 DDZ_DEV bool redeal(Env& e, const int8_t* perm, const int8_t* lord_pile, int pool_games, int B, int b) {
     uint32_t games = e.meta >> 8;
@@ -97,83 +121,23 @@ __global__ void __launch_bounds__(kEnvs) k_reset(void* state, const int8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_transition: [step] [re-deal] count
+// thermometer rows (envi.py:140-146) through a 5-entry LUT in shared memory
 // ------------------------------------------------------------------------------------------------
-struct StepArgs {
-    const int32_t* offsets; const uint64_t* actions; const void* choice; int mode;
-    uint64_t seed, env0; uint32_t stepno; int32_t rewards[3];
-    const int8_t* perm; const int8_t* lord_pile; int pool_games;
-    int8_t* r; uint8_t* done; int8_t* cat; float* reward;
-};
-
-template <bool STEP, bool RAW>
-__global__ void __launch_bounds__(kEnvs) k_transition(void* state, const uint64_t* __restrict__ raw_hands,
-                                                      const uint64_t* __restrict__ raw_lasts, StepArgs a,
-                                                      Workspace ws, int64_t* stats, int B) {
-    __shared__ int s_red[kWarps];
-    int b = blockIdx.x * kEnvs + threadIdx.x;
-    bool valid = b < B;
-    int n = 0;
-    long long d_games = 0, d_lord = 0, d_down = 0, d_up = 0, d_steps = 0, d_retl = 0, d_retf = 0, d_err = 0, d_pass = 0;
-    if (RAW) {
-        if (valid) n = count_legal(masks_of(raw_hands[b]), raw_lasts[b]);
-    } else if (valid) {
-        StateView v = view_of(state, B);
-        Env e = load_env(v, b);
-        if (STEP) {
-            int o_r = 0, o_cat = -1;
-            float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
-            if (!e.done()) {
-                int base = a.offsets[b], cnt = a.offsets[b + 1] - base;
-                long long idx = -1;
-                if (a.mode == DDZ_CHOICE_INDEX) idx = ((const int32_t*)a.choice)[b];
-                else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)(((const uint32_t*)a.choice)[b] % (uint32_t)cnt) : -1;
-                else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, a.stepno) % (uint32_t)cnt) : -1;
-                else {
-                    uint64_t want = ((const uint64_t*)a.choice)[b];
-                    for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
-                }
-                if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; d_err = 1; }
-                else {
-                    StepOut o = apply_move(e, a.actions[base + idx], a.rewards);
-                    o_r = o.r; o_cat = o.cat; rw0 = o.reward[0]; rw1 = o.reward[1]; rw2 = o.reward[2];
-                    d_steps = 1; d_pass = o.pass;
-                    if (o.done) {
-                        d_games = 1; d_lord = (o.winner == 1); d_down = (o.winner == 2); d_up = (o.winner == 0);
-                        d_retl = (long long)rw1; d_retf = (long long)rw0 + (long long)rw2;
-                    }
-                }
-            }
-            if (a.r) a.r[b] = (int8_t)o_r;
-            if (a.done) a.done[b] = (uint8_t)e.done();
-            if (a.cat) a.cat[b] = (int8_t)o_cat;
-            if (a.reward) { a.reward[3 * (size_t)b] = rw0; a.reward[3 * (size_t)b + 1] = rw1; a.reward[3 * (size_t)b + 2] = rw2; }
-            if (a.perm && e.done()) d_err += !redeal(e, a.perm, a.lord_pile, a.pool_games, B, b);
-            store_env(v, b, e);
-        }
-        if (!e.done()) n = count_legal(masks_of(hand_to_move(e)), trick_of(e));
-    }
-    if (ws.counts) {
-        if (valid) ws.counts[b] = n;
-        int w = warp_sum(n);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = w;
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < kWarps; i++) t += s_red[i]; ws.blk[blockIdx.x] = t; }
-    }
-    if (STEP) {
-        stat_add(stats, 0, d_games); stat_add(stats, 1, d_lord); stat_add(stats, 2, d_down); stat_add(stats, 3, d_up);
-        stat_add(stats, 4, d_steps); stat_add(stats, 5, d_retl); stat_add(stats, 6, d_retf); stat_add(stats, 7, d_err);
-        stat_add(stats, 9, d_pass);
+// one row = 15 float4: rank k -> {c>0, c>1, c>2, c>3} * s, c = nibble k of `packed`
+template <bool SCALED>
+DDZ_DEV void fill_row(float4* __restrict__ row, uint64_t packed, float s, const float4* __restrict__ lut) {
+    const uint32_t lo = (uint32_t)packed, hi = (uint32_t)(packed >> 32);
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+        const uint32_t w = (k < 8) ? lo : hi;
+        const int sh = 4 * (k & 7);
+        const uint32_t off = (sh == 0) ? ((w << 4) & 0xF0u) : ((w >> (sh - 4)) & 0xF0u);   // count * 16 bytes
+        float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(lut) + off);
+        if (SCALED) { q.x *= s; q.y *= s; q.z *= s; q.w *= s; }
+        row[k] = q;
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_emit: offsets, packed moves, thermometer rows
-// ------------------------------------------------------------------------------------------------
-DDZ_DEV float4 thermo_row(uint64_t packed, int rank, float s) {
-    uint32_t c = (uint32_t)(packed >> (4 * rank)) & 15u;
-    return make_float4(c > 0 ? s : 0.f, c > 1 ? s : 0.f, c > 2 ? s : 0.f, c > 3 ? s : 0.f);
-}
 template <int V> struct FaceCfg;
 template <> struct FaceCfg<0> { static constexpr int C = 4; };
 template <> struct FaceCfg<1> { static constexpr int C = 7; };
@@ -209,18 +173,253 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
     p[1] = tot > 0 ? __fdiv_rn((float)size2, (float)tot) : 0.f;
 }
 
-// the CTA's face block [nenv][C][15] float4 is contiguous: thread i writes vector i, i+kEnvs, ...
-template <int C>
-DDZ_DEV void store_face_rows(float4* __restrict__ dst, int nenv, const uint64_t* s_planes, const float* s_p) {
-    const int nvec = nenv * C * 15;
-    for (int i = threadIdx.x; i < nvec; i += kEnvs) {
-        int row = i / 15, rank = i - row * 15;
-        int env = row / C, c = row - env * C;
-        float s = (c >= C - 2) ? s_p[env * 2 + (c - (C - 2))] : 1.f;
-        dst[i] = thermo_row(s_planes[row], rank, s);
+// Staging: two tiles of kTileRows rows.  Every thread fills one row, then one thread issues the bulk store.
+struct Stager {
+    float4* tiles;   // [2][kTileRows*15]
+    int k;           // tiles issued so far by this CTA
+    DDZ_DEV float4* acquire() {   // all threads
+        // the bulk store issued two tiles ago read this buffer: wait for that read before overwriting it
+        if (threadIdx.x == 0) tma_wait_read<1>();
+        __syncthreads();
+        return tiles + (size_t)(k & 1) * (kTileRows * 15);
+    }
+    DDZ_DEV void release(void* gdst, uint32_t bytes) {   // all threads
+        fence_async_smem();        // this thread's generic-proxy smem writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) tma_store(gdst, tiles + (size_t)(k & 1) * (kTileRows * 15), bytes);
+        k++;
+    }
+};
+
+struct StepArgs {
+    const int32_t* offsets; const uint64_t* actions; const void* choice; int mode;
+    uint64_t seed, env0; uint32_t stepno; int32_t rewards[3];
+    const int8_t* perm; const int8_t* lord_pile; int pool_games;
+    int8_t* r; uint8_t* done; int8_t* cat; float* reward;
+};
+struct OutArgs {
+    int32_t* offsets; uint64_t* actions_u64; float4* actions_f32; long long cap; float4* face;
+};
+
+struct SmemEmitter {      // enumerate_legal functor: packed moves into the CTA's shared segment
+    uint64_t* out; int pos;
+    DDZ_DEV void operator()(uint64_t mv) { out[pos++] = mv; }
+};
+
+struct __align__(128) Smem {
+    float4 tiles[2][kTileRows * 15];                        // 61 440 B
+    union {                                                 // the planes are dead before the moves are produced
+        struct { uint64_t planes[kEnvs * 9]; float p[kEnvs * 2]; } f;
+        uint64_t moves[kMoveCap];
+    } u;
+    float4 lut[8];
+    int scan[kWarps];
+    int segfirst[kMaxSegs];                                 // local offset of the first move of each segment
+    int tile, nseg;
+    unsigned int epoch;
+    long long base;
+};
+static_assert(sizeof(Smem) <= 76800, "three CTAs per SM need <= 76 800 B of shared memory each");
+
+// V: face variant or -1 (no face).  MODE: see enum Mode.
+template <int V, int MODE>
+__global__ void __launch_bounds__(kEnvs) k_env(void* state, const uint64_t* __restrict__ raw_hands,
+                                               const uint64_t* __restrict__ raw_lasts, StepArgs a, OutArgs o,
+                                               Workspace ws, int64_t* stats, int B) {
+    constexpr bool STEP = (MODE == kStepOnly || MODE == kStepObserve);
+    constexpr bool EMIT = (MODE != kStepOnly);
+    constexpr int C = FaceCfg<(V < 0 ? 0 : V)>::C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nblk = gridDim.x;
+
+    // ---- 1. tile ticket: tiles are handed out in start order, so every lower tile is already running
+    int t = blockIdx.x;
+    if (EMIT) {
+        if (tid == 0) {
+            sm.tile = (int)atomicAdd(&ws.h->ticket, 1u);
+            sm.epoch = ws.h->epoch;
+            sm.nseg = 0;
+        }
+        if (tid < 5) sm.lut[tid] = make_float4(tid > 0 ? 1.f : 0.f, tid > 1 ? 1.f : 0.f, tid > 2 ? 1.f : 0.f, tid > 3 ? 1.f : 0.f);
+        for (int i = tid; i < kMaxSegs; i += kEnvs) sm.segfirst[i] = 0x7FFFFFFF;
+        __syncthreads();
+        t = sm.tile;
+    }
+    const unsigned long long epoch_tag = EMIT ? ((unsigned long long)(sm.epoch & 0x3FFFFFFFu) << 34) : 0ull;
+    const int b0 = t * kEnvs, b = b0 + tid;
+    const bool valid = b < B;
+    const int nenv = min(kEnvs, B - b0);
+
+    // ---- 2. state transition
+    Env e;
+    uint64_t hand = 0, last = 0;
+    int n = 0;
+    long long d_games = 0, d_lord = 0, d_down = 0, d_up = 0, d_steps = 0, d_retl = 0, d_retf = 0, d_err = 0, d_pass = 0;
+    if (MODE == kRaw) {
+        if (valid) { hand = raw_hands[b]; last = raw_lasts[b]; n = count_legal(masks_of(hand), last); }
+    } else if (valid) {
+        StateView v = view_of(state, B);
+        e = load_env(v, b);
+        if (STEP) {
+            int o_r = 0, o_cat = -1;
+            float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
+            if (!e.done()) {
+                int base = a.offsets[b], cnt = a.offsets[b + 1] - base;
+                long long idx = -1;
+                if (a.mode == DDZ_CHOICE_INDEX) idx = ((const int32_t*)a.choice)[b];
+                else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)(((const uint32_t*)a.choice)[b] % (uint32_t)cnt) : -1;
+                else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, a.stepno) % (uint32_t)cnt) : -1;
+                else {
+                    uint64_t want = ((const uint64_t*)a.choice)[b];
+                    for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
+                }
+                if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; d_err = 1; }
+                else {
+                    StepOut so = apply_move(e, a.actions[base + idx], a.rewards);
+                    o_r = so.r; o_cat = so.cat; rw0 = so.reward[0]; rw1 = so.reward[1]; rw2 = so.reward[2];
+                    d_steps = 1; d_pass = so.pass;
+                    if (so.done) {
+                        d_games = 1; d_lord = (so.winner == 1); d_down = (so.winner == 2); d_up = (so.winner == 0);
+                        d_retl = (long long)rw1; d_retf = (long long)rw0 + (long long)rw2;
+                    }
+                }
+            }
+            if (a.r) a.r[b] = (int8_t)o_r;
+            if (a.done) a.done[b] = (uint8_t)e.done();
+            if (a.cat) a.cat[b] = (int8_t)o_cat;
+            if (a.reward) { a.reward[3 * (size_t)b] = rw0; a.reward[3 * (size_t)b + 1] = rw1; a.reward[3 * (size_t)b + 2] = rw2; }
+            if (a.perm && e.done()) d_err += !redeal(e, a.perm, a.lord_pile, a.pool_games, B, b);
+            store_env(v, b, e);
+        }
+        if (EMIT && !e.done()) { hand = hand_to_move(e); last = trick_of(e); n = count_legal(masks_of(hand), last); }
+    }
+    if (STEP) {
+        stat_add(stats, 0, d_games); stat_add(stats, 1, d_lord); stat_add(stats, 2, d_down); stat_add(stats, 3, d_up);
+        stat_add(stats, 4, d_steps); stat_add(stats, 5, d_retl); stat_add(stats, 6, d_retf); stat_add(stats, 7, d_err);
+        stat_add(stats, 9, d_pass);
+    }
+    if (!EMIT) return;
+
+    // ---- 3. CTA scan, publish the CTA total for the look-back, cut the envs into segments
+    int total;
+    const int local = block_exclusive_scan(n, sm.scan, &total);
+    if (tid == 0) st_relaxed(&ws.tile[t], epoch_tag | (t == 0 ? kInclusive : kAggregate) | (unsigned int)total);
+    // Env i (with moves) belongs to segment local_i / kSegMoves.  Consecutive starts differ by <= 512 < kSegMoves,
+    // so no segment index is skipped and a segment spans < kSegMoves + 512 = kMoveCap moves.
+    const int seg = local / kSegMoves;
+    if (valid && n > 0) { atomicMin(&sm.segfirst[seg], local); atomicMax(&sm.nseg, seg + 1); }
+
+    Stager stg{&sm.tiles[0][0], 0};
+
+    // ---- 4. face rows
+    if (V >= 0 && o.face) {
+        if (valid) {
+            uint64_t pl[C]; float p[2];
+            face_planes<(V < 0 ? 0 : V)>(e, pl, p);
+#pragma unroll
+            for (int c = 0; c < C; c++) sm.u.f.planes[tid * C + c] = pl[c];
+            sm.u.f.p[tid * 2] = p[0]; sm.u.f.p[tid * 2 + 1] = p[1];
+        }
+        __syncthreads();
+        const int nrows = nenv * C;
+        char* gface = reinterpret_cast<char*>(o.face) + (size_t)b0 * C * 240;
+        for (int r0 = 0; r0 < nrows; r0 += kTileRows) {
+            float4* tile = stg.acquire();
+            const int row = r0 + tid;
+            if (row < nrows) {
+                const int env = row / C, c = row - env * C;
+                const float s = (c >= C - 2) ? sm.u.f.p[env * 2 + (c - (C - 2))] : 1.f;
+                fill_row<true>(tile + tid * 15, sm.u.f.planes[row], s, sm.lut);
+            }
+            stg.release(gface + (size_t)r0 * 240, (uint32_t)min(kTileRows, nrows - r0) * 240u);
+        }
+    }
+
+    // ---- 5. look-back for the global base (warp 0); its predecessors published long ago
+    if (tid < 32) {
+        long long prefix = 0;
+        if (t > 0) {
+            int p = t - 1;                                  // walk the predecessors 32 at a time
+            unsigned int spins = 0;
+            bool finished = false;
+            while (!finished) {
+                const int idx = p - tid;
+                unsigned long long w = 0;
+                bool ok = true;
+                if (idx >= 0) {
+                    w = ld_relaxed(&ws.tile[idx]);
+                    ok = ((w >> 34) == (epoch_tag >> 34)) && ((w >> 32) & 3ull) != 0;
+                }
+                if (__all_sync(0xFFFFFFFFu, ok)) {
+                    const bool inc = idx >= 0 && ((w >> 32) & 3ull) == 2ull;
+                    const unsigned int incmask = __ballot_sync(0xFFFFFFFFu, inc);
+                    // lanes up to and including the nearest inclusive predecessor contribute
+                    const int stop = incmask ? (__ffs(incmask) - 1) : 31;
+                    const long long v = (idx >= 0 && tid <= stop) ? (long long)(unsigned int)w : 0;
+                    prefix += warp_sum_ll(v);
+                    if (incmask || p - 32 < 0) finished = true;
+                    p -= 32;
+                } else if (++spins > (1u << 24)) {          // never hang the GPU: flag the error and carry on
+                    if (tid == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                    finished = true;
+                }
+            }
+            if (tid == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(prefix + total));
+        }
+        if (tid == 0) sm.base = prefix;
+    }
+    __syncthreads();   // base, segfirst, nseg visible; the face planes are dead: the union now holds moves
+    const long long base = sm.base;
+    if (valid) o.offsets[b] = (int32_t)(base + local);
+    if (t == nblk - 1 && tid == 0) {
+        o.offsets[B] = (int32_t)(base + total);
+        if (stats) {
+            atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
+            if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
+        }
+    }
+    long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this CTA that fit
+
+    // ---- 6. per segment: enumerate into shared memory, then packed list + one-hot rows out
+    const int nseg = sm.nseg;
+    int disagree = 0;
+    for (int k = 0; k < nseg; k++) {
+        const int first = sm.segfirst[k];
+        const int seg_end = (k + 1 < nseg) ? sm.segfirst[k + 1] : total;
+        if (valid && n > 0 && seg == k) {
+            SmemEmitter em{sm.u.moves, local - first};
+            enumerate_legal(masks_of(hand), last, em);
+            disagree |= (em.pos != local - first + n);
+        }
+        __syncthreads();
+        const int keep = (int)max(0ll, min((long long)(seg_end - first), lim - first));
+        for (int i = tid; i < keep; i += kEnvs) o.actions_u64[base + first + i] = sm.u.moves[i];   // coalesced
+        if (o.actions_f32) {
+            char* gact = reinterpret_cast<char*>(o.actions_f32) + (size_t)(base + first) * 240;
+            for (int r0 = 0; r0 < keep; r0 += kTileRows) {
+                float4* tile = stg.acquire();
+                const int row = r0 + tid;
+                if (row < keep) fill_row<false>(tile + tid * 15, sm.u.moves[row], 1.f, sm.lut);
+                stg.release(gact + (size_t)r0 * 240, (uint32_t)min(kTileRows, keep - r0) * 240u);
+            }
+        }
+        __syncthreads();   // the moves of this segment are consumed before the next segment overwrites them
+    }
+    stat_add(stats, 7, disagree);
+    if (tid == 0) {
+        tma_wait_read<0>();                                 // shared memory must outlive the bulk reads
+        __threadfence();
+        const unsigned int fin = atomicAdd(&ws.h->finished, 1u);
+        if (fin == (unsigned int)nblk - 1) {                // the last CTA of the launch re-arms the workspace
+            ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = sm.epoch + 1;
+            __threadfence();
+        }
     }
 }
 
+// face only (ddz_encode_face): same planes + LUT rows, plain coalesced stores
 template <int V>
 __global__ void __launch_bounds__(kEnvs) k_face(const void* state, float4* __restrict__ face, int B) {
     constexpr int C = FaceCfg<V>::C;
@@ -236,90 +435,14 @@ __global__ void __launch_bounds__(kEnvs) k_face(const void* state, float4* __res
         s_p[tid * 2] = p[0]; s_p[tid * 2 + 1] = p[1];
     }
     __syncthreads();
-    store_face_rows<C>(face + (size_t)b0 * C * 15, min(kEnvs, B - b0), s_planes, s_p);
-}
-
-struct Emitter {
-    uint64_t* out; long long pos, end;
-    DDZ_DEV void operator()(uint64_t mv) { if (pos < end) out[pos] = mv; pos++; }
-};
-
-// V < 0: no face.  RAW: hands/lasts arrays instead of a state.
-template <int V, bool RAW>
-__global__ void __launch_bounds__(kEnvs) k_emit(const void* state, const uint64_t* __restrict__ raw_hands,
-                                                const uint64_t* __restrict__ raw_lasts, Workspace ws,
-                                                int32_t* __restrict__ offsets, uint64_t* actions_u64,
-                                                float4* __restrict__ actions_f32, long long cap,
-                                                float4* __restrict__ face, int64_t* stats, int B) {
-    constexpr int C = FaceCfg<(V < 0 ? 0 : V)>::C;
-    __shared__ int s_scan[kWarps];
-    __shared__ long long s_base;
-    __shared__ uint64_t s_planes[V < 0 ? 1 : kEnvs * C];
-    __shared__ float s_p[V < 0 ? 1 : kEnvs * 2];
-    const int tid = threadIdx.x, b0 = blockIdx.x * kEnvs, b = b0 + tid;
-    const bool valid = b < B;
-    const int nenv = min(kEnvs, B - b0);
-
-    // ---- global offset of this CTA = sum of the totals of the CTAs before it
-    long long part = 0;
-    for (int i = tid; i < (int)blockIdx.x; i += kEnvs) part += ws.blk[i];
-    part = warp_sum_ll(part);
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    if ((tid & 31) == 0 && part) atomicAdd((unsigned long long*)&s_base, (unsigned long long)part);
-    __syncthreads();
-    const long long base = s_base;
-
-    const int n = valid ? ws.counts[b] : 0;
-    int total;
-    const int local = block_exclusive_scan(n, s_scan, &total);
-    const long long off = base + local;
-    if (valid) offsets[b] = (int32_t)off;
-    if (b == B - 1) {
-        offsets[B] = (int32_t)(off + n);
-        if (stats) {
-            atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(off + n));
-            if (off + n > cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
-        }
-    }
-
-    // ---- rule work: one env per thread
-    Env e;
-    if (valid) {
-        uint64_t hand, last;
-        if (RAW) { hand = raw_hands[b]; last = raw_lasts[b]; }
-        else {
-            StateView v = view_of(const_cast<void*>(state), B);
-            e = load_env(v, b);
-            hand = hand_to_move(e); last = trick_of(e);
-        }
-        if (n > 0) {
-            Emitter em{actions_u64, off, cap};
-            enumerate_legal(masks_of(hand), last, em);
-            if (em.pos != off + n && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);  // count/emit disagree
-        }
-        if (V >= 0 && face) {
-            uint64_t pl[C]; float p[2];
-            face_planes<(V < 0 ? 0 : V)>(e, pl, p);
-#pragma unroll
-            for (int c = 0; c < C; c++) s_planes[tid * C + c] = pl[c];
-            s_p[tid * 2] = p[0]; s_p[tid * 2 + 1] = p[1];
-        }
-    }
-    __syncthreads();  // packed moves (global) and planes (shared) of the whole CTA are visible
-
-    // ---- face rows: [nenv][C][15] float4, contiguous for the CTA
-    if (V >= 0 && face) store_face_rows<C>(face + (size_t)b0 * C * 15, nenv, s_planes, s_p);
-    // ---- action rows: [total][15] float4, contiguous for the CTA
-    if (actions_f32) {
-        long long lim = cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;
-        float4* dst = actions_f32 + (size_t)base * 15;
-        const uint64_t* src = actions_u64 + base;
-        const long long nvec = lim * 15;
-        for (long long i = tid; i < nvec; i += kEnvs) {
-            int row = (int)(i / 15), rank = (int)(i - (long long)row * 15);
-            dst[i] = thermo_row(__ldcg(src + row), rank, 1.f);
-        }
+    float4* dst = face + (size_t)b0 * C * 15;
+    const int nvec = min(kEnvs, B - b0) * C * 15;
+    for (int i = tid; i < nvec; i += kEnvs) {
+        int row = i / 15, rank = i - row * 15;
+        int env = row / C, c = row - env * C;
+        float s = (c >= C - 2) ? s_p[env * 2 + (c - (C - 2))] : 1.f;
+        uint32_t cnt = (uint32_t)(s_planes[row] >> (4 * rank)) & 15u;
+        dst[i] = make_float4(cnt > 0 ? s : 0.f, cnt > 1 ? s : 0.f, cnt > 2 ? s : 0.f, cnt > 3 ? s : 0.f);
     }
 }
 
@@ -328,7 +451,8 @@ __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restri
     long long nvec = n * 15;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         long long row = i / 15; int rank = (int)(i - row * 15);
-        out[i] = thermo_row(actions[row], rank, 1.f);
+        uint32_t c = (uint32_t)(actions[row] >> (4 * rank)) & 15u;
+        out[i] = make_float4(c > 0 ? 1.f : 0.f, c > 1 ? 1.f : 0.f, c > 2 ? 1.f : 0.f, c > 3 ? 1.f : 0.f);
     }
 }
 
@@ -350,6 +474,32 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, what);             \
     } while (0)
 
+template <int V, int MODE>
+static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
+                      void* workspace, int64_t* stats, int B, cudaStream_t st) {
+    const size_t smem = (MODE == kStepOnly) ? 0 : sizeof(Smem);
+    if (smem > 48 * 1024) {   // idempotent, cheap; per device, so it is simply repeated
+        cudaError_t e = cudaFuncSetAttribute(k_env<V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
+    k_env<V, MODE><<<nblocks(B), kEnvs, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
+    DDZ_LAUNCH_CHECK("k_env");
+    return 0;
+}
+template <int MODE>
+static int launch_env_v(int variant, bool want_face, void* state, const StepArgs& a, const OutArgs& o, void* workspace,
+                        int64_t* stats, int B, cudaStream_t st) {
+    if (!want_face) return launch_env<-1, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+    switch (variant) {
+        case 0: return launch_env<0, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+        case 1: return launch_env<1, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+        case 2: return launch_env<2, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+        case 3: return launch_env<3, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+    }
+    return DDZ_E_ARG;
+}
+
 extern "C" {
 
 int ddz_abi_version(void) { return DDZ_ABI_VERSION; }
@@ -358,9 +508,7 @@ int ddz_face_channels(int variant) {
     return (variant < 0 || variant > 3) ? DDZ_E_ARG : C[variant];
 }
 size_t ddz_state_bytes(int B) { return B <= 0 ? 0 : (size_t)B * (9 * 8 + 4); }
-size_t ddz_workspace_bytes(int B) {
-    return B <= 0 ? 0 : align_up((size_t)B * 4, 256) + align_up((size_t)nblocks(B) * 4, 256);
-}
+size_t ddz_workspace_bytes(int B) { return B <= 0 ? 0 : 256 + (size_t)nblocks(B) * 8; }
 const char* ddz_last_error(void) { return g_err; }
 
 int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool_games, int only_done,
@@ -371,33 +519,14 @@ int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool
     return 0;
 }
 
-static int launch_emit(const void* state, const uint64_t* hands, const uint64_t* lasts, Workspace ws, int variant,
-                       int32_t* offsets, uint64_t* au, float* af, int64_t cap, float* face, int64_t* stats, int B,
-                       cudaStream_t st) {
-    dim3 g(nblocks(B)), t(kEnvs);
-    float4* af4 = (float4*)af; float4* f4 = (float4*)face;
-    if (hands) k_emit<-1, true><<<g, t, 0, st>>>(nullptr, hands, lasts, ws, offsets, au, af4, cap, nullptr, stats, B);
-    else if (!face) k_emit<-1, false><<<g, t, 0, st>>>(state, nullptr, nullptr, ws, offsets, au, af4, cap, nullptr, stats, B);
-    else switch (variant) {
-        case 0: k_emit<0, false><<<g, t, 0, st>>>(state, nullptr, nullptr, ws, offsets, au, af4, cap, f4, stats, B); break;
-        case 1: k_emit<1, false><<<g, t, 0, st>>>(state, nullptr, nullptr, ws, offsets, au, af4, cap, f4, stats, B); break;
-        case 2: k_emit<2, false><<<g, t, 0, st>>>(state, nullptr, nullptr, ws, offsets, au, af4, cap, f4, stats, B); break;
-        default: k_emit<3, false><<<g, t, 0, st>>>(state, nullptr, nullptr, ws, offsets, au, af4, cap, f4, stats, B); break;
-    }
-    DDZ_LAUNCH_CHECK("k_emit");
-    return 0;
-}
-
 int ddz_observe(const void* state, void* workspace, int variant, int32_t* offsets, uint64_t* actions_u64,
                 float* actions_f32, int64_t cap, float* face, int64_t* stats, int B, void* stream) {
     if (!state || !workspace || !offsets || !actions_u64 || B <= 0 || cap < 0) return DDZ_E_ARG;
     if (face && ddz_face_channels(variant) < 0) return DDZ_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    Workspace ws = ws_of(workspace, B);
     StepArgs a; memset(&a, 0, sizeof a);
-    k_transition<false, false><<<nblocks(B), kEnvs, 0, st>>>(const_cast<void*>(state), nullptr, nullptr, a, ws, stats, B);
-    DDZ_LAUNCH_CHECK("k_transition");
-    return launch_emit(state, nullptr, nullptr, ws, variant, offsets, actions_u64, actions_f32, cap, face, stats, B, st);
+    OutArgs o{offsets, actions_u64, (float4*)actions_f32, cap, (float4*)face};
+    return launch_env_v<kObserve>(variant, face != nullptr, const_cast<void*>(state), a, o, workspace, stats, B,
+                                  (cudaStream_t)stream);
 }
 
 static int fill_step_args(StepArgs& a, const int32_t* offsets, const uint64_t* actions, const void* choice, int mode,
@@ -422,35 +551,8 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
     StepArgs a;
     int rc = fill_step_args(a, offsets, actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
-    Workspace ws; ws.counts = nullptr; ws.blk = nullptr;
-    k_transition<true, false><<<nblocks(B), kEnvs, 0, (cudaStream_t)stream>>>(state, nullptr, nullptr, a, ws, stats, B);
-    DDZ_LAUNCH_CHECK("k_transition");
-    return 0;
-}
-
-int ddz_rollout_step_begin(void* state, void* workspace,
-                           const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
-                           const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
-                           const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
-                           int8_t* r, uint8_t* done, int8_t* cat, float* reward, int64_t* stats, int B, void* stream) {
-    if (!state || !workspace || B <= 0) return DDZ_E_ARG;
-    if (perm && pool_games < 1) return DDZ_E_ARG;
-    StepArgs a;
-    int rc = fill_step_args(a, prev_offsets, prev_actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
-    if (rc) return rc;
-    a.perm = perm; a.lord_pile = lord_pile; a.pool_games = perm ? pool_games : 1;
-    k_transition<true, false><<<nblocks(B), kEnvs, 0, (cudaStream_t)stream>>>(state, nullptr, nullptr, a, ws_of(workspace, B), stats, B);
-    DDZ_LAUNCH_CHECK("k_transition");
-    return 0;
-}
-
-int ddz_rollout_step_end(const void* state, void* workspace, int variant,
-                         int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
-                         float* face, int64_t* stats, int B, void* stream) {
-    if (!state || !workspace || !out_offsets || !out_actions_u64 || B <= 0 || cap < 0) return DDZ_E_ARG;
-    if (face && ddz_face_channels(variant) < 0) return DDZ_E_ARG;
-    return launch_emit(state, nullptr, nullptr, ws_of(workspace, B), variant, out_offsets, out_actions_u64,
-                       out_actions_f32, cap, face, stats, B, (cudaStream_t)stream);
+    OutArgs o{nullptr, nullptr, nullptr, 0, nullptr};
+    return launch_env<-1, kStepOnly>(state, nullptr, nullptr, a, o, nullptr, stats, B, (cudaStream_t)stream);
 }
 
 int ddz_rollout_step(void* state, void* workspace, int variant,
@@ -460,24 +562,24 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
                      int8_t* r, uint8_t* done, int8_t* cat, float* reward,
                      int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
                      float* face, int64_t* stats, int B, void* stream) {
-    if (!out_offsets || !out_actions_u64 || out_offsets == prev_offsets || out_actions_u64 == prev_actions_u64) return DDZ_E_ARG;
+    if (!state || !workspace || !out_offsets || !out_actions_u64 || B <= 0 || cap < 0) return DDZ_E_ARG;
+    if (out_offsets == prev_offsets || out_actions_u64 == prev_actions_u64) return DDZ_E_ARG;
     if (face && ddz_face_channels(variant) < 0) return DDZ_E_ARG;
-    int rc = ddz_rollout_step_begin(state, workspace, prev_offsets, prev_actions_u64, choice, choice_mode, seed, env0,
-                                    stepno, rewards, perm, lord_pile, pool_games, r, done, cat, reward, stats, B, stream);
+    if (perm && pool_games < 1) return DDZ_E_ARG;
+    StepArgs a;
+    int rc = fill_step_args(a, prev_offsets, prev_actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
-    return ddz_rollout_step_end(state, workspace, variant, out_offsets, out_actions_u64, out_actions_f32, cap, face,
-                                stats, B, stream);
+    a.perm = perm; a.lord_pile = lord_pile; a.pool_games = perm ? pool_games : 1;
+    OutArgs o{out_offsets, out_actions_u64, (float4*)out_actions_f32, cap, (float4*)face};
+    return launch_env_v<kStepObserve>(variant, face != nullptr, state, a, o, workspace, stats, B, (cudaStream_t)stream);
 }
 
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,
                     uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream) {
     if (!hands || !lasts || !workspace || !offsets || !actions_u64 || n <= 0 || cap < 0) return DDZ_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    Workspace ws = ws_of(workspace, n);
     StepArgs a; memset(&a, 0, sizeof a);
-    k_transition<false, true><<<nblocks(n), kEnvs, 0, st>>>(nullptr, hands, lasts, a, ws, stats, n);
-    DDZ_LAUNCH_CHECK("k_transition");
-    return launch_emit(nullptr, hands, lasts, ws, -1, offsets, actions_u64, nullptr, cap, nullptr, stats, n, st);
+    OutArgs o{offsets, actions_u64, nullptr, cap, nullptr};
+    return launch_env<-1, kRaw>(nullptr, hands, lasts, a, o, workspace, stats, n, (cudaStream_t)stream);
 }
 
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream) {

@@ -232,31 +232,22 @@ class BatchedEnv:
         """envi.py:72-77: RHCP heuristic opponent -- out of scope for this build."""
         raise NotImplementedError("step_auto (RHCP rule AI of the absent native env) is not part of the hot path")
 
-    def rollout_step(self, choice=None, mode=N.CHOICE_PHILOX, perm=None, lord_pile=None, pool_games=1, mid_event=None):
-        """One fused env-step: apply the chosen move, re-deal finished envs from perm (device int8 [pool*B,54]) when
-        given, and produce face + legal lists of the new state.  Two launches (ddz_rollout_step); mid_event, a
-        torch.cuda.Event, is recorded between them (bench.py times the dominant kernel with it)."""
+    def rollout_step(self, choice=None, mode=N.CHOICE_PHILOX, perm=None, lord_pile=None, pool_games=1):
+        """One fused env-step in ONE launch (ddz_rollout_step): apply the chosen move, re-deal finished envs from perm
+        (device int8 [pool*B,54]) when given, and produce face + legal lists of the new state."""
         self._ensure()
         nxt = 1 - self._cur
         if choice is not None:
             choice = self._to_dev(choice, torch.int64 if mode == N.CHOICE_MOVE else torch.int32)
-        st = self._stream()
         with torch.cuda.device(self.device):
-            step_args = (self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]),
-                         self._p(choice), mode, self.seed, self.env0, self._stepno, self._rewards.data_ptr(),
-                         self._p(perm), self._p(lord_pile), int(pool_games),
-                         self._p(self.r), self._p(self.done), self._p(self.cat), self._p(self.reward))
-            emit_args = (self._p(self._offsets[nxt]), self._p(self._actions_u64[nxt]), self._p(self._actions_f32),
-                         self.cap, self._p(self._face), self._p(self.stats), self.B, st)
-            if mid_event is None:
-                N.check(N.lib.ddz_rollout_step(self._p(self._state), self._p(self._ws), self.VARIANT, *step_args,
-                                               *emit_args), "ddz_rollout_step")
-            else:
-                N.check(N.lib.ddz_rollout_step_begin(self._p(self._state), self._p(self._ws), *step_args,
-                                                     self._p(self.stats), self.B, st), "ddz_rollout_step_begin")
-                mid_event.record(torch.cuda.current_stream(self.device))
-                N.check(N.lib.ddz_rollout_step_end(self._p(self._state), self._p(self._ws), self.VARIANT, *emit_args),
-                        "ddz_rollout_step_end")
+            N.check(N.lib.ddz_rollout_step(
+                self._p(self._state), self._p(self._ws), self.VARIANT,
+                self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]),
+                self._p(choice), mode, self.seed, self.env0, self._stepno, self._rewards.data_ptr(),
+                self._p(perm), self._p(lord_pile), int(pool_games),
+                self._p(self.r), self._p(self.done), self._p(self.cat), self._p(self.reward),
+                self._p(self._offsets[nxt]), self._p(self._actions_u64[nxt]), self._p(self._actions_f32), self.cap,
+                self._p(self._face), self._p(self.stats), self.B, self._stream()), "ddz_rollout_step")
         self._cur, self._fresh, self._n_total = nxt, True, None
         self._stepno += 1
         return self.r, self.done, self.cat
@@ -286,7 +277,7 @@ class BatchedEnv:
 
     def get_last_two_cards(self):
         """int64 [B,2,15]: [previous player's hand-out, the one before]; zeros = pass (envi.py:103)."""
-        rec = self.recent_handout
+        rec = self._recent_t()
         s = self._role()
         ar = torch.arange(self.B, device=self.device)
         return torch.stack([rec[ar, (s + 2) % 3], rec[ar, (s + 1) % 3]], 1)
@@ -296,20 +287,26 @@ class BatchedEnv:
         """cards left per role int64 [B,3] (envi.py:23,39)."""
         return self.hands().sum(-1)
 
+    def _history_t(self):
+        return unpack_counts(self._fields()[0][3:6].t().contiguous())
+
+    def _recent_t(self):
+        return unpack_counts(self._fields()[0][6:9].t().contiguous())
+
     @property
     def history(self):
         """int64 [B,3,15] (envi.py:25,41)."""
-        return unpack_counts(self._fields()[0][3:6].t().contiguous())
+        return self._history_t()
 
     @property
     def taken(self):
         """int64 [B,15] (envi.py:22,40)."""
-        return self.history.sum(1)
+        return self._history_t().sum(1)
 
     @property
     def recent_handout(self):
         """int64 [B,3,15] (envi.py:26,42-43)."""
-        return unpack_counts(self._fields()[0][6:9].t().contiguous())
+        return self._recent_t()
 
     @property
     def is_done(self):
@@ -456,11 +453,11 @@ class Env(BatchedEnv):
 
     @property
     def history(self):
-        return _RoleDict(lambda: BatchedEnv.history.fget(self))
+        return _RoleDict(self._history_t)
 
     @property
     def recent_handout(self):
-        return _RoleDict(lambda: BatchedEnv.recent_handout.fget(self))
+        return _RoleDict(self._recent_t)
 
 
 class EnvComplicated(Env):

@@ -61,7 +61,10 @@ extern "C" {
 int ddz_abi_version(void);
 int ddz_face_channels(int variant);          /* 4 / 7 / 9 / 6, or DDZ_E_ARG */
 size_t ddz_state_bytes(int B);
-size_t ddz_workspace_bytes(int B);           /* scratch for observe / rollout_step / legal_moves (n <= B) */
+/* Scratch for observe / rollout_step / legal_moves (n <= B): tile ticket + one look-back word per CTA.
+ * The caller zero-fills it ONCE after allocation; every launch re-arms it.  One workspace per stream:
+ * two launches that share a workspace must not run concurrently. */
+size_t ddz_workspace_bytes(int B);
 const char* ddz_last_error(void);            /* text of the last CUDA error seen by this thread */
 
 /* env.Env.reset() + prepare()  (envi.py:30-36, game.py:170-171) with host-chosen shuffles:
@@ -90,7 +93,7 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
              int8_t* r, uint8_t* done, int8_t* cat, float* reward, int64_t* stats, int B, void* stream);
 
 /* One fused env-step = ddz_step, then ddz_reset(only_done=1) when perm != NULL, then ddz_observe of the
- * new state, in two launches.  prev_* are the lists of the state being stepped, out_* receive the new
+ * new state, in ONE launch.  prev_* are the lists of the state being stepped, out_* receive the new
  * lists (ping-pong; they must not alias). */
 int ddz_rollout_step(void* state, void* workspace, int variant,
                      const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
@@ -99,18 +102,6 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
                      int8_t* r, uint8_t* done, int8_t* cat, float* reward,
                      int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
                      float* face, int64_t* stats, int B, void* stream);
-
-/* The two launches of ddz_rollout_step as separate calls, so a caller can record a CUDA event between them
- * (bench.py times the dominant kernel this way).  _begin = apply move + re-deal + count; _end = offsets +
- * move lists + encoders.  Calling _begin then _end with the same arguments IS ddz_rollout_step. */
-int ddz_rollout_step_begin(void* state, void* workspace,
-                           const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
-                           const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
-                           const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
-                           int8_t* r, uint8_t* done, int8_t* cat, float* reward, int64_t* stats, int B, void* stream);
-int ddz_rollout_step_end(const void* state, void* workspace, int variant,
-                         int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
-                         float* face, int64_t* stats, int B, void* stream);
 
 /* r.get_moves(hand15, last15) for n independent (hand, last) pairs  (envi.py:111, server/core.py:65):
  * hands/lasts packed uint64[n]; last == 0 means lead.  Same CSR outputs as ddz_observe. */

@@ -272,7 +272,9 @@ def test_state_dict_resume_is_exact(D):
     for _ in range(40):
         a.rollout_step(perm=pd, lord_pile=ld, pool_games=2)
         b.rollout_step(perm=pd, lord_pile=ld, pool_games=2)
-    assert torch.equal(a._state, b._state) and torch.equal(a.face, b.face) and torch.equal(a.stats, b.stats)
+    keep = [0, 1, 2, 3, 4, 5, 6, 7, 9]        # stats[8] (moves emitted) also counts b's extra observe() after the load
+    assert torch.equal(a._state, b._state) and torch.equal(a.face, b.face) and torch.equal(a.stats[keep], b.stats[keep])
+    assert torch.equal(a.offsets, b.offsets) and torch.equal(a.actions_packed, b.actions_packed)
 
 
 def test_full_size_invariants(D, oracle):
@@ -287,7 +289,6 @@ def test_full_size_invariants(D, oracle):
     ref = oracle.RefBatch(len(sample), 2)
     ref.deal(perm.reshape(G, B, 54)[:, sample].reshape(-1, 54), lord.reshape(G, B)[:, sample].reshape(-1), pool_games=G)
     for t in range(130):
-        env.observe() if t == 0 else None
         off = env.offsets.to(torch.int64)
         cnt = off[1:] - off[:-1]
         assert (cnt >= 0).all() and int(off[0]) == 0
@@ -312,8 +313,6 @@ def test_full_size_invariants(D, oracle):
             ref.observe(want_f32=False, want_face=False)
         env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
         # the oracle sample follows the same Philox stream: env ids are the sampled global ids
-        for i, b in enumerate(sample):
-            pass
         ent = np.array([oracle.philox(seed, int(b), t) for b in sample], dtype=np.uint32)
         ref.step(ent.view(np.int32), mode=1)
         ref.deal(perm.reshape(G, B, 54)[:, sample].reshape(-1, 54), lord.reshape(G, B)[:, sample].reshape(-1),
