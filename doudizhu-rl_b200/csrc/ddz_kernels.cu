@@ -1,22 +1,24 @@
 // ddz_kernels.cu -- sm_100a kernels and the C-ABI launchers of libddz_b200.so (see include/ddz_b200.h).
 //
-// k_env<V, MODE> is the whole env-step in ONE launch.  A CTA owns kEnvs consecutive envs (thread t <-> env b0+t for
-// the rule work, the whole CTA for the output):
-//   1. tile ticket (atomic) -> b0; load the packed state (SoA, coalesced)
+// k_env<V, MODE, NBUF> is the whole env-step in ONE launch.  The unit of work is a WARP: warp <-> 32 consecutive envs
+// (lane <-> env for the rule work, the whole warp for the output).  Warps never synchronise with each other; a CTA is
+// only a container of kWarpsPerCta independent warps.
+//   1. tile ticket (atomic) -> first env; load the packed state (SoA, coalesced)
 //   2. [MODE step] pick the move (index / entropy % N / Philox % N / explicit), apply it, terminal + rewards,
 //      [re-deal finished envs from the host-supplied permutation pool], store the state
-//   3. count legal moves (closed form), CTA-wide exclusive scan, publish the CTA total for the decoupled
-//      look-back that turns per-CTA totals into global CSR offsets without a second pass over the state
-//   4. face rows: the C count planes of every env go to shared memory; each thread expands one 240-byte row
-//      (15 x float4 through a 5-entry thermometer LUT) into a 128-row staging tile; one elected thread pushes the
-//      tile to HBM with a TMA bulk store (cp.async.bulk.global.shared::cta) while the CTA fills the other tile
+//   3. count legal moves (closed form: popc x binomial), warp exclusive scan (shfl), publish the warp total for the
+//      decoupled look-back that turns per-warp totals into global CSR offsets without a second pass over the state
+//   4. face rows: the C count planes of every env go to shared memory; each lane expands one 240-byte row
+//      (15 x float4 through a 5-entry thermometer LUT) into a 32-row staging tile; lane 0 pushes the tile to HBM with
+//      a TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP)
 //   5. look-back (its latency is hidden behind 4) -> global base, offsets
-//   6. enumerate the legal moves in canonical order into shared memory (segments of < kMoveCap moves), write
-//      the packed list (coalesced) and the action rows (same tile + TMA path as the face)
+//   6. enumerate the legal moves in canonical order into shared memory (windows of kWin moves), write the packed
+//      list (coalesced) and the action rows (same tile + TMA path as the face)
 // Nothing is re-read from HBM: algorithmic bytes == DRAM traffic (profiles/).
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ddz_b200.h"
@@ -24,24 +26,23 @@
 
 namespace ddz {
 
-constexpr int kEnvs = 128;                       // envs per CTA == threads per CTA
-constexpr int kWarps = kEnvs / 32;
-constexpr int kTileRows = 128;                   // rows (240 B each) per staging tile, one per thread
-constexpr int kSegMoves = 1280;                  // a new segment of envs starts every kSegMoves legal moves ...
-constexpr int kMoveCap = kSegMoves + DDZ_MAX_LEGAL;  // ... so a segment never holds this many (an env has <= 512)
-constexpr int kMaxSegs = kEnvs * DDZ_MAX_LEGAL / kSegMoves + 2;
+constexpr int kThreads = 128;                    // threads per CTA
+constexpr int kWarpsPerCta = kThreads / 32;
+constexpr int kEnvs = kThreads;                  // envs per CTA for the simple thread-per-env kernels
+constexpr int kWin = 320;                        // legal moves staged per window (one warp)
 
 enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
 
-// workspace: header (ticket, finished, epoch) + one look-back word per CTA.  Must be zero when first used.
+// workspace: header (ticket, finished, epoch) + one look-back word per warp tile.  Must be zero when first used.
 struct WsHeader { unsigned int ticket, finished, epoch, pad; };
 struct Workspace { WsHeader* h; unsigned long long* tile; };
+static inline int ntiles(int B) { return (B + 31) / 32; }
 static inline int nblocks(int B) { return (B + kEnvs - 1) / kEnvs; }
 static inline Workspace ws_of(void* p) {
     Workspace w; w.h = (WsHeader*)p; w.tile = (unsigned long long*)((char*)p + 256);
     return w;
 }
-// look-back word: [63:34] epoch, [33:32] status (1 = CTA total, 2 = inclusive prefix), [31:0] value
+// look-back word: [63:34] epoch, [33:32] status (1 = tile total, 2 = inclusive prefix), [31:0] value
 constexpr unsigned long long kAggregate = 1ull << 32, kInclusive = 2ull << 32;
 
 // ------------------------------------------------------------------------------------------------
@@ -74,21 +75,6 @@ DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {
     v = warp_sum_ll(v);
     if ((threadIdx.x & 31) == 0 && v != 0 && stats) atomicAdd((unsigned long long*)&stats[slot], (unsigned long long)v);
 }
-// exclusive scan of one int per thread over the CTA; *total = CTA sum.  smem: int[kWarps]; ends after a barrier
-DDZ_DEV int block_exclusive_scan(int v, int* smem, int* total) {
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) smem[w] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < kWarps; i++) { int s = smem[i]; if (i < w) base += s; tot += s; }
-    *total = tot;
-    return base + inc - v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // deal
 // ------------------------------------------------------------------------------------------------
@@ -173,20 +159,21 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
     p[1] = tot > 0 ? __fdiv_rn((float)size2, (float)tot) : 0.f;
 }
 
-// Staging: two tiles of kTileRows rows.  Every thread fills one row, then one thread issues the bulk store.
+// Staging: NBUF tiles of 32 rows per warp.  Every lane fills one row, then lane 0 issues the bulk store.
+template <int NBUF>
 struct Stager {
-    float4* tiles;   // [2][kTileRows*15]
-    int k;           // tiles issued so far by this CTA
-    DDZ_DEV float4* acquire() {   // all threads
-        // the bulk store issued two tiles ago read this buffer: wait for that read before overwriting it
-        if (threadIdx.x == 0) tma_wait_read<1>();
-        __syncthreads();
-        return tiles + (size_t)(k & 1) * (kTileRows * 15);
+    float4* tiles;   // [NBUF][32*15]
+    int k;           // tiles issued so far by this warp
+    DDZ_DEV float4* acquire() {   // whole warp
+        // the bulk store issued NBUF tiles ago read this buffer: wait for that read before overwriting it
+        if ((threadIdx.x & 31) == 0) tma_wait_read<NBUF - 1>();
+        __syncwarp();
+        return tiles + (size_t)(k % NBUF) * (32 * 15);
     }
-    DDZ_DEV void release(void* gdst, uint32_t bytes) {   // all threads
-        fence_async_smem();        // this thread's generic-proxy smem writes -> visible to the async proxy
-        __syncthreads();
-        if (threadIdx.x == 0) tma_store(gdst, tiles + (size_t)(k & 1) * (kTileRows * 15), bytes);
+    DDZ_DEV void release(void* gdst, uint32_t bytes) {   // whole warp
+        fence_async_smem();        // this lane's generic-proxy smem writes -> visible to the async proxy
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) tma_store(gdst, tiles + (size_t)(k % NBUF) * (32 * 15), bytes);
         k++;
     }
 };
@@ -201,56 +188,51 @@ struct OutArgs {
     int32_t* offsets; uint64_t* actions_u64; float4* actions_f32; long long cap; float4* face;
 };
 
-struct SmemEmitter {      // enumerate_legal functor: packed moves into the CTA's shared segment
-    uint64_t* out; int pos;
-    DDZ_DEV void operator()(uint64_t mv) { out[pos++] = mv; }
+struct WindowEmitter {    // enumerate_legal functor: keeps the moves that fall into the warp's current window
+    uint64_t* out; int pos;   // pos = index of the next move relative to the window start (may be negative)
+    DDZ_DEV void operator()(uint64_t mv) { if ((unsigned)pos < (unsigned)kWin) out[pos] = mv; pos++; }
 };
 
-struct __align__(128) Smem {
-    float4 tiles[2][kTileRows * 15];                        // 61 440 B
+template <int NBUF>
+struct __align__(128) WarpSmem {
+    float4 tiles[NBUF][32 * 15];                            // 7 680 B each
     union {                                                 // the planes are dead before the moves are produced
-        struct { uint64_t planes[kEnvs * 9]; float p[kEnvs * 2]; } f;
-        uint64_t moves[kMoveCap];
+        struct { uint64_t planes[32 * 9]; float p[32 * 2]; } f;
+        uint64_t moves[kWin];
     } u;
     float4 lut[8];
-    int scan[kWarps];
-    int segfirst[kMaxSegs];                                 // local offset of the first move of each segment
-    int tile, nseg;
-    unsigned int epoch;
-    long long base;
 };
-static_assert(sizeof(Smem) <= 76800, "three CTAs per SM need <= 76 800 B of shared memory each");
 
-// V: face variant or -1 (no face).  MODE: see enum Mode.
-template <int V, int MODE>
-__global__ void __launch_bounds__(kEnvs) k_env(void* state, const uint64_t* __restrict__ raw_hands,
-                                               const uint64_t* __restrict__ raw_lasts, StepArgs a, OutArgs o,
-                                               Workspace ws, int64_t* stats, int B) {
+// V: face variant or -1 (no face).  MODE: see enum Mode.  NBUF: staging tiles per warp.
+template <int V, int MODE, int NBUF>
+__global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* __restrict__ raw_hands,
+                                                  const uint64_t* __restrict__ raw_lasts, StepArgs a, OutArgs o,
+                                                  Workspace ws, int64_t* stats, int B) {
     constexpr bool STEP = (MODE == kStepOnly || MODE == kStepObserve);
     constexpr bool EMIT = (MODE != kStepOnly);
     constexpr int C = FaceCfg<(V < 0 ? 0 : V)>::C;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int nblk = gridDim.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpSmem<NBUF>& sm = reinterpret_cast<WarpSmem<NBUF>*>(smem_raw)[wib];
+    const int nt = (B + 31) / 32;
+    const unsigned int nwarps = gridDim.x * kWarpsPerCta;
 
     // ---- 1. tile ticket: tiles are handed out in start order, so every lower tile is already running
-    int t = blockIdx.x;
+    int t = blockIdx.x * kWarpsPerCta + wib;
+    unsigned int epoch = 0;
     if (EMIT) {
-        if (tid == 0) {
-            sm.tile = (int)atomicAdd(&ws.h->ticket, 1u);
-            sm.epoch = ws.h->epoch;
-            sm.nseg = 0;
-        }
-        if (tid < 5) sm.lut[tid] = make_float4(tid > 0 ? 1.f : 0.f, tid > 1 ? 1.f : 0.f, tid > 2 ? 1.f : 0.f, tid > 3 ? 1.f : 0.f);
-        for (int i = tid; i < kMaxSegs; i += kEnvs) sm.segfirst[i] = 0x7FFFFFFF;
-        __syncthreads();
-        t = sm.tile;
+        if (lane == 0) { t = (int)atomicAdd(&ws.h->ticket, 1u); epoch = ws.h->epoch; }
+        t = __shfl_sync(FULL, t, 0);
+        epoch = __shfl_sync(FULL, epoch, 0);
+        if (lane < 5) sm.lut[lane] = make_float4(lane > 0 ? 1.f : 0.f, lane > 1 ? 1.f : 0.f, lane > 2 ? 1.f : 0.f, lane > 3 ? 1.f : 0.f);
+        __syncwarp();
     }
-    const unsigned long long epoch_tag = EMIT ? ((unsigned long long)(sm.epoch & 0x3FFFFFFFu) << 34) : 0ull;
-    const int b0 = t * kEnvs, b = b0 + tid;
+    const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
+    if (t < nt) {
+    const int b0 = t * 32, b = b0 + lane;
     const bool valid = b < B;
-    const int nenv = min(kEnvs, B - b0);
+    const int nenv = min(32, B - b0);
 
     // ---- 2. state transition
     Env e;
@@ -300,120 +282,115 @@ __global__ void __launch_bounds__(kEnvs) k_env(void* state, const uint64_t* __re
         stat_add(stats, 4, d_steps); stat_add(stats, 5, d_retl); stat_add(stats, 6, d_retf); stat_add(stats, 7, d_err);
         stat_add(stats, 9, d_pass);
     }
-    if (!EMIT) return;
+    if (EMIT) {
+    // ---- 3. warp scan, publish the warp total for the look-back
+    int inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
+    const int local = inc - n;
+    const int total = __shfl_sync(FULL, inc, 31);
+    if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | (t == 0 ? kInclusive : kAggregate) | (unsigned int)total);
 
-    // ---- 3. CTA scan, publish the CTA total for the look-back, cut the envs into segments
-    int total;
-    const int local = block_exclusive_scan(n, sm.scan, &total);
-    if (tid == 0) st_relaxed(&ws.tile[t], epoch_tag | (t == 0 ? kInclusive : kAggregate) | (unsigned int)total);
-    // Env i (with moves) belongs to segment local_i / kSegMoves.  Consecutive starts differ by <= 512 < kSegMoves,
-    // so no segment index is skipped and a segment spans < kSegMoves + 512 = kMoveCap moves.
-    const int seg = local / kSegMoves;
-    if (valid && n > 0) { atomicMin(&sm.segfirst[seg], local); atomicMax(&sm.nseg, seg + 1); }
+    Stager<NBUF> stg{&sm.tiles[0][0], 0};
 
-    Stager stg{&sm.tiles[0][0], 0};
-
-    // ---- 4. face rows
+    // ---- 4. face rows: [nenv][C] rows of 240 B, contiguous for the warp
     if (V >= 0 && o.face) {
         if (valid) {
             uint64_t pl[C]; float p[2];
             face_planes<(V < 0 ? 0 : V)>(e, pl, p);
 #pragma unroll
-            for (int c = 0; c < C; c++) sm.u.f.planes[tid * C + c] = pl[c];
-            sm.u.f.p[tid * 2] = p[0]; sm.u.f.p[tid * 2 + 1] = p[1];
+            for (int c = 0; c < C; c++) sm.u.f.planes[lane * C + c] = pl[c];
+            sm.u.f.p[lane * 2] = p[0]; sm.u.f.p[lane * 2 + 1] = p[1];
         }
-        __syncthreads();
+        __syncwarp();
         const int nrows = nenv * C;
         char* gface = reinterpret_cast<char*>(o.face) + (size_t)b0 * C * 240;
-        for (int r0 = 0; r0 < nrows; r0 += kTileRows) {
+        for (int r0 = 0; r0 < nrows; r0 += 32) {
             float4* tile = stg.acquire();
-            const int row = r0 + tid;
+            const int row = r0 + lane;
             if (row < nrows) {
                 const int env = row / C, c = row - env * C;
                 const float s = (c >= C - 2) ? sm.u.f.p[env * 2 + (c - (C - 2))] : 1.f;
-                fill_row<true>(tile + tid * 15, sm.u.f.planes[row], s, sm.lut);
+                fill_row<true>(tile + lane * 15, sm.u.f.planes[row], s, sm.lut);
             }
-            stg.release(gface + (size_t)r0 * 240, (uint32_t)min(kTileRows, nrows - r0) * 240u);
+            stg.release(gface + (size_t)r0 * 240, (uint32_t)min(32, nrows - r0) * 240u);
         }
     }
 
-    // ---- 5. look-back for the global base (warp 0); its predecessors published long ago
-    if (tid < 32) {
-        long long prefix = 0;
-        if (t > 0) {
-            int p = t - 1;                                  // walk the predecessors 32 at a time
-            unsigned int spins = 0;
-            bool finished = false;
-            while (!finished) {
-                const int idx = p - tid;
-                unsigned long long w = 0;
-                bool ok = true;
-                if (idx >= 0) {
-                    w = ld_relaxed(&ws.tile[idx]);
-                    ok = ((w >> 34) == (epoch_tag >> 34)) && ((w >> 32) & 3ull) != 0;
-                }
-                if (__all_sync(0xFFFFFFFFu, ok)) {
-                    const bool inc = idx >= 0 && ((w >> 32) & 3ull) == 2ull;
-                    const unsigned int incmask = __ballot_sync(0xFFFFFFFFu, inc);
-                    // lanes up to and including the nearest inclusive predecessor contribute
-                    const int stop = incmask ? (__ffs(incmask) - 1) : 31;
-                    const long long v = (idx >= 0 && tid <= stop) ? (long long)(unsigned int)w : 0;
-                    prefix += warp_sum_ll(v);
-                    if (incmask || p - 32 < 0) finished = true;
-                    p -= 32;
-                } else if (++spins > (1u << 24)) {          // never hang the GPU: flag the error and carry on
-                    if (tid == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
+    // ---- 5. look-back for the global base; the predecessors published long ago
+    long long base = 0;
+    if (t > 0) {
+        int p = t - 1;                                      // walk the predecessors 32 at a time
+        unsigned int spins = 0;
+        bool finished = false;
+        while (!finished) {
+            const int idx = p - lane;
+            unsigned long long w = 0;
+            bool ok = true;
+            if (idx >= 0) {
+                w = ld_relaxed(&ws.tile[idx]);
+                ok = ((w >> 34) == (epoch_tag >> 34)) && ((w >> 32) & 3ull) != 0;
+            }
+            if (__all_sync(FULL, ok)) {
+                const bool incl = idx >= 0 && ((w >> 32) & 3ull) == 2ull;
+                const unsigned int incmask = __ballot_sync(FULL, incl);
+                // lanes up to and including the nearest inclusive predecessor contribute
+                const int stop = incmask ? (__ffs(incmask) - 1) : 31;
+                const long long v = (idx >= 0 && lane <= stop) ? (long long)(unsigned int)w : 0;
+                base += warp_sum_ll(v);
+                if (incmask || p - 32 < 0) finished = true;
+                p -= 32;
+            } else {
+                __nanosleep(64);
+                if (++spins > (1u << 22)) {                 // never hang the GPU: flag the error and carry on
+                    if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
                     finished = true;
                 }
             }
-            if (tid == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(prefix + total));
         }
-        if (tid == 0) sm.base = prefix;
+        if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
     }
-    __syncthreads();   // base, segfirst, nseg visible; the face planes are dead: the union now holds moves
-    const long long base = sm.base;
     if (valid) o.offsets[b] = (int32_t)(base + local);
-    if (t == nblk - 1 && tid == 0) {
+    if (t == nt - 1 && lane == 0) {
         o.offsets[B] = (int32_t)(base + total);
         if (stats) {
             atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
             if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
         }
     }
-    long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this CTA that fit
+    long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
 
-    // ---- 6. per segment: enumerate into shared memory, then packed list + one-hot rows out
-    const int nseg = sm.nseg;
+    // ---- 6. windows of kWin moves: enumerate into shared memory, then packed list + one-hot rows out
     int disagree = 0;
-    for (int k = 0; k < nseg; k++) {
-        const int first = sm.segfirst[k];
-        const int seg_end = (k + 1 < nseg) ? sm.segfirst[k + 1] : total;
-        if (valid && n > 0 && seg == k) {
-            SmemEmitter em{sm.u.moves, local - first};
+    for (int w0 = 0; w0 < total; w0 += kWin) {
+        if (n > 0 && local < w0 + kWin && local + n > w0) {
+            WindowEmitter em{sm.u.moves, local - w0};
             enumerate_legal(masks_of(hand), last, em);
-            disagree |= (em.pos != local - first + n);
+            disagree |= (em.pos != local - w0 + n);
         }
-        __syncthreads();
-        const int keep = (int)max(0ll, min((long long)(seg_end - first), lim - first));
-        for (int i = tid; i < keep; i += kEnvs) o.actions_u64[base + first + i] = sm.u.moves[i];   // coalesced
+        __syncwarp();
+        const int keep = (int)max(0ll, min((long long)min(kWin, total - w0), lim - w0));
+        for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = sm.u.moves[i];   // coalesced
         if (o.actions_f32) {
-            char* gact = reinterpret_cast<char*>(o.actions_f32) + (size_t)(base + first) * 240;
-            for (int r0 = 0; r0 < keep; r0 += kTileRows) {
+            char* gact = reinterpret_cast<char*>(o.actions_f32) + (size_t)(base + w0) * 240;
+            for (int r0 = 0; r0 < keep; r0 += 32) {
                 float4* tile = stg.acquire();
-                const int row = r0 + tid;
-                if (row < keep) fill_row<false>(tile + tid * 15, sm.u.moves[row], 1.f, sm.lut);
-                stg.release(gact + (size_t)r0 * 240, (uint32_t)min(kTileRows, keep - r0) * 240u);
+                const int row = r0 + lane;
+                if (row < keep) fill_row<false>(tile + lane * 15, sm.u.moves[row], 1.f, sm.lut);
+                stg.release(gact + (size_t)r0 * 240, (uint32_t)min(32, keep - r0) * 240u);
             }
         }
-        __syncthreads();   // the moves of this segment are consumed before the next segment overwrites them
+        __syncwarp();      // the moves of this window are consumed before the next window overwrites them
     }
     stat_add(stats, 7, disagree);
-    if (tid == 0) {
+    }  // EMIT
+    }  // t < nt
+    if (EMIT && lane == 0) {
         tma_wait_read<0>();                                 // shared memory must outlive the bulk reads
         __threadfence();
         const unsigned int fin = atomicAdd(&ws.h->finished, 1u);
-        if (fin == (unsigned int)nblk - 1) {                // the last CTA of the launch re-arms the workspace
-            ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = sm.epoch + 1;
+        if (fin == nwarps - 1) {                            // the last warp of the launch re-arms the workspace
+            ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = epoch + 1;
             __threadfence();
         }
     }
@@ -474,18 +451,34 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, what);             \
     } while (0)
 
-template <int V, int MODE>
-static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
-                      void* workspace, int64_t* stats, int B, cudaStream_t st) {
-    const size_t smem = (MODE == kStepOnly) ? 0 : sizeof(Smem);
-    if (smem > 48 * 1024) {   // idempotent, cheap; per device, so it is simply repeated
-        cudaError_t e = cudaFuncSetAttribute(k_env<V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static int g_nbuf = 0;   // staging tiles per warp: 1 (more warps per SM) or 2 (double-buffered); DDZ_NBUF overrides
+static int nbuf() {
+    if (g_nbuf == 0) {
+        const char* s = getenv("DDZ_NBUF");
+        g_nbuf = (s && atoi(s) == 2) ? 2 : 1;
+    }
+    return g_nbuf;
+}
+
+template <int V, int MODE, int NBUF>
+static int launch_env_n(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
+                        void* workspace, int64_t* stats, int B, cudaStream_t st) {
+    const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem<NBUF>);
+    if (smem > 48 * 1024) {   // idempotent and cheap; per device, so it is simply repeated
+        cudaError_t e = cudaFuncSetAttribute(k_env<V, MODE, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
     }
     Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
-    k_env<V, MODE><<<nblocks(B), kEnvs, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
+    const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_env<V, MODE, NBUF><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
     DDZ_LAUNCH_CHECK("k_env");
     return 0;
+}
+template <int V, int MODE>
+static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
+                      void* workspace, int64_t* stats, int B, cudaStream_t st) {
+    if (MODE != kStepOnly && nbuf() == 2) return launch_env_n<V, MODE, 2>(state, hands, lasts, a, o, workspace, stats, B, st);
+    return launch_env_n<V, MODE, 1>(state, hands, lasts, a, o, workspace, stats, B, st);
 }
 template <int MODE>
 static int launch_env_v(int variant, bool want_face, void* state, const StepArgs& a, const OutArgs& o, void* workspace,
@@ -508,7 +501,7 @@ int ddz_face_channels(int variant) {
     return (variant < 0 || variant > 3) ? DDZ_E_ARG : C[variant];
 }
 size_t ddz_state_bytes(int B) { return B <= 0 ? 0 : (size_t)B * (9 * 8 + 4); }
-size_t ddz_workspace_bytes(int B) { return B <= 0 ? 0 : 256 + (size_t)nblocks(B) * 8; }
+size_t ddz_workspace_bytes(int B) { return B <= 0 ? 0 : 256 + (size_t)ntiles(B) * 8; }
 const char* ddz_last_error(void) { return g_err; }
 
 int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool_games, int only_done,

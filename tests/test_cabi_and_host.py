@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert [D.native.lib.ddz_face_channels(v) for v in range(4)] == [4, 7, 9, 6]
     assert D.native.lib.ddz_face_channels(4) == D.native.E_ARG
     assert D.native.lib.ddz_state_bytes(1000) == 1000 * 76 and D.native.lib.ddz_state_bytes(0) == 0
-    assert D.native.lib.ddz_workspace_bytes(4096) == 256 + 8 * 32
+    assert D.native.lib.ddz_workspace_bytes(4096) == 256 + 8 * 128
 
 
 def test_sass_is_sm100a_only():
