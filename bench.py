@@ -188,20 +188,30 @@ def run_ours(args):
     if int(env.stats[7].item()):
         raise SystemExit("env reported errors during warm-up")
 
-    # ---------------- timed region: device-resident inputs, CUDA events on the launching (current) stream
+    # ---------------- timed region: device-resident inputs, CUDA events on the launching (current) stream.
+    # The rollout loop is launch-bound from Python (~0.15 ms of host work per step), so the ping-pong pair of
+    # launches is captured in a CUDA graph and replayed; an odd K ends with one eager step.
+    graphed = D.GraphedRollout(env, perm_d, lord_d, G)
+    for _ in range(max(W, 3)):
+        graphed.replay()
+    torch.cuda.synchronize(dev)
     stats0 = env.stats.clone()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    nrep = K // 2
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(nrep + 2)]
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     ev[0].record()
-    for k in range(K):
-        env.rollout_step(**step_kw)         # one launch: k_env<cooperation, step+observe>
+    for k in range(nrep):
+        graphed.replay()                    # two launches of k_env<cooperation, step+observe>
         ev[k + 1].record()
+    if K % 2:
+        env.rollout_step(**step_kw)
+    ev[nrep + 1].record()
     barrier()
     clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[K])
-    kern_ms = sum(ev[k].elapsed_time(ev[k + 1]) for k in range(K)) / K   # the kernel's average launch duration
+    total_ms = ev[0].elapsed_time(ev[nrep + 1])
+    kern_ms = total_ms / K                  # average launch duration of the one kernel of a step (gaps included)
     dstats_t = (env.stats - stats0).clone()
     dstats = dstats_t.cpu().numpy()
     if int(env.stats[7].item()):
@@ -209,6 +219,16 @@ def run_ours(args):
     local_steps = int(dstats[4])
     assert local_steps == B * K, (local_steps, B * K)   # every env applied one move per step (finished ones re-dealt)
     nbar = float(dstats[8]) / local_steps
+
+    # ---------------- for information: the same K steps launched one by one from Python (host-bound)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    g0.record()
+    for _ in range(K):
+        env.rollout_step(**step_kw)
+    g1.record()
+    torch.cuda.synchronize(dev)
+    eager_ms = g0.elapsed_time(g1) / K
 
     # ---------------- e2e: same step through the public API with HOST buffers (pinned) every step
     R = 4
@@ -267,6 +287,7 @@ def run_ours(args):
                                    "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % B,
                        "envs_per_gpu": B, "face_channels": CHANNELS, "mean_legal_moves": nbar,
                        "prefill_steps": args.prefill, "pool_games": G, "parallelism": "env-shard x%d" % world,
+                       "launch": "CUDA graph replay of the 2-launch ping-pong pair", "eager_python_ms_per_step": eager_ms,
                        "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
                        "games_finished": int(gstats[0].item()),
                        "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))},

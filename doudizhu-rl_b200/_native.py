@@ -6,12 +6,13 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libddz_b200.so")
+LIB_PATH = os.environ.get("DDZ_LIB") or os.path.join(HERE, "libddz_b200.so")   # DDZ_LIB: developer builds
 
 E_ARG, E_CUDA = -1, -2
 FACE_FIRST, FACE_COMPLICATED, FACE_COOPERATION, FACE_SIMPLIFY = range(4)
 CHOICE_INDEX, CHOICE_MOD, CHOICE_PHILOX, CHOICE_MOVE = range(4)
 MAX_LEGAL = 512
+STEPNO_AUTO = 0xFFFFFFFF
 ABI_VERSION = 1
 
 if not os.path.exists(LIB_PATH):

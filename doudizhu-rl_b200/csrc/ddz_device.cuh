@@ -264,6 +264,135 @@ DDZ_DEV void enumerate_legal(const Masks& m, uint64_t last, F& f) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// warp-cooperative enumeration of ONE env (same list, same order), for envs with many legal moves.
+// All 32 lanes walk the canonical group sequence with identical control flow; a group of c moves starting at
+// list index `off` is expanded by the lanes in parallel (lane j -> j-th set bit / j-th chunk of the kicker
+// combinations, found by unranking), and f(index, packed_move) stores it.  A thread-per-env enumeration of a
+// 300-move hand is a 300-step dependent chain in one lane; this makes it ~10 steps per lane.
+// ------------------------------------------------------------------------------------------------
+DDZ_DEV uint32_t nth_bit(uint32_t mask, int j) { return 1u << __fns(mask, 0, j + 1); }   // j-th set bit (0-based)
+
+// idx-th k-subset of S in lexicographic order
+DDZ_DEV uint32_t unrank_combo(uint32_t S, int k, int idx) {
+    uint32_t out = 0;
+    int n = __popc(S);
+    for (int i = 0; i < k; i++) {
+        for (;;) {
+            const int c = binom(n - 1, k - i - 1);     // subsets whose next element is the lowest one left
+            const uint32_t low = S & (0u - S);
+            S ^= low; n--;
+            if (idx < c) { out |= low; break; }
+            idx -= c;
+        }
+    }
+    return out;
+}
+// c kicker sets of size k out of S for one main group, split into 32 contiguous chunks
+template <class F>
+DDZ_DEV void coop_kicker_sets(uint32_t main, uint32_t mult, uint32_t S, int k, uint32_t kmult, int off, int lane, F& f) {
+    const int c = binom(__popc(S), k);
+    const int per = (c + 31) >> 5;
+    const int i0 = lane * per, i1 = min(c, i0 + per);
+    if (i0 >= i1) return;
+    const uint64_t base = pack_move(main, mult, 0, 0);
+    uint32_t combo = unrank_combo(S, k, i0);
+    for (int i = i0; i < i1; i++) { f(off + i, base + pack_move(combo, kmult, 0, 0)); combo = next_combo(combo, S); }
+}
+template <int MULT, class F>
+DDZ_DEV int coop_ranks(uint32_t mask, int off, int lane, F& f) {
+    const int c = __popc(mask);
+    if (lane < c) f(off + lane, pack_move(nth_bit(mask, lane), MULT, 0, 0));
+    return c;
+}
+template <class F>
+DDZ_DEV int coop_main_plus_one(uint32_t mains, uint32_t kicksrc, uint32_t kmult, int off, int lane, F& f) {
+    const int nm = __popc(mains), nk = __popc(kicksrc) - 1;   // every main rank is itself in kicksrc
+    const int c = nm * nk;
+    for (int i = lane; i < c; i += 32) {
+        const int mi = i / nk, ki = i - mi * nk;
+        const uint32_t main = nth_bit(mains, mi);
+        f(off + i, pack_move(main, 3, nth_bit(kicksrc & ~main, ki), kmult));
+    }
+    return c;
+}
+template <int MULT, int LMIN, int LMAX, class F>
+DDZ_DEV int coop_lines(uint32_t src, const Rule& ru, int cat, int off, int lane, F& f) {
+    const uint32_t R = src & kLineMask;
+    uint32_t t = R;
+#pragma unroll
+    for (int L = 2; L <= LMIN; L++) t &= R >> (L - 1);
+    t &= ru.from(cat);
+    const bool same = !ru.lead && cat == ru.cat;
+    int n = 0;
+    while (t) {                                            // uniform: every lane sees the same starts
+        const int s = __ffs(t) - 1; t &= t - 1;
+        const int run = __ffs(~(R >> s)) - 1;              // length of the run of ones starting at s
+        const int maxL = min(run, LMAX);
+        const int c = same ? ((ru.len >= LMIN && ru.len <= maxL) ? 1 : 0) : (maxL - LMIN + 1);
+        if (lane < c) {
+            const int L = same ? ru.len : LMIN + lane;
+            f(off + n + lane, pack_move(((1u << L) - 1u) << s, MULT, 0, 0));
+        }
+        n += c;
+    }
+    return n;
+}
+template <int LMAX, int KMULT, class F>
+DDZ_DEV int coop_planes(uint32_t g3, uint32_t kicksrc, const Rule& ru, int cat, int off, int lane, F& f) {
+    const uint32_t R = g3 & kLineMask;
+    uint32_t t = R & (R >> 1) & ru.from(cat);
+    int n = 0;
+    while (t) {
+        const int s = __ffs(t) - 1; t &= t - 1;
+        uint32_t run = 3u << s;
+        for (int L = 2; L <= LMAX; L++) {
+            if ((R & run) != run) break;
+            if (ru.len_ok(cat, L)) {
+                const uint32_t S = kicksrc & ~run;
+                coop_kicker_sets(run, 3, S, L, KMULT, off + n, lane, f);
+                n += binom(__popc(S), L);
+            }
+            run |= run << 1;
+        }
+    }
+    return n;
+}
+template <int KMULT, class F>
+DDZ_DEV int coop_four_two(uint32_t mains, uint32_t kicksrc, int off, int lane, F& f) {
+    int n = 0;
+    while (mains) {
+        const uint32_t b = mains & (0u - mains); mains ^= b;
+        const uint32_t S = kicksrc & ~b;
+        coop_kicker_sets(b, 4, S, 2, KMULT, off + n, lane, f);
+        n += binom(__popc(S), 2);
+    }
+    return n;
+}
+// returns the number of moves (must equal count_legal); f(index, move) is called once per move by some lane
+template <class F>
+DDZ_DEV int enumerate_legal_warp(const Masks& m, uint64_t last, int lane, F& f) {
+    if (m.g1 == 0) { if (last && lane == 0) f(0, 0ull); return last ? 1 : 0; }
+    const Rule ru = rule_of(last);
+    int off = 0;
+    if (!ru.lead) { if (lane == 0) f(0, 0ull); off = 1; }
+    if (ru.allowed(1)) off += coop_ranks<1>(m.g1 & ru.from(1), off, lane, f);
+    if (ru.allowed(2)) off += coop_ranks<2>(m.g2 & ru.from(2), off, lane, f);
+    if (ru.allowed(3)) off += coop_ranks<3>(m.g3 & ru.from(3), off, lane, f);
+    if (ru.allowed(4)) off += coop_ranks<4>(m.g4 & ru.from(4), off, lane, f);
+    if (ru.allowed(5)) off += coop_main_plus_one(m.g3 & ru.from(5), m.g1, 1, off, lane, f);
+    if (ru.allowed(6)) off += coop_main_plus_one(m.g3 & ru.from(6), m.g2, 2, off, lane, f);
+    if (ru.allowed(7)) off += coop_lines<1, 5, 12>(m.g1, ru, 7, off, lane, f);
+    if (ru.allowed(8)) off += coop_lines<2, 3, 10>(m.g2, ru, 8, off, lane, f);
+    if (ru.allowed(9)) off += coop_lines<3, 2, 6>(m.g3, ru, 9, off, lane, f);
+    if (ru.allowed(10)) off += coop_planes<5, 1>(m.g3, m.g1, ru, 10, off, lane, f);
+    if (ru.allowed(11)) off += coop_planes<4, 2>(m.g3, m.g2, ru, 11, off, lane, f);
+    if (ru.allowed(12) && (m.g1 & kRocket) == kRocket) { if (lane == 0) f(off, pack_move(kRocket, 1, 0, 0)); off++; }
+    if (ru.allowed(13)) off += coop_four_two<1>(m.g4 & ru.from(13), m.g1, off, lane, f);
+    if (ru.allowed(14)) off += coop_four_two<2>(m.g4 & ru.from(14), m.g2, off, lane, f);
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10, counter (env_lo, env_hi, step, 0), key (seed_lo, seed_hi): the action-index stream
 // ------------------------------------------------------------------------------------------------
 DDZ_DEV uint32_t philox(uint64_t seed, uint64_t env, uint32_t step) {

@@ -1,6 +1,6 @@
 // ddz_kernels.cu -- sm_100a kernels and the C-ABI launchers of libddz_b200.so (see include/ddz_b200.h).
 //
-// k_env<V, MODE, NBUF> is the whole env-step in ONE launch.  The unit of work is a WARP: warp <-> 32 consecutive envs
+// k_env<V, MODE> is the whole env-step in ONE launch.  The unit of work is a WARP: warp <-> 32 consecutive envs
 // (lane <-> env for the rule work, the whole warp for the output).  Warps never synchronise with each other; a CTA is
 // only a container of kWarpsPerCta independent warps.
 //   1. tile ticket (atomic) -> first env; load the packed state (SoA, coalesced)
@@ -8,13 +8,16 @@
 //      [re-deal finished envs from the host-supplied permutation pool], store the state
 //   3. count legal moves (closed form: popc x binomial), warp exclusive scan (shfl), publish the warp total for the
 //      decoupled look-back that turns per-warp totals into global CSR offsets without a second pass over the state
-//   4. face rows: the C count planes of every env go to shared memory; each lane expands one 240-byte row
-//      (15 x float4 through a 5-entry thermometer LUT) into a 32-row staging tile; lane 0 pushes the tile to HBM with
-//      a TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP)
+//   4. face rows: the C count planes of every env go to shared memory; lanes 0..29 are (row parity, rank) pairs, so
+//      one warp instruction writes two whole 240-byte rows as 30 coalesced 128-bit streaming stores (st.global.cs),
+//      each value coming from a 5-entry thermometer LUT
 //   5. look-back (its latency is hidden behind 4) -> global base, offsets
 //   6. enumerate the legal moves in canonical order into shared memory (windows of kWin moves), write the packed
-//      list (coalesced) and the action rows (same tile + TMA path as the face)
-// Nothing is re-read from HBM: algorithmic bytes == DRAM traffic (profiles/).
+//      list (coalesced) and the action rows (same row writer as the face)
+// Stores are fire-and-forget: no staging tiles, no waits.  Nothing is re-read from HBM: algorithmic bytes == DRAM
+// traffic (profiles/).  Two earlier variants that staged rows in shared memory and pushed them with TMA bulk stores
+// (cp.async.bulk) measured slower (profiles/r1b*, r1c*): the path is nowhere near issue-bound, what it
+// needs is many independent warps with stores in flight and no synchronisation.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -30,11 +33,14 @@ constexpr int kThreads = 128;                    // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr int kEnvs = kThreads;                  // envs per CTA for the simple thread-per-env kernels
 constexpr int kWin = 320;                        // legal moves staged per window (one warp)
+constexpr int kMinCtasPerSm = 7;                 // 28 warps per SM (one wave at 131 072 envs): <= 72 registers
+constexpr int kHeavy = 32;                       // envs with more legal moves than this are expanded by the whole warp
+constexpr int kLookBack = 4;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
 
 enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
 
 // workspace: header (ticket, finished, epoch) + one look-back word per warp tile.  Must be zero when first used.
-struct WsHeader { unsigned int ticket, finished, epoch, pad; };
+struct WsHeader { unsigned int ticket, finished, epoch, auto_step; };
 struct Workspace { WsHeader* h; unsigned long long* tile; };
 static inline int ntiles(int B) { return (B + 31) / 32; }
 static inline int nblocks(int B) { return (B + kEnvs - 1) / kEnvs; }
@@ -48,15 +54,6 @@ constexpr unsigned long long kAggregate = 1ull << 32, kInclusive = 2ull << 32;
 // ------------------------------------------------------------------------------------------------
 // small PTX wrappers
 // ------------------------------------------------------------------------------------------------
-DDZ_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-DDZ_DEV void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {   // bytes % 16 == 0, both 16-B aligned
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-DDZ_DEV void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-DDZ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DDZ_DEV unsigned long long ld_relaxed(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -65,6 +62,19 @@ DDZ_DEV unsigned long long ld_relaxed(const unsigned long long* p) {
 DDZ_DEV void st_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+#ifdef DDZ_TRACE
+// developer build only (profiles/trace_phases.py): per-warp phase timestamps, 8 x uint64 per tile
+__device__ unsigned long long* g_trace = nullptr;
+DDZ_DEV void trace(int tile, int slot) {
+    if (g_trace && (threadIdx.x & 31) == 0) {
+        unsigned long long ts; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ts));
+        g_trace[(size_t)tile * 8 + slot] = ts;
+    }
+}
+#else
+DDZ_DEV void trace(int, int) {}
+#endif
 
 DDZ_DEV long long warp_sum_ll(long long v) {
 #pragma unroll
@@ -107,21 +117,51 @@ __global__ void __launch_bounds__(kEnvs) k_reset(void* state, const int8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// thermometer rows (envi.py:140-146) through a 5-entry LUT in shared memory
+// thermometer rows (envi.py:140-146): 240-byte rows of 15 float4, rank k -> {c>0, c>1, c>2, c>3} * s
 // ------------------------------------------------------------------------------------------------
-// one row = 15 float4: rank k -> {c>0, c>1, c>2, c>3} * s, c = nibble k of `packed`
-template <bool SCALED>
-DDZ_DEV void fill_row(float4* __restrict__ row, uint64_t packed, float s, const float4* __restrict__ lut) {
-    const uint32_t lo = (uint32_t)packed, hi = (uint32_t)(packed >> 32);
-#pragma unroll
-    for (int k = 0; k < 15; k++) {
-        const uint32_t w = (k < 8) ? lo : hi;
-        const int sh = 4 * (k & 7);
-        const uint32_t off = (sh == 0) ? ((w << 4) & 0xF0u) : ((w >> (sh - 4)) & 0xF0u);   // count * 16 bytes
-        float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(lut) + off);
-        if (SCALED) { q.x *= s; q.y *= s; q.z *= s; q.w *= s; }
-        row[k] = q;
+// Lane l < 30 owns rank k = l % 15 of the rows with parity l / 15: one warp store instruction covers two complete
+// rows (480 contiguous bytes).  The nibble position is a per-lane constant, the row index an immediate.
+struct RowLane {
+    int first;        // 0 or 1: first row of this lane; huge for the parked lanes 30, 31
+    int k;            // rank
+    uint32_t sh;      // shift of the rank's nibble inside its 32-bit half, pre-scaled to a LUT byte offset
+    bool hi;          // rank >= 8 -> upper half of the packed word
+    DDZ_DEV static RowLane make(int lane) {
+        RowLane r; r.first = lane / 15; r.k = lane - 15 * r.first; r.hi = r.k >= 8; r.sh = 4u * (uint32_t)(r.k & 7);
+        if (lane >= 30) { r.first = 0x3FFFFFFF; r.k = 0; }   // parked: the row loops never run
+        return r;
     }
+    DDZ_DEV const float4& thermo(uint64_t packed, const float4* lut) const {
+        const uint32_t w = hi ? (uint32_t)(packed >> 32) : (uint32_t)packed;
+        return lut[(w >> sh) & 15u];
+    }
+};
+struct FaceRow { uint64_t packed; float s; float pad; };   // 16 B: one LDS.128 per store
+
+// rows [0, nrows) of the warp's contiguous block starting at gdst; src(r) yields the packed counts (and scale)
+template <class RowT>
+DDZ_DEV void write_rows(float4* __restrict__ gdst, int nrows, const RowLane& rl, const float4* __restrict__ lut,
+                        const RowT* __restrict__ rows);
+template <>
+DDZ_DEV void write_rows<FaceRow>(float4* __restrict__ gdst, int nrows, const RowLane& rl, const float4* __restrict__ lut,
+                                 const FaceRow* __restrict__ rows) {
+    float4* dst = gdst + (rl.first & 1) * 15 + rl.k;
+#pragma unroll 4
+    for (int r = rl.first; r < nrows; r += 2, dst += 30) {
+        const float4 raw = *reinterpret_cast<const float4*>(&rows[r]);
+        const uint64_t packed = ((uint64_t)__float_as_uint(raw.y) << 32) | __float_as_uint(raw.x);
+        const float s = raw.z;
+        float4 q = rl.thermo(packed, lut);
+        q.x *= s; q.y *= s; q.z *= s; q.w *= s;
+        __stcs(dst, q);
+    }
+}
+template <>
+DDZ_DEV void write_rows<uint64_t>(float4* __restrict__ gdst, int nrows, const RowLane& rl, const float4* __restrict__ lut,
+                                  const uint64_t* __restrict__ rows) {
+    float4* dst = gdst + (rl.first & 1) * 15 + rl.k;
+#pragma unroll 4
+    for (int r = rl.first; r < nrows; r += 2, dst += 30) __stcs(dst, rl.thermo(rows[r], lut));
 }
 
 template <int V> struct FaceCfg;
@@ -159,25 +199,6 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
     p[1] = tot > 0 ? __fdiv_rn((float)size2, (float)tot) : 0.f;
 }
 
-// Staging: NBUF tiles of 32 rows per warp.  Every lane fills one row, then lane 0 issues the bulk store.
-template <int NBUF>
-struct Stager {
-    float4* tiles;   // [NBUF][32*15]
-    int k;           // tiles issued so far by this warp
-    DDZ_DEV float4* acquire() {   // whole warp
-        // the bulk store issued NBUF tiles ago read this buffer: wait for that read before overwriting it
-        if ((threadIdx.x & 31) == 0) tma_wait_read<NBUF - 1>();
-        __syncwarp();
-        return tiles + (size_t)(k % NBUF) * (32 * 15);
-    }
-    DDZ_DEV void release(void* gdst, uint32_t bytes) {   // whole warp
-        fence_async_smem();        // this lane's generic-proxy smem writes -> visible to the async proxy
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) tma_store(gdst, tiles + (size_t)(k % NBUF) * (32 * 15), bytes);
-        k++;
-    }
-};
-
 struct StepArgs {
     const int32_t* offsets; const uint64_t* actions; const void* choice; int mode;
     uint64_t seed, env0; uint32_t stepno; int32_t rewards[3];
@@ -193,19 +214,20 @@ struct WindowEmitter {    // enumerate_legal functor: keeps the moves that fall 
     DDZ_DEV void operator()(uint64_t mv) { if ((unsigned)pos < (unsigned)kWin) out[pos] = mv; pos++; }
 };
 
-template <int NBUF>
+struct IndexedWindowEmitter {   // enumerate_legal_warp functor: move number idx of the env goes to window slot base + idx
+    uint64_t* out; int base;
+    DDZ_DEV void operator()(int idx, uint64_t mv) { const unsigned rel = (unsigned)(base + idx); if (rel < (unsigned)kWin) out[rel] = mv; }
+};
+
 struct __align__(128) WarpSmem {
-    float4 tiles[NBUF][32 * 15];                            // 7 680 B each
-    union {                                                 // the planes are dead before the moves are produced
-        struct { uint64_t planes[32 * 9]; float p[32 * 2]; } f;
-        uint64_t moves[kWin];
-    } u;
+    FaceRow face[32 * 9];                                   // 4 608 B
+    uint64_t moves[kWin];                                   // 2 560 B
     float4 lut[8];
 };
 
-// V: face variant or -1 (no face).  MODE: see enum Mode.  NBUF: staging tiles per warp.
-template <int V, int MODE, int NBUF>
-__global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* __restrict__ raw_hands,
+// V: face variant or -1 (no face).  MODE: see enum Mode.
+template <int V, int MODE>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, const uint64_t* __restrict__ raw_hands,
                                                   const uint64_t* __restrict__ raw_lasts, StepArgs a, OutArgs o,
                                                   Workspace ws, int64_t* stats, int B) {
     constexpr bool STEP = (MODE == kStepOnly || MODE == kStepObserve);
@@ -214,17 +236,21 @@ __global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* _
     constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem<NBUF>& sm = reinterpret_cast<WarpSmem<NBUF>*>(smem_raw)[wib];
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[wib];
+    const RowLane rl = RowLane::make(lane);
     const int nt = (B + 31) / 32;
     const unsigned int nwarps = gridDim.x * kWarpsPerCta;
 
     // ---- 1. tile ticket: tiles are handed out in start order, so every lower tile is already running
     int t = blockIdx.x * kWarpsPerCta + wib;
-    unsigned int epoch = 0;
+    unsigned int epoch = 0, stepno = a.stepno;
     if (EMIT) {
-        if (lane == 0) { t = (int)atomicAdd(&ws.h->ticket, 1u); epoch = ws.h->epoch; }
+        unsigned int autostep = 0;
+        if (lane == 0) { t = (int)atomicAdd(&ws.h->ticket, 1u); epoch = ws.h->epoch; autostep = ws.h->auto_step; }
         t = __shfl_sync(FULL, t, 0);
         epoch = __shfl_sync(FULL, epoch, 0);
+        autostep = __shfl_sync(FULL, autostep, 0);
+        if (STEP && a.stepno == DDZ_STEPNO_AUTO) stepno = autostep;
         if (lane < 5) sm.lut[lane] = make_float4(lane > 0 ? 1.f : 0.f, lane > 1 ? 1.f : 0.f, lane > 2 ? 1.f : 0.f, lane > 3 ? 1.f : 0.f);
         __syncwarp();
     }
@@ -233,6 +259,7 @@ __global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* _
     const int b0 = t * 32, b = b0 + lane;
     const bool valid = b < B;
     const int nenv = min(32, B - b0);
+    trace(t, 0);
 
     // ---- 2. state transition
     Env e;
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* _
                 long long idx = -1;
                 if (a.mode == DDZ_CHOICE_INDEX) idx = ((const int32_t*)a.choice)[b];
                 else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)(((const uint32_t*)a.choice)[b] % (uint32_t)cnt) : -1;
-                else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, a.stepno) % (uint32_t)cnt) : -1;
+                else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, stepno) % (uint32_t)cnt) : -1;
                 else {
                     uint64_t want = ((const uint64_t*)a.choice)[b];
                     for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
@@ -291,106 +318,110 @@ __global__ void __launch_bounds__(kThreads) k_env(void* state, const uint64_t* _
     const int total = __shfl_sync(FULL, inc, 31);
     if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | (t == 0 ? kInclusive : kAggregate) | (unsigned int)total);
 
-    Stager<NBUF> stg{&sm.tiles[0][0], 0};
-
-    // ---- 4. face rows: [nenv][C] rows of 240 B, contiguous for the warp
-    if (V >= 0 && o.face) {
-        if (valid) {
-            uint64_t pl[C]; float p[2];
-            face_planes<(V < 0 ? 0 : V)>(e, pl, p);
+    // ---- 4. the face planes of every env go to shared memory while the state is still in registers
+    if (V >= 0 && o.face && valid) {
+        uint64_t pl[C]; float p[2];
+        face_planes<(V < 0 ? 0 : V)>(e, pl, p);
 #pragma unroll
-            for (int c = 0; c < C; c++) sm.u.f.planes[lane * C + c] = pl[c];
-            sm.u.f.p[lane * 2] = p[0]; sm.u.f.p[lane * 2 + 1] = p[1];
-        }
-        __syncwarp();
-        const int nrows = nenv * C;
-        char* gface = reinterpret_cast<char*>(o.face) + (size_t)b0 * C * 240;
-        for (int r0 = 0; r0 < nrows; r0 += 32) {
-            float4* tile = stg.acquire();
-            const int row = r0 + lane;
-            if (row < nrows) {
-                const int env = row / C, c = row - env * C;
-                const float s = (c >= C - 2) ? sm.u.f.p[env * 2 + (c - (C - 2))] : 1.f;
-                fill_row<true>(tile + lane * 15, sm.u.f.planes[row], s, sm.lut);
-            }
-            stg.release(gface + (size_t)r0 * 240, (uint32_t)min(32, nrows - r0) * 240u);
+        for (int c = 0; c < C; c++) {
+            FaceRow fr; fr.packed = pl[c]; fr.s = (c >= C - 2) ? p[c - (C - 2)] : 1.f; fr.pad = 0.f;
+            *reinterpret_cast<float4*>(&sm.face[lane * C + c]) = *reinterpret_cast<const float4*>(&fr);
         }
     }
+    __syncwarp();
+    trace(t, 1);
 
-    // ---- 5. look-back for the global base; the predecessors published long ago
-    long long base = 0;
-    if (t > 0) {
-        int p = t - 1;                                      // walk the predecessors 32 at a time
-        unsigned int spins = 0;
-        bool finished = false;
-        while (!finished) {
-            const int idx = p - lane;
-            unsigned long long w = 0;
-            bool ok = true;
-            if (idx >= 0) {
-                w = ld_relaxed(&ws.tile[idx]);
-                ok = ((w >> 34) == (epoch_tag >> 34)) && ((w >> 32) & 3ull) != 0;
-            }
-            if (__all_sync(FULL, ok)) {
-                const bool incl = idx >= 0 && ((w >> 32) & 3ull) == 2ull;
-                const unsigned int incmask = __ballot_sync(FULL, incl);
-                // lanes up to and including the nearest inclusive predecessor contribute
-                const int stop = incmask ? (__ffs(incmask) - 1) : 31;
-                const long long v = (idx >= 0 && lane <= stop) ? (long long)(unsigned int)w : 0;
-                base += warp_sum_ll(v);
-                if (incmask || p - 32 < 0) finished = true;
-                p -= 32;
-            } else {
-                __nanosleep(64);
-                if (++spins > (1u << 22)) {                 // never hang the GPU: flag the error and carry on
-                    if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
-                    finished = true;
+    // Two output phases.  Odd tiles run them in the opposite order, so that at any moment about half of the warps
+    // of an SM stream rows out while the other half does rule work (look-back, enumeration).
+    int disagree = 0;
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ph++) {
+    if ((ph == 0) != ((t & 1) != 0)) {
+        // ---- 5. face rows: [nenv][C] rows of 240 B, contiguous for the warp
+        trace(t, 2);
+        if (V >= 0 && o.face) write_rows<FaceRow>(o.face + (size_t)b0 * C * 15, nenv * C, rl, sm.lut, sm.face);
+        trace(t, 3);
+    } else {
+        trace(t, 4);
+        // ---- 6. look-back for the global base: kLookBack windows of 32 predecessors per round trip
+        long long base = 0;
+        if (t > 0) {
+            int p = t - 1;
+            unsigned int spins = 0;
+            bool finished = false;
+            while (!finished) {
+                unsigned long long w[kLookBack];
+#pragma unroll
+                for (int j = 0; j < kLookBack; j++) {
+                    const int idx = p - 32 * j - lane;
+                    w[j] = idx >= 0 ? ld_relaxed(&ws.tile[idx]) : (epoch_tag | kInclusive);   // before tile 0: prefix 0
+                }
+#pragma unroll
+                for (int j = 0; j < kLookBack; j++) {
+                    if (finished) break;
+                    const bool ok = ((w[j] >> 34) == (epoch_tag >> 34)) && ((w[j] >> 32) & 3ull) != 0;
+                    if (!__all_sync(FULL, ok)) {            // not published yet: poll again from this window
+                        __nanosleep(64);
+                        if (++spins > (1u << 22)) {         // never hang the GPU: flag the error and carry on
+                            if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                            finished = true;
+                        }
+                        break;
+                    }
+                    const unsigned int incmask = __ballot_sync(FULL, ((w[j] >> 32) & 3ull) == 2ull);
+                    // lanes up to and including the nearest inclusive predecessor contribute
+                    const int stop = incmask ? (__ffs(incmask) - 1) : 31;
+                    base += warp_sum_ll(lane <= stop ? (long long)(unsigned int)w[j] : 0ll);
+                    p -= 32;
+                    if (incmask) finished = true;
                 }
             }
+            if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
         }
-        if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
-    }
-    if (valid) o.offsets[b] = (int32_t)(base + local);
-    if (t == nt - 1 && lane == 0) {
-        o.offsets[B] = (int32_t)(base + total);
-        if (stats) {
-            atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
-            if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
-        }
-    }
-    long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
-
-    // ---- 6. windows of kWin moves: enumerate into shared memory, then packed list + one-hot rows out
-    int disagree = 0;
-    for (int w0 = 0; w0 < total; w0 += kWin) {
-        if (n > 0 && local < w0 + kWin && local + n > w0) {
-            WindowEmitter em{sm.u.moves, local - w0};
-            enumerate_legal(masks_of(hand), last, em);
-            disagree |= (em.pos != local - w0 + n);
-        }
-        __syncwarp();
-        const int keep = (int)max(0ll, min((long long)min(kWin, total - w0), lim - w0));
-        for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = sm.u.moves[i];   // coalesced
-        if (o.actions_f32) {
-            char* gact = reinterpret_cast<char*>(o.actions_f32) + (size_t)(base + w0) * 240;
-            for (int r0 = 0; r0 < keep; r0 += 32) {
-                float4* tile = stg.acquire();
-                const int row = r0 + lane;
-                if (row < keep) fill_row<false>(tile + lane * 15, sm.u.moves[row], 1.f, sm.lut);
-                stg.release(gact + (size_t)r0 * 240, (uint32_t)min(32, keep - r0) * 240u);
+        if (valid) o.offsets[b] = (int32_t)(base + local);
+        if (t == nt - 1 && lane == 0) {
+            o.offsets[B] = (int32_t)(base + total);
+            if (stats) {
+                atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
+                if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
             }
         }
-        __syncwarp();      // the moves of this window are consumed before the next window overwrites them
+        long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
+        trace(t, 5);
+
+        // ---- 7. windows of kWin moves: enumerate into shared memory, then packed list + one-hot rows out
+        for (int w0 = 0; w0 < total; w0 += kWin) {
+            const bool inwin = n > 0 && local < w0 + kWin && local + n > w0;
+            if (inwin && n <= kHeavy) {                     // short lists: one env per lane
+                WindowEmitter em{sm.moves, local - w0};
+                enumerate_legal(masks_of(hand), last, em);
+                disagree |= (em.pos != local - w0 + n);
+            }
+            unsigned int heavy = __ballot_sync(FULL, inwin && n > kHeavy);
+            while (heavy) {                                 // long lists: the whole warp expands one env at a time
+                const int src = __ffs(heavy) - 1; heavy &= heavy - 1;
+                const uint64_t h = __shfl_sync(FULL, hand, src), l = __shfl_sync(FULL, last, src);
+                const int loc = __shfl_sync(FULL, local, src), nn = __shfl_sync(FULL, n, src);
+                IndexedWindowEmitter em{sm.moves, loc - w0};
+                disagree |= (enumerate_legal_warp(masks_of(h), l, lane, em) != nn);
+            }
+            __syncwarp();
+            const int keep = (int)max(0ll, min((long long)min(kWin, total - w0), lim - w0));
+            for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = sm.moves[i];   // coalesced
+            if (o.actions_f32) write_rows<uint64_t>(o.actions_f32 + (size_t)(base + w0) * 15, keep, rl, sm.lut, sm.moves);
+            __syncwarp();  // the moves of this window are consumed before the next window overwrites them
+        }
+        trace(t, 6);
+    }
     }
     stat_add(stats, 7, disagree);
     }  // EMIT
     }  // t < nt
     if (EMIT && lane == 0) {
-        tma_wait_read<0>();                                 // shared memory must outlive the bulk reads
-        __threadfence();
         const unsigned int fin = atomicAdd(&ws.h->finished, 1u);
         if (fin == nwarps - 1) {                            // the last warp of the launch re-arms the workspace
             ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = epoch + 1;
+            if (STEP) ws.h->auto_step = stepno + 1;
             __threadfence();
         }
     }
@@ -451,34 +482,15 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, what);             \
     } while (0)
 
-static int g_nbuf = 0;   // staging tiles per warp: 1 (more warps per SM) or 2 (double-buffered); DDZ_NBUF overrides
-static int nbuf() {
-    if (g_nbuf == 0) {
-        const char* s = getenv("DDZ_NBUF");
-        g_nbuf = (s && atoi(s) == 2) ? 2 : 1;
-    }
-    return g_nbuf;
-}
-
-template <int V, int MODE, int NBUF>
-static int launch_env_n(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
-                        void* workspace, int64_t* stats, int B, cudaStream_t st) {
-    const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem<NBUF>);
-    if (smem > 48 * 1024) {   // idempotent and cheap; per device, so it is simply repeated
-        cudaError_t e = cudaFuncSetAttribute(k_env<V, MODE, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
-    Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
-    const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_env<V, MODE, NBUF><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
-    DDZ_LAUNCH_CHECK("k_env");
-    return 0;
-}
 template <int V, int MODE>
 static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
                       void* workspace, int64_t* stats, int B, cudaStream_t st) {
-    if (MODE != kStepOnly && nbuf() == 2) return launch_env_n<V, MODE, 2>(state, hands, lasts, a, o, workspace, stats, B, st);
-    return launch_env_n<V, MODE, 1>(state, hands, lasts, a, o, workspace, stats, B, st);
+    const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem);
+    Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
+    const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
+    DDZ_LAUNCH_CHECK("k_env");
+    return 0;
 }
 template <int MODE>
 static int launch_env_v(int variant, bool want_face, void* state, const StepArgs& a, const OutArgs& o, void* workspace,
@@ -495,6 +507,11 @@ static int launch_env_v(int variant, bool want_face, void* state, const StepArgs
 
 extern "C" {
 
+#ifdef DDZ_TRACE
+int ddz_debug_set_trace(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(g_trace, &buf, sizeof buf) == cudaSuccess ? 0 : DDZ_E_CUDA;
+}
+#endif
 int ddz_abi_version(void) { return DDZ_ABI_VERSION; }
 int ddz_face_channels(int variant) {
     static const int C[4] = {4, 7, 9, 6};

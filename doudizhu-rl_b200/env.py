@@ -122,6 +122,7 @@ class BatchedEnv:
         self._state.zero_()
         f, meta = self._fields()
         meta.fill_(1)            # lord to move, not done, no deals consumed
+        self._ws.zero_()         # tile ticket / look-back words / device step counter
         self._fresh = False
         self._stepno = 0
 
@@ -232,9 +233,10 @@ class BatchedEnv:
         """envi.py:72-77: RHCP heuristic opponent -- out of scope for this build."""
         raise NotImplementedError("step_auto (RHCP rule AI of the absent native env) is not part of the hot path")
 
-    def rollout_step(self, choice=None, mode=N.CHOICE_PHILOX, perm=None, lord_pile=None, pool_games=1):
+    def rollout_step(self, choice=None, mode=N.CHOICE_PHILOX, perm=None, lord_pile=None, pool_games=1, auto_step=False):
         """One fused env-step in ONE launch (ddz_rollout_step): apply the chosen move, re-deal finished envs from perm
-        (device int8 [pool*B,54]) when given, and produce face + legal lists of the new state."""
+        (device int8 [pool*B,54]) when given, and produce face + legal lists of the new state.  auto_step: the Philox
+        step number comes from the device-side counter instead of the host (CUDA-graph replay, see GraphedRollout)."""
         self._ensure()
         nxt = 1 - self._cur
         if choice is not None:
@@ -243,8 +245,8 @@ class BatchedEnv:
             N.check(N.lib.ddz_rollout_step(
                 self._p(self._state), self._p(self._ws), self.VARIANT,
                 self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]),
-                self._p(choice), mode, self.seed, self.env0, self._stepno, self._rewards.data_ptr(),
-                self._p(perm), self._p(lord_pile), int(pool_games),
+                self._p(choice), mode, self.seed, self.env0, N.STEPNO_AUTO if auto_step else self._stepno,
+                self._rewards.data_ptr(), self._p(perm), self._p(lord_pile), int(pool_games),
                 self._p(self.r), self._p(self.done), self._p(self.cat), self._p(self.reward),
                 self._p(self._offsets[nxt]), self._p(self._actions_u64[nxt]), self._p(self._actions_f32), self.cap,
                 self._p(self._face), self._p(self.stats), self.B, self._stream()), "ddz_rollout_step")
@@ -362,6 +364,32 @@ class BatchedEnv:
             N.check(N.lib.ddz_encode_actions(packed.data_ptr(), packed.numel(), out.data_ptr(),
                                              torch.cuda.current_stream(packed.device).cuda_stream), "ddz_encode_actions")
         return out
+
+
+class GraphedRollout:
+    """CUDA-graph replay of the fused env-step: the two launches of a ping-pong pair are captured once and replayed,
+    which removes the per-step host cost (argument marshalling + launch) from a rollout loop.  Moves are chosen on
+    the device (Philox stream, or host-refreshed entropy in `entropy`); finished envs re-deal from `perm`."""
+
+    def __init__(self, env, perm=None, lord_pile=None, pool_games=1, entropy=None):
+        self.env = env
+        env._ensure()
+        torch.cuda.synchronize(env.device)
+        mode = N.CHOICE_PHILOX if entropy is None else N.CHOICE_MOD
+        kw = dict(choice=entropy, mode=mode, perm=perm, lord_pile=lord_pile, pool_games=pool_games, auto_step=True)
+        self._keep = (perm, lord_pile, entropy)
+        self.graph = torch.cuda.CUDAGraph()
+        stepno = env._stepno
+        with torch.cuda.graph(self.graph):
+            env.rollout_step(**kw)
+            env.rollout_step(**kw)
+        env._stepno = stepno          # capture launched nothing; the device counter still holds `stepno`
+
+    def replay(self):
+        """two env-steps"""
+        self.graph.replay()
+        self.env._stepno += 2
+        self.env._n_total = None
 
 
 class BatchedEnvComplicated(BatchedEnv):

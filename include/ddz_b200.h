@@ -58,6 +58,10 @@ extern "C" {
 #define DDZ_CHOICE_PHILOX 2  /* philox4x32-10(key=seed, ctr=(env0+b, stepno)) % N, no input buffer        */
 #define DDZ_CHOICE_MOVE 3    /* moves[b] is the packed move itself (envi.py:63-70 step_manual); must be legal */
 
+/* stepno value for ddz_rollout_step: take the Philox step number from the counter kept in the workspace (uint32 at
+ * byte 12; every stepping launch leaves it at its step number + 1).  Makes a captured CUDA graph replayable. */
+#define DDZ_STEPNO_AUTO 0xFFFFFFFFu
+
 int ddz_abi_version(void);
 int ddz_face_channels(int variant);          /* 4 / 7 / 9 / 6, or DDZ_E_ARG */
 size_t ddz_state_bytes(int B);

@@ -1,0 +1,118 @@
+// Microbenchmark: what store patterns does a B200 SM sustain when 4096 independent warps each stream ~120 KB?
+// Isolates the output path of k_env from its rule logic.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3
+// -o store_patterns store_patterns.cu ; run on the GPU box.  Prints GB/s per variant (CUDA events, best of 5).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+constexpr int kRowsPerWarp = 480;          // 480 rows x 240 B = 115 200 B per warp
+constexpr int kVecPerWarp = kRowsPerWarp * 15;
+
+__device__ __forceinline__ void st_default(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void st_cs(float4* p, float4 v) { __stcs(p, v); }
+
+// variant 0/1: 32 lanes x 16 B, warp-contiguous chunk
+template <bool CS>
+__global__ void __launch_bounds__(128, 8) k_aligned(float4* out, int nwarps) {
+    int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    float4* dst = out + (size_t)w * kVecPerWarp + lane;
+    float4 v = make_float4(1.f, 0.f, 1.f, (float)w);
+#pragma unroll 4
+    for (int i = 0; i < kVecPerWarp / 32; i++, dst += 32) { if (CS) st_cs(dst, v); else st_default(dst, v); }
+}
+// variant 2/3: lanes 0..29, two 240-B rows per instruction
+template <bool CS>
+__global__ void __launch_bounds__(128, 8) k_rows30(float4* out, int nwarps) {
+    int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= nwarps || lane >= 30) return;
+    float4* dst = out + (size_t)w * kVecPerWarp + lane;
+    float4 v = make_float4(1.f, 0.f, 1.f, (float)w);
+#pragma unroll 4
+    for (int i = 0; i < kRowsPerWarp / 2; i++, dst += 30) { if (CS) st_cs(dst, v); else st_default(dst, v); }
+}
+// variant 4: rows30 + the LDS(row) -> LDS(lut) -> FMUL chain of k_env
+template <bool CS>
+__global__ void __launch_bounds__(128, 8) k_rows30_lut(float4* out, int nwarps) {
+    __shared__ float4 rows[4][288];
+    __shared__ float4 lut[8];
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * 4 + wib, lane = threadIdx.x & 31;
+    if (threadIdx.x < 5) lut[threadIdx.x] = make_float4(threadIdx.x > 0, threadIdx.x > 1, threadIdx.x > 2, threadIdx.x > 3);
+    for (int i = lane; i < 288; i += 32) rows[wib][i] = make_float4(__uint_as_float(0x43210123u * (i + 1)), __uint_as_float(0x01234321u + i), 1.f, 0.f);
+    __syncthreads();
+    if (w >= nwarps || lane >= 30) return;
+    int first = lane / 15, k = lane % 15; bool hi = k >= 8; unsigned sh = 4 * (k & 7);
+    float4* dst = out + (size_t)w * kVecPerWarp + lane;
+#pragma unroll 4
+    for (int r = first; r < kRowsPerWarp; r += 2, dst += 30) {
+        float4 raw = rows[wib][r % 288];
+        unsigned wd = hi ? __float_as_uint(raw.y) : __float_as_uint(raw.x);
+        float4 q = lut[((wd >> sh) & 15u) % 5];
+        float s = raw.z; q.x *= s; q.y *= s; q.z *= s; q.w *= s;
+        if (CS) st_cs(dst, q); else st_default(dst, q);
+    }
+}
+// variant 5: grid-strided like a fill kernel (every warp instruction 512 B, warps interleaved)
+__global__ void __launch_bounds__(128, 8) k_gridstride(float4* out, size_t nvec) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    float4 v = make_float4(1.f, 0.f, 1.f, 2.f);
+#pragma unroll 4
+    for (; i < nvec; i += stride) out[i] = v;
+}
+// variant 6: TMA bulk store of a 7 680-B tile per warp (single buffer)
+__global__ void __launch_bounds__(128, 8) k_tma(float4* out, int nwarps) {
+    extern __shared__ __align__(128) float4 tiles[];
+    int wib = threadIdx.x >> 5, w = blockIdx.x * 4 + wib, lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    float4* tile = tiles + wib * 480;
+    char* dst = (char*)(out + (size_t)w * kVecPerWarp);
+    for (int t = 0; t < kRowsPerWarp / 32; t++) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        for (int k = 0; k < 15; k++) tile[lane * 15 + k] = make_float4(1.f, 0.f, (float)k, (float)t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)t * 7680),
+                         "r"((unsigned)__cvta_generic_to_shared(tile)), "r"(7680) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <class F>
+static float best_ms(F launch) {
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    float best = 1e9f;
+    for (int i = 0; i < 6; i++) {
+        CK(cudaEventRecord(a)); launch(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (i > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return best;
+}
+
+int main() {
+    const int nwarps = 4096, grid = nwarps / 4;
+    const size_t nvec = (size_t)nwarps * kVecPerWarp, bytes = nvec * 16;
+    float4* out; CK(cudaMalloc(&out, bytes + 4096));
+    CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 7680));
+    printf("{\"bytes\": %zu", bytes);
+#define REPORT(name, call) { float ms = best_ms([&] { call; }); printf(", \"%s_GBs\": %.0f", name, bytes / ms / 1e6); }
+    REPORT("aligned512", (k_aligned<false><<<grid, 128>>>(out, nwarps)));
+    REPORT("aligned512_cs", (k_aligned<true><<<grid, 128>>>(out, nwarps)));
+    REPORT("rows30", (k_rows30<false><<<grid, 128>>>(out, nwarps)));
+    REPORT("rows30_cs", (k_rows30<true><<<grid, 128>>>(out, nwarps)));
+    REPORT("rows30_lut", (k_rows30_lut<false><<<grid, 128>>>(out, nwarps)));
+    REPORT("rows30_lut_cs", (k_rows30_lut<true><<<grid, 128>>>(out, nwarps)));
+    REPORT("gridstride", (k_gridstride<<<grid, 128>>>(out, nvec)));
+    REPORT("gridstride_148x8", (k_gridstride<<<148 * 8, 128>>>(out, nvec)));
+    REPORT("tma_tile", (k_tma<<<grid, 128, 4 * 7680>>>(out, nwarps)));
+    printf("}\n");
+    return 0;
+}

@@ -277,6 +277,35 @@ def test_state_dict_resume_is_exact(D):
     assert torch.equal(a.offsets, b.offsets) and torch.equal(a.actions_packed, b.actions_packed)
 
 
+def test_cuda_graph_replay_matches_oracle(D, oracle):
+    """GraphedRollout: the captured ping-pong pair, replayed with the device-side step counter, follows the same
+    Philox stream as explicit stepping."""
+    B, G, seed = 1024, 4, 99
+    perm, lord = D.random_deals(B, seed=12, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = D.BatchedEnvCooperation(B, seed=seed)
+    env.prepare(pd, ld, pool_games=G)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=G)
+    t = 0
+    for _ in range(3):                       # a few explicit steps first: the counter must carry over
+        ref.observe(want_f32=False, want_face=False)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
+        ref.step(mode=2, seed=seed, step=t); ref.deal(perm, lord, only_done=True, pool_games=G); t += 1
+    gr = D.GraphedRollout(env, pd, ld, G)
+    for _ in range(40):
+        gr.replay()
+        for _ in range(2):
+            ref.observe(want_f32=False, want_face=False)
+            ref.step(mode=2, seed=seed, step=t); ref.deal(perm, lord, only_done=True, pool_games=G); t += 1
+    _compare_observation(env, ref, t)
+    _compare_state(env, ref, t)
+    env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)     # and explicit stepping continues seamlessly
+    ref.step(mode=2, seed=seed, step=t); ref.deal(perm, lord, only_done=True, pool_games=G)
+    _compare_observation(env, ref, t + 1)
+    assert int(env.stats[7].item()) == 0
+
+
 def test_full_size_invariants(D, oracle):
     """BASELINE config 4 slice: 131 072 envs on one GPU.  Size-independent properties + oracle spot checks."""
     B, G, seed = 131072, 4, 7
