@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -182,6 +182,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     step_kw = dict(mode=D.native.CHOICE_PHILOX, perm=perm_d, lord_pile=lord_d, pool_games=G)
+    sampler = ClockSampler(local)       # samples from here to the end of the e2e region: the same kernel runs throughout
+    sampler.start()
     for _ in range(args.prefill + W):
         env.rollout_step(**step_kw)
     torch.cuda.synchronize(dev)
@@ -198,8 +200,6 @@ def run_ours(args):
     stats0 = env.stats.clone()
     nrep = K // 2
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(nrep + 2)]
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     ev[0].record()
     for k in range(nrep):
@@ -209,7 +209,6 @@ def run_ours(args):
         env.rollout_step(**step_kw)
     ev[nrep + 1].record()
     barrier()
-    clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[nrep + 1])
     kern_ms = total_ms / K                  # average launch duration of the one kernel of a step (gaps included)
     dstats_t = (env.stats - stats0).clone()
@@ -230,39 +229,45 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     eager_ms = g0.elapsed_time(g1) / K
 
-    # ---------------- e2e: same step through the public API with HOST buffers (pinned) every step
-    R = 4
-    perm_h = [torch.as_tensor(D.random_deals(B, seed=SEED + 77 + i + 1000 * rank)[0]).pin_memory() for i in range(R)]
-    lord_h = [torch.zeros(B, dtype=torch.int8).pin_memory() for _ in range(R)]
+    # ---------------- e2e: the same env-step through the host-facing API (HostRollout) with HOST buffers every step:
+    # H2D of the step's entropy (int32 [B], pinned) and of the deal-pool refill (one slot of host-made permutations
+    # every REFILL steps = about one game length, the rate at which deals are consumed), D2H of the step's results
+    # (r, done, cat, reward) into pinned memory.  All copies are inside the timed region.
+    R, REFILL = 4, 64
     rng = np.random.default_rng(SEED + rank)
     ent_h = [torch.as_tensor(rng.integers(0, 1 << 31, B, dtype=np.int64).astype(np.int32)).pin_memory() for _ in range(R)]
-    perm_e, lord_e = torch.empty_like(perm_h[0], device=dev), torch.empty_like(lord_h[0], device=dev)
-    ent_e = torch.empty_like(ent_h[0], device=dev)
-    out_h = {"r": torch.empty(B, dtype=torch.int8).pin_memory(), "done": torch.empty(B, dtype=torch.uint8).pin_memory(),
-             "cat": torch.empty(B, dtype=torch.int8).pin_memory(), "reward": torch.empty((B, 3), dtype=torch.float32).pin_memory()}
+    pool_h = []
+    for i in range(2):
+        pp, ll = D.random_deals(B, seed=SEED + 77 + i + 1000 * rank)
+        pool_h.append((torch.as_tensor(pp).pin_memory(), torch.as_tensor(ll).pin_memory()))
+    host = D.HostRollout(env, perm_d, lord_d, G)
+    sink = 0
 
     def e2e_step(i):
-        perm_e.copy_(perm_h[i % R], non_blocking=True)
-        lord_e.copy_(lord_h[i % R], non_blocking=True)
-        ent_e.copy_(ent_h[i % R], non_blocking=True)
-        env.rollout_step(choice=ent_e, mode=D.native.CHOICE_MOD, perm=perm_e, lord_pile=lord_e, pool_games=1)
-        out_h["r"].copy_(env.r, non_blocking=True)
-        out_h["done"].copy_(env.done, non_blocking=True)
-        out_h["cat"].copy_(env.cat, non_blocking=True)
-        out_h["reward"].copy_(env.reward, non_blocking=True)
+        if i % REFILL == 0:
+            pp, ll = pool_h[(i // REFILL) % 2]
+            host.refill((i // REFILL) % G, pp, ll)
+        return host.step(ent_h[i % R])
 
     for i in range(max(W, 3)):
         e2e_step(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    stats_e0 = env.stats.clone()
     e0.record()
+    last = None
     for i in range(K):
-        e2e_step(i)
+        last = e2e_step(i)
     e1.record()
     barrier()
+    D.HostRollout.wait(last)
+    clocks = sampler.stop()
+    sink += int(last.done.sum())                      # the host really reads the results
     e2e_ms = e0.elapsed_time(e1)
-    h2d = B * (54 + 1 + 4)
-    d2h = B * (1 + 1 + 1 + 12)
+    e2e_steps = int((env.stats - stats_e0)[4].item())
+    assert e2e_steps == B * K
+    h2d = 4 * B + (55 * B * ((K + REFILL - 1) // REFILL)) // K
+    d2h = host.results_h[0].nbytes
     if int(env.stats[7].item()):
         raise SystemExit("env reported errors during the e2e region")
 
@@ -295,7 +300,9 @@ def run_ours(args):
                          "unit": "GB/s", "frac": kern_gbs / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_env": eb, "ms_per_launch": kern_ms},
             "e2e": {"value": B * K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
+                    "api": "HostRollout.step(entropy_host) + refill(slot, perm_host, lord_host) every %d steps; "
+                           "results (r, done, cat, reward) read back to pinned host memory every step" % REFILL},
             "gpu_launches": K,
             "clocks": clocks,
         }

@@ -6,11 +6,11 @@ importlib.import_module("doudizhu-rl_b200").
 """
 from . import _native as native  # raises ImportError when libddz_b200.so has not been built
 from . import sharding
-from .env import (GraphedRollout, BatchedEnv, BatchedEnvComplicated, BatchedEnvCooperation, BatchedEnvCooperationSimplify,
+from .env import (GraphedRollout, HostRollout, StepResults, BatchedEnv, BatchedEnvComplicated, BatchedEnvCooperation, BatchedEnvCooperationSimplify,
                   Env, EnvComplicated, EnvCooperation, EnvCooperationSimplify,
                   get_moves, pack_counts, unpack_counts, default_deals, random_deals,
                   VARIANT_CHANNELS, DEFAULT_REWARDS)
 
-__all__ = ["native", "sharding", "GraphedRollout", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
+__all__ = ["native", "sharding", "GraphedRollout", "HostRollout", "StepResults", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
            "Env", "EnvComplicated", "EnvCooperation", "EnvCooperationSimplify", "get_moves", "pack_counts",
            "unpack_counts", "default_deals", "random_deals", "VARIANT_CHANNELS", "DEFAULT_REWARDS"]

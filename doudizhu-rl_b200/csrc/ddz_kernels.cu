@@ -270,12 +270,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         if (valid) { hand = raw_hands[b]; last = raw_lasts[b]; n = count_legal(masks_of(hand), last); }
     } else if (valid) {
         StateView v = view_of(state, B);
+        int prev_off = 0, prev_end = 0;
+        if (STEP) { prev_off = a.offsets[b]; prev_end = a.offsets[b + 1]; }   // independent of the state: issued together
         e = load_env(v, b);
         if (STEP) {
             int o_r = 0, o_cat = -1;
             float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
             if (!e.done()) {
-                int base = a.offsets[b], cnt = a.offsets[b + 1] - base;
+                const int base = prev_off, cnt = prev_end - prev_off;
                 long long idx = -1;
                 if (a.mode == DDZ_CHOICE_INDEX) idx = ((const int32_t*)a.choice)[b];
                 else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)(((const uint32_t*)a.choice)[b] % (uint32_t)cnt) : -1;
@@ -343,54 +345,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         trace(t, 3);
     } else {
         trace(t, 4);
-        // ---- 6. look-back for the global base: kLookBack windows of 32 predecessors per round trip
-        long long base = 0;
-        if (t > 0) {
-            int p = t - 1;
-            unsigned int spins = 0;
-            bool finished = false;
-            while (!finished) {
-                unsigned long long w[kLookBack];
-#pragma unroll
-                for (int j = 0; j < kLookBack; j++) {
-                    const int idx = p - 32 * j - lane;
-                    w[j] = idx >= 0 ? ld_relaxed(&ws.tile[idx]) : (epoch_tag | kInclusive);   // before tile 0: prefix 0
-                }
-#pragma unroll
-                for (int j = 0; j < kLookBack; j++) {
-                    if (finished) break;
-                    const bool ok = ((w[j] >> 34) == (epoch_tag >> 34)) && ((w[j] >> 32) & 3ull) != 0;
-                    if (!__all_sync(FULL, ok)) {            // not published yet: poll again from this window
-                        __nanosleep(64);
-                        if (++spins > (1u << 22)) {         // never hang the GPU: flag the error and carry on
-                            if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
-                            finished = true;
-                        }
-                        break;
-                    }
-                    const unsigned int incmask = __ballot_sync(FULL, ((w[j] >> 32) & 3ull) == 2ull);
-                    // lanes up to and including the nearest inclusive predecessor contribute
-                    const int stop = incmask ? (__ffs(incmask) - 1) : 31;
-                    base += warp_sum_ll(lane <= stop ? (long long)(unsigned int)w[j] : 0ll);
-                    p -= 32;
-                    if (incmask) finished = true;
-                }
-            }
-            if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
-        }
-        if (valid) o.offsets[b] = (int32_t)(base + local);
-        if (t == nt - 1 && lane == 0) {
-            o.offsets[B] = (int32_t)(base + total);
-            if (stats) {
-                atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
-                if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
-            }
-        }
-        long long lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
-        trace(t, 5);
-
-        // ---- 7. windows of kWin moves: enumerate into shared memory, then packed list + one-hot rows out
-        for (int w0 = 0; w0 < total; w0 += kWin) {
+        // ---- 6..8. per window of kWin moves: enumerate into shared memory; (first window only) look-back for the
+        // global base -- whatever wait it has is hidden behind the enumeration; then packed list + one-hot rows out
+        long long base = 0, lim = 0;
+        int w0 = 0;
+#pragma unroll 1
+        do {
             const bool inwin = n > 0 && local < w0 + kWin && local + n > w0;
             if (inwin && n <= kHeavy) {                     // short lists: one env per lane
                 WindowEmitter em{sm.moves, local - w0};
@@ -406,11 +366,60 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 disagree |= (enumerate_legal_warp(masks_of(h), l, lane, em) != nn);
             }
             __syncwarp();
+
+            if (w0 == 0) {
+                // look-back: kLookBack windows of 32 predecessor tiles per round trip
+                if (t > 0) {
+                    int p = t - 1;
+                    unsigned int spins = 0;
+                    bool finished = false;
+                    while (!finished) {
+                        unsigned long long w[kLookBack];
+#pragma unroll
+                        for (int j = 0; j < kLookBack; j++) {
+                            const int idx = p - 32 * j - lane;
+                            w[j] = idx >= 0 ? ld_relaxed(&ws.tile[idx]) : (epoch_tag | kInclusive);   // before tile 0: prefix 0
+                        }
+#pragma unroll
+                        for (int j = 0; j < kLookBack; j++) {
+                            if (finished) break;
+                            const bool ok = ((w[j] >> 34) == (epoch_tag >> 34)) && ((w[j] >> 32) & 3ull) != 0;
+                            if (!__all_sync(FULL, ok)) {    // not published yet: poll again from this window
+                                __nanosleep(64);
+                                if (++spins > (1u << 22)) { // never hang the GPU: flag the error and carry on
+                                    if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                                    finished = true;
+                                }
+                                break;
+                            }
+                            const unsigned int incmask = __ballot_sync(FULL, ((w[j] >> 32) & 3ull) == 2ull);
+                            // lanes up to and including the nearest inclusive predecessor contribute
+                            const int stop = incmask ? (__ffs(incmask) - 1) : 31;
+                            base += warp_sum_ll(lane <= stop ? (long long)(unsigned int)w[j] : 0ll);
+                            p -= 32;
+                            if (incmask) finished = true;
+                        }
+                    }
+                    if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
+                }
+                if (valid) o.offsets[b] = (int32_t)(base + local);
+                if (t == nt - 1 && lane == 0) {
+                    o.offsets[B] = (int32_t)(base + total);
+                    if (stats) {
+                        atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
+                        if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                    }
+                }
+                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
+                trace(t, 5);
+            }
+
             const int keep = (int)max(0ll, min((long long)min(kWin, total - w0), lim - w0));
             for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = sm.moves[i];   // coalesced
             if (o.actions_f32) write_rows<uint64_t>(o.actions_f32 + (size_t)(base + w0) * 15, keep, rl, sm.lut, sm.moves);
             __syncwarp();  // the moves of this window are consumed before the next window overwrites them
-        }
+            w0 += kWin;
+        } while (w0 < total);
         trace(t, 6);
     }
     }

@@ -51,6 +51,27 @@ def unpack_counts(packed):
     return (p.unsqueeze(-1) >> _shifts(p.device)) & 15
 
 
+def _align(x, a):
+    return (x + a - 1) // a * a
+
+
+class StepResults:
+    """Outputs of one step in ONE contiguous buffer (a single D2H copy fetches them): r int8[B] | done uint8[B] |
+    cat int8[B] | pad | reward float32[B,3]."""
+
+    def __init__(self, B, device, pin=False):
+        self.B = B
+        self.off_reward = _align(3 * B, 16)
+        self.nbytes = self.off_reward + 12 * B
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        if pin:
+            self.buf = self.buf.pin_memory()
+        self.r = self.buf[0:B].view(torch.int8)
+        self.done = self.buf[B:2 * B]
+        self.cat = self.buf[2 * B:3 * B].view(torch.int8)
+        self.reward = self.buf[self.off_reward:].view(torch.float32).view(B, 3)
+
+
 class BatchedEnv:
     """B independent Doudizhu games on one GPU.  Reference: envi.py:16-157 (class Env, C=4 face)."""
 
@@ -78,10 +99,8 @@ class BatchedEnv:
             self._actions_u64 = [torch.zeros(self.cap, dtype=torch.int64, device=dev) for _ in range(2)]
             self._actions_f32 = torch.empty((self.cap, 15, 4), dtype=torch.float32, device=dev)
             self._face = torch.empty((B, self.C, 15, 4), dtype=torch.float32, device=dev)
-            self.r = torch.zeros(B, dtype=torch.int8, device=dev)
-            self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
-            self.cat = torch.zeros(B, dtype=torch.int8, device=dev)
-            self.reward = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+            self._results = [StepResults(B, dev) for _ in range(2)]   # two sets: a D2H read of one may overlap the next step
+            self._res = 0
             self.stats = torch.zeros(16, dtype=torch.int64, device=dev)
             self._rewards = torch.tensor(list(rewards), dtype=torch.int32, device="cpu")
         self._cur = 0            # which ping-pong list describes the current state
@@ -92,6 +111,23 @@ class BatchedEnv:
         self._perm_dev = None
         self._lord_dev = None
         self.reset()
+
+    # results of the most recent step (device tensors; views into one contiguous buffer)
+    @property
+    def r(self):
+        return self._results[self._res].r
+
+    @property
+    def done(self):
+        return self._results[self._res].done
+
+    @property
+    def cat(self):
+        return self._results[self._res].cat
+
+    @property
+    def reward(self):
+        return self._results[self._res].reward
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -239,6 +275,7 @@ class BatchedEnv:
         step number comes from the device-side counter instead of the host (CUDA-graph replay, see GraphedRollout)."""
         self._ensure()
         nxt = 1 - self._cur
+        self._res = nxt               # result set follows the ping-pong, so a graph replay leaves it consistent
         if choice is not None:
             choice = self._to_dev(choice, torch.int64 if mode == N.CHOICE_MOVE else torch.int32)
         with torch.cuda.device(self.device):
@@ -390,6 +427,85 @@ class GraphedRollout:
         self.graph.replay()
         self.env._stepno += 2
         self.env._n_total = None
+
+
+class HostRollout:
+    """Rollout driven from HOST buffers: the call a host-side user makes per env-step.
+
+    Every step the caller hands over a pinned host array of entropy (uint32/int32 [B]: move index = entropy % N, the
+    batched form of envi.py:83 random.choice) and gets the step's results (r, done, cat, reward) back in pinned host
+    memory.  Deck permutations are host-supplied too: `refill(slot, perm, lord_pile)` uploads one slot of the
+    device-resident deal pool (each env consumes one deal per game, so one slot per ~game length keeps it fresh).
+    Copies run on their own streams: the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t.
+    """
+
+    def __init__(self, env, perm, lord_pile, pool_games):
+        self.env, self.G = env, int(pool_games)
+        dev, B = env.device, env.B
+        self.perm_d = env._to_dev(perm, torch.int8).reshape(self.G, B, 54).contiguous()
+        self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.G, B).contiguous()
+        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.results_h = [StepResults(B, "cpu", pin=True) for _ in range(2)]
+        self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_k = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.ev_in_free = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self._stage = None
+        env._ensure()
+        main = torch.cuda.current_stream(dev)
+        for e in self.ev_out + self.ev_in_free:
+            e.record(main)
+
+    def refill(self, slot, perm, lord_pile):
+        """upload one slot of the deal pool: perm int8 [B,54], lord_pile int8 [B], pinned host memory.  The upload
+        lands in a staging buffer on the copy stream (overlapping the kernels); the slot itself is replaced by a
+        device-to-device copy ordered between two steps, so no kernel ever reads a half-written permutation."""
+        B, main = self.env.B, torch.cuda.current_stream(self.env.device)
+        if self._stage is None:
+            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=self.env.device),
+                           torch.empty(B, dtype=torch.int8, device=self.env.device))
+            self._stage_free, self._stage_full = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(main)
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(self._stage_free)
+            self._stage[0].copy_(torch.as_tensor(perm).reshape(B, 54), non_blocking=True)
+            self._stage[1].copy_(torch.as_tensor(lord_pile).reshape(B), non_blocking=True)
+            self._stage_full.record(self.h2d)
+        main.wait_event(self._stage_full)
+        self.perm_d[slot].copy_(self._stage[0], non_blocking=True)
+        self.lord_d[slot].copy_(self._stage[1], non_blocking=True)
+        self._stage_free.record(main)
+
+    def step(self, entropy_h):
+        """entropy_h: pinned int32 [B].  Returns the StepResults (pinned host views) this step will fill; they are
+        valid after `wait(results)` (or any later synchronisation)."""
+        env, k = self.env, self.i & 1
+        main = torch.cuda.current_stream(env.device)
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(self.ev_in_free[k])          # the kernel that read entropy_d[k] two steps ago is done
+            self.entropy_d[k].copy_(entropy_h, non_blocking=True)
+            self.ev_in[k].record(self.h2d)
+        main.wait_event(self.ev_in[k])
+        main.wait_event(self.ev_out[1 - env._cur])           # the D2H that read this result set has finished
+        env.rollout_step(choice=self.entropy_d[k], mode=N.CHOICE_MOD, perm=self.perm_d, lord_pile=self.lord_d,
+                         pool_games=self.G)
+        self.ev_k[k].record(main)
+        self.ev_in_free[k].record(main)
+        res_d, res_h = env._results[env._res], self.results_h[env._res]
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.ev_k[k])
+            res_h.buf.copy_(res_d.buf, non_blocking=True)
+            self.ev_out[env._res].record(self.d2h)
+        res_h._event = self.ev_out[env._res]
+        self.i += 1
+        return res_h
+
+    @staticmethod
+    def wait(results):
+        results._event.synchronize()
+        return results
 
 
 class BatchedEnvComplicated(BatchedEnv):

@@ -43,6 +43,8 @@ dur = {"phaseA": tr[:, 1] - tr[:, 0], "face_rows": tr[:, 3] - tr[:, 2], "lookbac
 for k, v in dur.items():
     out["dur_" + k] = {"mean": float(np.nanmean(v)), "p50": float(np.nanmedian(v)), "p99": float(np.nanpercentile(v, 99)),
                        "max": float(np.nanmax(v))}
+end = np.fmax(tr[:, 3], tr[:, 6])
+out["warp_end_percentiles_us"] = {str(q): float(np.nanpercentile(end, q)) for q in (1, 10, 25, 50, 75, 90, 99, 100)}
 out["kernel_span_us"] = float(np.nanmax(tr))
 even = np.arange(nt) % 2 == 0
 out["even_tiles_end_p50"] = float(np.nanmedian(np.maximum(tr[even, 3], tr[even, 6])))

@@ -306,6 +306,42 @@ def test_cuda_graph_replay_matches_oracle(D, oracle):
     assert int(env.stats[7].item()) == 0
 
 
+def test_host_rollout_pipeline_matches_oracle(D, oracle):
+    """HostRollout: entropy from pinned host memory every step, deal-pool slots refilled from the host, results read
+    back into pinned memory -- with the copies on their own streams.  Every step's results must equal the oracle's."""
+    B, G = 2048, 2
+    rng = np.random.default_rng(31)
+    perm, lord = D.random_deals(B, seed=13, pool_games=G)
+    pool = [np.array(perm.reshape(G, B, 54)), np.array(lord.reshape(G, B))]
+    env = D.BatchedEnvCooperation(B)
+    env.prepare(perm, lord, pool_games=G)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=G)
+    host = D.HostRollout(env, perm, lord, G)
+    ents = [torch.as_tensor(rng.integers(0, 1 << 31, B).astype(np.int32)).pin_memory() for _ in range(6)]
+    pending = []
+    for t in range(120):
+        if t % 40 == 20:                              # refresh slot (t // 40) % G with new host-made deals
+            slot = (t // 40) % G
+            p2, l2 = D.random_deals(B, seed=100 + t)
+            host.refill(slot, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory())
+            pool[0][slot], pool[1][slot] = p2, l2
+        res = host.step(ents[t % 6])
+        ref.observe(want_f32=False, want_face=False)
+        want = ref.step(ents[t % 6].numpy(), mode=1)
+        ref.deal(pool[0].reshape(-1, 54), pool[1].reshape(-1), only_done=True, pool_games=G)
+        pending.append((res, [w.copy() for w in want]))
+        if len(pending) == 2:                         # results of step t-1 are read while step t is in flight
+            got, (rr, rd, rc, rrew) = pending.pop(0)
+            D.HostRollout.wait(got)
+            assert np.array_equal(got.r.numpy(), rr) and np.array_equal(got.done.numpy(), rd), t
+            assert np.array_equal(got.cat.numpy(), rc) and np.array_equal(got.reward.numpy(), rrew), t
+            pending[0] = (pending[0][0], pending[0][1])
+    torch.cuda.synchronize()
+    _compare_state(env, ref, 120)
+    assert int(env.stats[7].item()) == 0 and int(env.stats[0].item()) == ref.stats[0] > 0
+
+
 def test_full_size_invariants(D, oracle):
     """BASELINE config 4 slice: 131 072 envs on one GPU.  Size-independent properties + oracle spot checks."""
     B, G, seed = 131072, 4, 7
