@@ -140,9 +140,8 @@ DDZ_DEV int count_planes(uint32_t g3, int nkick, const Rule& ru, int cat) {
     }
     return n;
 }
-DDZ_DEV int count_legal(const Masks& m, uint64_t last) {
-    if (m.g1 == 0) return last ? 1 : 0;  // empty hand (finished env): pass only / nothing
-    Rule ru = rule_of(last);
+DDZ_DEV int count_legal(const Masks& m, const Rule& ru, bool has_last) {
+    if (m.g1 == 0) return has_last ? 1 : 0;  // empty hand (finished env): pass only / nothing
     int n = ru.lead ? 0 : 1;             // pass
     int n1 = __popc(m.g1), n2 = __popc(m.g2);
     if (ru.allowed(1)) n += __popc(m.g1 & ru.from(1));
@@ -163,7 +162,7 @@ DDZ_DEV int count_legal(const Masks& m, uint64_t last) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// enumeration in canonical order; f(packed_move) is called once per legal move
+// enumeration in canonical order
 // ------------------------------------------------------------------------------------------------
 // lexicographic successor of the k-subset c of S (the order itertools.combinations yields, card.py:115);
 // returns 0 when c was the last one
@@ -183,6 +182,22 @@ DDZ_DEV uint32_t next_combo(uint32_t c, uint32_t S) {
     for (int i = 0; i < j; i++) { out |= rem & (0u - rem); rem &= rem - 1; }
     return out;
 }
+// idx-th k-subset of S in lexicographic order (idx 0 = the k lowest elements)
+DDZ_DEV uint32_t unrank_combo(uint32_t S, int k, int idx) {
+    uint32_t out = 0;
+    int n = __popc(S);
+    for (int i = 0; i < k; i++) {
+        for (;;) {
+            const int c = binom(n - 1, k - i - 1);     // subsets whose next element is the lowest one left
+            const uint32_t low = S & (0u - S);
+            S ^= low; n--;
+            if (idx < c) { out |= low; break; }
+            idx -= c;
+        }
+    }
+    return out;
+}
+
 DDZ_DEV uint32_t first_combo(uint32_t S, int k) {
     uint32_t c = 0;
     for (int i = 0; i < k; i++) { c |= S & (0u - S); S &= S - 1; }
@@ -230,10 +245,11 @@ DDZ_DEV void each_plane(uint32_t g3, uint32_t kicksrc, const Rule& ru, int cat, 
         }
     }
 }
+// one env per lane, one loop nest per category with compile-time constants (the fast path for short lists);
+// f(move) is called in canonical order
 template <class F>
-DDZ_DEV void enumerate_legal(const Masks& m, uint64_t last, F& f) {
-    if (m.g1 == 0) { if (last) f(0ull); return; }
-    Rule ru = rule_of(last);
+DDZ_DEV void enumerate_legal(const Masks& m, const Rule& ru, bool has_last, F& f) {
+    if (m.g1 == 0) { if (has_last) f(0ull); return; }
     if (!ru.lead) f(0ull);
     if (ru.allowed(1)) each_rank<1>(m.g1 & ru.from(1), f);
     if (ru.allowed(2)) each_rank<2>(m.g2 & ru.from(2), f);
@@ -272,21 +288,6 @@ DDZ_DEV void enumerate_legal(const Masks& m, uint64_t last, F& f) {
 // ------------------------------------------------------------------------------------------------
 DDZ_DEV uint32_t nth_bit(uint32_t mask, int j) { return 1u << __fns(mask, 0, j + 1); }   // j-th set bit (0-based)
 
-// idx-th k-subset of S in lexicographic order
-DDZ_DEV uint32_t unrank_combo(uint32_t S, int k, int idx) {
-    uint32_t out = 0;
-    int n = __popc(S);
-    for (int i = 0; i < k; i++) {
-        for (;;) {
-            const int c = binom(n - 1, k - i - 1);     // subsets whose next element is the lowest one left
-            const uint32_t low = S & (0u - S);
-            S ^= low; n--;
-            if (idx < c) { out |= low; break; }
-            idx -= c;
-        }
-    }
-    return out;
-}
 // c kicker sets of size k out of S for one main group, split into 32 contiguous chunks
 template <class F>
 DDZ_DEV void coop_kicker_sets(uint32_t main, uint32_t mult, uint32_t S, int k, uint32_t kmult, int off, int lane, F& f) {
@@ -370,9 +371,8 @@ DDZ_DEV int coop_four_two(uint32_t mains, uint32_t kicksrc, int off, int lane, F
 }
 // returns the number of moves (must equal count_legal); f(index, move) is called once per move by some lane
 template <class F>
-DDZ_DEV int enumerate_legal_warp(const Masks& m, uint64_t last, int lane, F& f) {
-    if (m.g1 == 0) { if (last && lane == 0) f(0, 0ull); return last ? 1 : 0; }
-    const Rule ru = rule_of(last);
+DDZ_DEV int enumerate_legal_warp(const Masks& m, const Rule& ru, bool has_last, int lane, F& f) {
+    if (m.g1 == 0) { if (has_last && lane == 0) f(0, 0ull); return has_last ? 1 : 0; }
     int off = 0;
     if (!ru.lead) { if (lane == 0) f(0, 0ull); off = 1; }
     if (ru.allowed(1)) off += coop_ranks<1>(m.g1 & ru.from(1), off, lane, f);
@@ -458,34 +458,64 @@ DDZ_DEV uint64_t trick_of(const Env& e) {
     return last_move(p1, p2);
 }
 
-// deal: returns false when perm is not a permutation of 0..53 or lord_pile is out of range
-DDZ_DEV bool deal(Env& e, const int8_t* __restrict__ perm, int lord_pile) {
-    uint64_t pile[4] = {0, 0, 0, 0}, seen = 0;
-    bool ok = (lord_pile >= 0 && lord_pile <= 2);
+// Warp-cooperative deal.  `need` = ballot of the lanes whose env must be re-dealt; for each of them the
+// whole warp reads the 54-byte permutation row (lane l < 27 loads cards 2l and 2l+1 as one 16-bit word), builds the
+// four piles with hardware warp reductions (nibble sums never carry: a rank has at most 4 cards) and checks that the
+// row is a permutation of 0..53.  One HBM round trip and ~60 instructions per deal, no per-lane 54-step chain.
+// Returns the ballot of lanes whose deal was refused (bad permutation / lord_pile): their env is left untouched.
+DDZ_DEV unsigned int warp_deal(unsigned int need, Env& e, const int8_t* __restrict__ perm,
+                               const int8_t* __restrict__ lord_pile, int pool_games, int B, int b, int lane) {
+    unsigned int bad = 0;
+    const unsigned long long myrow = (unsigned long long)((e.meta >> 8) % (uint32_t)pool_games) * (unsigned long long)B + (unsigned long long)b;
+    while (need) {
+        const int src = __ffs(need) - 1; need &= need - 1;
+        const unsigned long long row = __shfl_sync(0xFFFFFFFFu, myrow, src);
+        int lp = 0;
+        if (lane == src && lord_pile) lp = lord_pile[row];
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, seen_lo = 0, seen_hi = 0;
+        bool ok = true;
+        if (lane < 27) {
+            const uint32_t v = reinterpret_cast<const uint16_t*>(perm + 54 * row)[lane];
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int n = (p < 3) ? 17 : 3;
+            for (int c = 0; c < 2; c++) {
+                const int i = 2 * lane + c;
+                int id = (int)(int8_t)((v >> (8 * c)) & 0xFFu);
+                ok = ok && (id >= 0 && id < 54);
+                id = (id < 0) ? 0 : (id > 53 ? 53 : id);
+                if (id < 32) seen_lo |= 1u << id; else seen_hi |= 1u << (id - 32);
+                const int rank = id < 52 ? (id >> 2) : id - 39;
+                const int p = i < 17 ? 0 : (i < 34 ? 1 : (i < 51 ? 2 : 3));
+                const uint32_t nib = 1u << (4 * (rank & 7));
 #pragma unroll
-        for (int i = 0; i < n; i++) {
-            int id = perm[17 * p + i];
-            ok = ok && (id >= 0 && id < 54);
-            id = (id < 0) ? 0 : (id > 53 ? 53 : id);
-            seen |= 1ull << id;
-            int rank = id < 52 ? (id >> 2) : id - 39;
-            pile[p] += 1ull << (4 * rank);
+                for (int q = 0; q < 4; q++) if (p == q) { if (rank < 8) lo[q] += nib; else hi[q] += nib; }
+            }
+        }
+        uint64_t pile[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            pile[q] = ((uint64_t)__reduce_add_sync(0xFFFFFFFFu, hi[q]) << 32) | __reduce_add_sync(0xFFFFFFFFu, lo[q]);
+        seen_lo = __reduce_or_sync(0xFFFFFFFFu, seen_lo);
+        seen_hi = __reduce_or_sync(0xFFFFFFFFu, seen_hi);
+        ok = __all_sync(0xFFFFFFFFu, ok) && seen_lo == 0xFFFFFFFFu && seen_hi == 0x003FFFFFu;
+        if (lane == src) {
+            ok = ok && lp >= 0 && lp <= 2;
+            if (ok) {
+                e.hand[1] = pick3(lp, pile[0], pile[1], pile[2]) + pile[3];
+                e.hand[2] = pick3((lp + 1) % 3, pile[0], pile[1], pile[2]);
+                e.hand[0] = pick3((lp + 2) % 3, pile[0], pile[1], pile[2]);
+#pragma unroll
+                for (int q = 0; q < 3; q++) { e.hist[q] = 0; e.recent[q] = 0; }
+                const uint32_t games = (e.meta >> 8) + 1;
+                e.meta = 1u | (e.meta & 0x20u) | (games << 8);  // lord to move, not done, keep sticky error
+            } else {    // refuse: leave an empty, finished env with the sticky error bit
+#pragma unroll
+                for (int q = 0; q < 3; q++) { e.hand[q] = e.hist[q] = e.recent[q] = 0; }
+                e.meta = (e.meta & 0xFFFFFF00u) | 1u | 4u | 0x20u;
+                bad |= 1u << src;
+            }
         }
     }
-    ok = ok && (seen == (1ull << 54) - 1);
-    if (!ok) return false;
-    int lp = lord_pile;
-    e.hand[1] = pick3(lp, pile[0], pile[1], pile[2]) + pile[3];
-    e.hand[2] = pick3((lp + 1) % 3, pile[0], pile[1], pile[2]);
-    e.hand[0] = pick3((lp + 2) % 3, pile[0], pile[1], pile[2]);
-#pragma unroll
-    for (int q = 0; q < 3; q++) { e.hist[q] = 0; e.recent[q] = 0; }
-    uint32_t games = (e.meta >> 8) + 1;
-    e.meta = 1u | (e.meta & 0x20u) | (games << 8);  // lord to move, not done, keep sticky error
-    return true;
+    return __reduce_or_sync(0xFFFFFFFFu, bad);
 }
 
 struct StepOut { int r, done, cat; float reward[3]; bool applied, pass; int winner; };

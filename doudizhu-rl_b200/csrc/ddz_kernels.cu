@@ -88,32 +88,19 @@ DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {
 // ------------------------------------------------------------------------------------------------
 // deal
 // ------------------------------------------------------------------------------------------------
-DDZ_DEV bool redeal(Env& e, const int8_t* perm, const int8_t* lord_pile, int pool_games, int B, int b) {
-    uint32_t games = e.meta >> 8;
-    size_t row = (size_t)(games % (uint32_t)pool_games) * B + b;
-    bool ok = deal(e, perm + 54 * row, lord_pile ? lord_pile[row] : 0);
-    if (!ok) {  // refuse: leave an empty, finished env with the sticky error bit
-#pragma unroll
-        for (int q = 0; q < 3; q++) { e.hand[q] = e.hist[q] = e.recent[q] = 0; }
-        e.meta = (e.meta & 0xFFFFFF00u) | 1u | 4u | 0x20u;
-    }
-    return ok;
-}
-
 __global__ void __launch_bounds__(kEnvs) k_reset(void* state, const int8_t* __restrict__ perm,
                                                  const int8_t* __restrict__ lord_pile, int pool_games,
                                                  int only_done, int64_t* stats, int B) {
-    int b = blockIdx.x * kEnvs + threadIdx.x;
-    int err = 0;
-    if (b < B) {
-        StateView v = view_of(state, B);
-        Env e = load_env(v, b);
-        if (!only_done || e.done()) {
-            err = !redeal(e, perm, lord_pile, pool_games, B, b);
-            store_env(v, b, e);
-        }
-    }
-    stat_add(stats, 7, err);
+    const int b = blockIdx.x * kEnvs + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = b < B;
+    StateView v = view_of(state, B);
+    Env e;
+    if (valid) e = load_env(v, b); else e.meta = 0;
+    const bool want = valid && (!only_done || e.done());
+    const unsigned int need = __ballot_sync(0xFFFFFFFFu, want);
+    const unsigned int bad = warp_deal(need, e, perm, lord_pile, pool_games, B, b, lane);
+    if (want) store_env(v, b, e);
+    if (lane == 0 && bad && stats) atomicAdd((unsigned long long*)&stats[7], (unsigned long long)__popc(bad));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,12 +196,12 @@ struct OutArgs {
     int32_t* offsets; uint64_t* actions_u64; float4* actions_f32; long long cap; float4* face;
 };
 
-struct WindowEmitter {    // enumerate_legal functor: keeps the moves that fall into the warp's current window
+
+struct SeqWindowEmitter {  // enumerate_legal functor: keeps the moves that fall into the warp's current window
     uint64_t* out; int pos;   // pos = index of the next move relative to the window start (may be negative)
     DDZ_DEV void operator()(uint64_t mv) { if ((unsigned)pos < (unsigned)kWin) out[pos] = mv; pos++; }
 };
-
-struct IndexedWindowEmitter {   // enumerate_legal_warp functor: move number idx of the env goes to window slot base + idx
+struct WindowEmitter {   // enumerate_legal_warp functor: move number idx of the env goes to window slot base + idx
     uint64_t* out; int base;
     DDZ_DEV void operator()(int idx, uint64_t mv) { const unsigned rel = (unsigned)(base + idx); if (rel < (unsigned)kWin) out[rel] = mv; }
 };
@@ -263,11 +250,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
 
     // ---- 2. state transition
     Env e;
+    e.meta = 0;
     uint64_t hand = 0, last = 0;
+    Masks hm{0, 0, 0, 0};
+    Rule ru{true, 0, 1, 0};
     int n = 0;
     long long d_games = 0, d_lord = 0, d_down = 0, d_up = 0, d_steps = 0, d_retl = 0, d_retf = 0, d_err = 0, d_pass = 0;
     if (MODE == kRaw) {
-        if (valid) { hand = raw_hands[b]; last = raw_lasts[b]; n = count_legal(masks_of(hand), last); }
+        if (valid) {
+            hand = raw_hands[b]; last = raw_lasts[b];
+            hm = masks_of(hand); ru = rule_of(last); n = count_legal(hm, ru, last != 0);
+        }
     } else if (valid) {
         StateView v = view_of(state, B);
         int prev_off = 0, prev_end = 0;
@@ -301,10 +294,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             if (a.done) a.done[b] = (uint8_t)e.done();
             if (a.cat) a.cat[b] = (int8_t)o_cat;
             if (a.reward) { a.reward[3 * (size_t)b] = rw0; a.reward[3 * (size_t)b + 1] = rw1; a.reward[3 * (size_t)b + 2] = rw2; }
-            if (a.perm && e.done()) d_err += !redeal(e, a.perm, a.lord_pile, a.pool_games, B, b);
-            store_env(v, b, e);
         }
-        if (EMIT && !e.done()) { hand = hand_to_move(e); last = trick_of(e); n = count_legal(masks_of(hand), last); }
+    }
+    if (MODE != kRaw) {
+        if (STEP) {
+            if (a.perm) {   // re-deal the finished envs, the whole warp working on one of them at a time
+                const unsigned int need = __ballot_sync(FULL, valid && e.done());
+                d_err += (warp_deal(need, e, a.perm, a.lord_pile, a.pool_games, B, b, lane) >> lane) & 1u;
+            }
+            if (valid) store_env(view_of(state, B), b, e);
+        }
+        if (valid && EMIT && !e.done()) {
+            hand = hand_to_move(e); last = trick_of(e);
+            hm = masks_of(hand); ru = rule_of(last); n = count_legal(hm, ru, last != 0);
+        }
     }
     if (STEP) {
         stat_add(stats, 0, d_games); stat_add(stats, 1, d_lord); stat_add(stats, 2, d_down); stat_add(stats, 3, d_up);
@@ -353,17 +356,21 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         do {
             const bool inwin = n > 0 && local < w0 + kWin && local + n > w0;
             if (inwin && n <= kHeavy) {                     // short lists: one env per lane
-                WindowEmitter em{sm.moves, local - w0};
-                enumerate_legal(masks_of(hand), last, em);
+                SeqWindowEmitter em{sm.moves, local - w0};
+                enumerate_legal(hm, ru, last != 0, em);
                 disagree |= (em.pos != local - w0 + n);
             }
             unsigned int heavy = __ballot_sync(FULL, inwin && n > kHeavy);
             while (heavy) {                                 // long lists: the whole warp expands one env at a time
                 const int src = __ffs(heavy) - 1; heavy &= heavy - 1;
-                const uint64_t h = __shfl_sync(FULL, hand, src), l = __shfl_sync(FULL, last, src);
+                Masks sm_; Rule sr;
+                sm_.g1 = __shfl_sync(FULL, hm.g1, src); sm_.g2 = __shfl_sync(FULL, hm.g2, src);
+                sm_.g3 = __shfl_sync(FULL, hm.g3, src); sm_.g4 = __shfl_sync(FULL, hm.g4, src);
+                const int rpack = __shfl_sync(FULL, (int)ru.lead | (ru.cat << 1) | (ru.len << 8) | (ru.val << 16) | ((last != 0) << 24), src);
+                sr.lead = rpack & 1; sr.cat = (rpack >> 1) & 127; sr.len = (rpack >> 8) & 255; sr.val = (rpack >> 16) & 255;
                 const int loc = __shfl_sync(FULL, local, src), nn = __shfl_sync(FULL, n, src);
-                IndexedWindowEmitter em{sm.moves, loc - w0};
-                disagree |= (enumerate_legal_warp(masks_of(h), l, lane, em) != nn);
+                WindowEmitter em{sm.moves, loc - w0};
+                disagree |= (enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em) != nn);
             }
             __syncwarp();
 
