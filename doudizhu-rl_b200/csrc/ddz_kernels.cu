@@ -480,6 +480,31 @@ __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restri
     }
 }
 
+// Batched dqn.py:50-71: per env, the index of the best-scoring legal move (first maximum, like torch.argmax), or with
+// probability epsilon a uniformly random one (e_greedy_action).  One lane per env; segments are short (mean 5.6).
+__global__ void __launch_bounds__(256) k_select_actions(const float* __restrict__ q, const int32_t* __restrict__ offsets,
+                                                        float epsilon, uint64_t seed, uint64_t env0, uint32_t stepno,
+                                                        int32_t* __restrict__ choice, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int lo = offsets[b], n = offsets[b + 1] - lo;
+    int best = -1;
+    if (n > 0) {
+        bool explore = false;
+        if (epsilon > 0.f) {
+            // two independent Philox draws: counter word 3 distinguishes them from the env's move stream
+            const uint32_t u = philox(seed ^ 0x9E3779B97F4A7C15ull, env0 + (uint64_t)b, stepno);
+            explore = (float)(u >> 8) * (1.0f / 16777216.0f) < epsilon;
+            if (explore) best = (int)(philox(seed ^ 0xD1B54A32D192ED03ull, env0 + (uint64_t)b, stepno) % (uint32_t)n);
+        }
+        if (!explore) {
+            float bv = q[lo]; best = 0;
+            for (int i = 1; i < n; i++) { const float v = q[lo + i]; if (v > bv) { bv = v; best = i; } }
+        }
+    }
+    choice[b] = best;
+}
+
 }  // namespace ddz
 
 // ------------------------------------------------------------------------------------------------
@@ -616,6 +641,14 @@ int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void*
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_encode_actions<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(actions_u64, n, (float4*)out);
     DDZ_LAUNCH_CHECK("k_encode_actions");
+    return 0;
+}
+
+int ddz_select_actions(const float* q, const int32_t* offsets, float epsilon, uint64_t seed, uint64_t env0,
+                       uint32_t stepno, int32_t* choice, int B, void* stream) {
+    if (!q || !offsets || !choice || B <= 0 || !(epsilon >= 0.f && epsilon <= 1.f)) return DDZ_E_ARG;
+    k_select_actions<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, offsets, epsilon, seed, env0, stepno, choice, B);
+    DDZ_LAUNCH_CHECK("k_select_actions");
     return 0;
 }
 

@@ -347,6 +347,27 @@ class BatchedEnv:
         """int64 [B,3,15] (envi.py:26,42-43)."""
         return self._recent_t()
 
+    def get_state_prob(self):
+        """native get_state_prob (envi.py:94): float32 [B,120] = the two probability planes of the face, flattened."""
+        return self.face[:, self.C - 2:].reshape(self.B, 120)
+
+    @classmethod
+    def get_state_prob_manual(cls, known60, size1, size2, device=None):
+        """native get_state_prob_manual (server/core.py:26-33): known60 = thermometer one-hot [.., 60] of (played cards +
+        own hand), size1 / size2 = cards left of the next / next-next player.  float32 [.., 120] (SURVEY App. A form A)."""
+        k = torch.as_tensor(known60, device=device).reshape(-1, 15, 4)
+        known = (k != 0).sum(-1)
+        total = torch.tensor([4] * 13 + [1, 1], device=k.device)
+        unknown = (total - known).clamp_(min=0)
+        thermo = (torch.arange(4, device=k.device)[None, None, :] < unknown[:, :, None]).to(torch.float32).reshape(-1, 60)
+        s1 = torch.as_tensor(size1, device=k.device, dtype=torch.float32).reshape(-1, 1)
+        s2 = torch.as_tensor(size2, device=k.device, dtype=torch.float32).reshape(-1, 1)
+        tot = s1 + s2
+        p1 = torch.where(tot > 0, s1 / tot, torch.zeros_like(tot))
+        p2 = torch.where(tot > 0, s2 / tot, torch.zeros_like(tot))
+        out = torch.cat([thermo * p1, thermo * p2], -1)
+        return out if out.shape[0] > 1 else out[0]
+
     @property
     def is_done(self):
         return ((self._fields()[1] >> 2) & 1).to(torch.bool)
@@ -521,6 +542,30 @@ class BatchedEnvCooperation(BatchedEnv):
 class BatchedEnvCooperationSimplify(BatchedEnv):
     """envi.py:201-217, C=6"""
     VARIANT = N.FACE_SIMPLIFY
+
+
+class MoveGenerator:
+    """Batched r.get_moves (envi.py:111) with preallocated buffers: n independent (hand, last) pairs per call."""
+
+    def __init__(self, n, device=None, max_moves_per_hand=N.MAX_LEGAL):
+        if not torch.cuda.is_available():
+            raise N.DdzError("MoveGenerator needs a CUDA device")
+        self.n = int(n)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.cap = self.n * int(max_moves_per_hand)
+        self._ws = torch.zeros(max(1, N.lib.ddz_workspace_bytes(self.n) // 4 + 1), dtype=torch.int32, device=self.device)
+        self.offsets = torch.zeros(self.n + 1, dtype=torch.int32, device=self.device)
+        self.actions = torch.zeros(self.cap, dtype=torch.int64, device=self.device)
+        self.stats = torch.zeros(16, dtype=torch.int64, device=self.device)
+
+    def generate(self, hands_packed, lasts_packed):
+        """packed int64 [n] device tensors -> (actions int64 [cap] (first offsets[n] valid), offsets int32 [n+1]); async."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_legal_moves(hands_packed.data_ptr(), lasts_packed.data_ptr(), self._ws.data_ptr(),
+                                          self.offsets.data_ptr(), self.actions.data_ptr(), self.cap,
+                                          self.stats.data_ptr(), self.n,
+                                          torch.cuda.current_stream(self.device).cuda_stream), "ddz_legal_moves")
+        return self.actions, self.offsets
 
 
 def get_moves(hands, lasts, device=None):

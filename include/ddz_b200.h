@@ -115,6 +115,13 @@ int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspac
 /* Env.batch_arr2onehot over packed moves (envi.py:113,140-146): out float32[n][15][4] */
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream);
 
+/* Batched DQNFirst.greedy_action / e_greedy_action (dqn.py:50-71): q float32[offsets[B]] are the Q-values the caller's
+ * network gave to the legal moves (CSR order).  choice[b] = index of the first maximum of env b's segment (torch.argmax
+ * semantics), or, with probability epsilon, a uniformly random index (Philox keyed by seed, env0+b, stepno); -1 for an
+ * env without legal moves (finished).  Feed choice to ddz_step / ddz_rollout_step with DDZ_CHOICE_INDEX. */
+int ddz_select_actions(const float* q, const int32_t* offsets, float epsilon, uint64_t seed, uint64_t env0,
+                       uint32_t stepno, int32_t* choice, int B, void* stream);
+
 /* env.face only (envi.py:87-217) */
 int ddz_encode_face(const void* state, int variant, float* face, int B, void* stream);
 

@@ -610,3 +610,85 @@ int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t 
     free(jobs); free(th);
     return total;
 }
+
+/* ------------------------------------------------------------------ */
+/* exhaustive bound on the length of a legal-move list                  */
+/* ------------------------------------------------------------------ */
+/* Lead-move count of a hand in closed form (popcount x binomial), the same arithmetic the device uses; checked
+ * against the enumerating generators in tests.  Used to PROVE DDZ_REF_MAX_LEGAL: the legal set is monotone in the
+ * hand (containment), so the maximum over all hands is reached by a 20-card hand (the landlord's deal). */
+static const int BINOM[16][6] = {
+    {1, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0}, {1, 2, 1, 0, 0, 0}, {1, 3, 3, 1, 0, 0}, {1, 4, 6, 4, 1, 0},
+    {1, 5, 10, 10, 5, 1}, {1, 6, 15, 20, 15, 6}, {1, 7, 21, 35, 35, 21}, {1, 8, 28, 56, 70, 56},
+    {1, 9, 36, 84, 126, 126}, {1, 10, 45, 120, 210, 252}, {1, 11, 55, 165, 330, 462}, {1, 12, 66, 220, 495, 792},
+    {1, 13, 78, 286, 715, 1287}, {1, 14, 91, 364, 1001, 2002}, {1, 15, 105, 455, 1365, 3003}};
+static int binom_(int n, int k) { return (n < 0 || k > n || k > 5) ? 0 : BINOM[n][k]; }
+static int lines_(unsigned R, int lmin, int lmax) {
+    unsigned t = R; int n = 0;
+    for (int L = 2; L <= lmax; L++) { t &= R >> (L - 1); if (L >= lmin) n += __builtin_popcount(t); }
+    return n;
+}
+static int planes_(unsigned g3, int nk, int lmax) {
+    unsigned R = g3 & 0xFFF, t = R; int n = 0;
+    for (int L = 2; L <= lmax; L++) { t &= R >> (L - 1); n += __builtin_popcount(t) * binom_(nk - L, L); }
+    return n;
+}
+int ddz_ref_count_lead_closed(const int8_t hand[15]) {
+    unsigned g[5] = {0, 0, 0, 0, 0};
+    for (int r = 0; r < 15; r++) for (int k = 1; k <= 4; k++) if (hand[r] >= k) g[k] |= 1u << r;
+    if (!g[1]) return 0;
+    int n1 = __builtin_popcount(g[1]), n2 = __builtin_popcount(g[2]), n3 = __builtin_popcount(g[3]), n4 = __builtin_popcount(g[4]);
+    int n = n1 + n2 + n3 + n4 + n3 * (n1 - 1) + n3 * (n2 - 1);
+    n += lines_(g[1] & 0xFFF, 5, 12) + lines_(g[2] & 0xFFF, 3, 10) + lines_(g[3] & 0xFFF, 2, 6);
+    n += planes_(g[3], n1, 5) + planes_(g[3], n2, 4);
+    n += ((g[1] & 0x6000) == 0x6000);
+    n += n4 * binom_(n1 - 1, 2) + n4 * binom_(n2 - 1, 2);
+    return n;
+}
+typedef struct { int first_lo, first_hi; int best; int8_t arg[15]; long long visited; } ex_job;
+static void ex_rec(int8_t* h, int r, int left, ex_job* j) {
+    if (r == 15) {
+        if (left != 0) return;
+        j->visited++;
+        int c = ddz_ref_count_lead_closed(h);
+        if (c > j->best) { j->best = c; memcpy(j->arg, h, 15); }
+        return;
+    }
+    int cap = r < 13 ? 4 : 1;
+    int rest = 0; for (int q = r + 1; q < 15; q++) rest += q < 13 ? 4 : 1;
+    for (int c = 0; c <= cap && c <= left; c++) {
+        if (left - c > rest) continue;
+        h[r] = (int8_t)c; ex_rec(h, r + 1, left - c, j);
+    }
+    h[r] = 0;
+}
+static void* ex_worker(void* arg) {
+    ex_job* j = (ex_job*)arg;
+    int8_t h[15];
+    for (int code = j->first_lo; code < j->first_hi; code++) {   /* code = counts of ranks 0 and 1 */
+        memset(h, 0, 15);
+        h[0] = (int8_t)(code / 5); h[1] = (int8_t)(code % 5);
+        if (h[0] + h[1] <= 20) ex_rec(h, 2, 20 - h[0] - h[1], j);
+    }
+    return 0;
+}
+/* max number of lead moves over ALL 20-card hands of one deck; argmax hand in best_hand; *visited = hands examined */
+int ddz_ref_max_lead_moves_exhaustive(int nthreads, int8_t best_hand[15], long long* visited) {
+    ensure();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 25) nthreads = 25;
+    ex_job jobs[25]; pthread_t th[25];
+    for (int i = 0; i < nthreads; i++) {
+        memset(&jobs[i], 0, sizeof jobs[i]);
+        jobs[i].first_lo = 25 * i / nthreads; jobs[i].first_hi = 25 * (i + 1) / nthreads;
+        pthread_create(&th[i], 0, ex_worker, &jobs[i]);
+    }
+    int best = 0; long long vis = 0;
+    for (int i = 0; i < nthreads; i++) {
+        pthread_join(th[i], 0);
+        vis += jobs[i].visited;
+        if (jobs[i].best > best) { best = jobs[i].best; if (best_hand) memcpy(best_hand, jobs[i].arg, 15); }
+    }
+    if (visited) *visited = vis;
+    return best;
+}

@@ -91,6 +91,8 @@ def lib():
         L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
                                       C.POINTER(C.c_double)]
         L.ddz_ref_rollout.restype = C.c_int64
+        L.ddz_ref_count_lead_closed.argtypes = [i8p]
+        L.ddz_ref_max_lead_moves_exhaustive.argtypes = [C.c_int, i8p, C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -238,3 +240,16 @@ def rollout(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_game
                               _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64),
                               C.byref(cs), C.byref(sec))
     return int(n), float(sec.value), stats, int(cs.value)
+
+
+def count_lead_closed(hand):
+    h = _i8(hand)
+    return int(lib().ddz_ref_count_lead_closed(_ptr(h, C.c_int8)))
+
+
+def max_lead_moves_exhaustive(nthreads=8):
+    """(max lead moves over all 20-card hands, an argmax hand, hands visited)"""
+    best = np.zeros(15, np.int8)
+    vis = C.c_longlong(0)
+    m = lib().ddz_ref_max_lead_moves_exhaustive(int(nthreads), _ptr(best, C.c_int8), C.byref(vis))
+    return int(m), best, int(vis.value)

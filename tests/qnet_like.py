@@ -1,0 +1,25 @@
+"""A Q-network with the reference's input/output contract (net.py:81-102: face [N,C,15,4] or [C,15,4], actions [N,15,4]
+-> [N,1]) for tests of the batched Q-scoring shim.  Architecture as described in SURVEY.md section 2 (#4): the C face
+channels + 1 action channel go through (1,k) convolutions with stride (1,4), k = 1..4, and a (15,1) "shunzi"
+convolution, then two linear layers.  Written from that description for test purposes; weights are random."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class QNetLike(nn.Module):
+    def __init__(self, face_channels, width=32):
+        super().__init__()
+        cin = face_channels + 1
+        self.rank_convs = nn.ModuleList([nn.Conv2d(cin, width, (1, k), (1, 4)) for k in (1, 2, 3, 4)])
+        self.line_conv = nn.Conv2d(cin, width, (15, 1), 1)
+        self.fc1 = nn.Linear(width * (15 + 4), 64)
+        self.fc2 = nn.Linear(64, 1)
+
+    def forward(self, face, actions):
+        if face.dim() == 3:
+            face = face.unsqueeze(0).repeat((actions.shape[0], 1, 1, 1))
+        x = torch.cat((face, actions.unsqueeze(1)), dim=1)
+        r = torch.cat([c(x) for c in self.rank_convs], -1).max(-1).values.flatten(1)      # [N, width*15]
+        l = self.line_conv(x).flatten(1)                                                  # [N, width*4]
+        return self.fc2(F.relu(self.fc1(torch.cat([r, l], -1))))

@@ -162,3 +162,23 @@ def test_illegal_and_done_steps_are_noops(oracle):
     assert (cat == -1).all() and (r == 0).all() and not done.any()
     assert np.array_equal(before[0], after[0]) and rb.stats[7] == 2
     assert ((after[1] >> 5) & 1).all()                                           # sticky error flag
+
+
+def test_max_legal_bound_is_proved_exhaustively(oracle):
+    """DDZ_MAX_LEGAL = 512: the closed-form lead count equals the enumerators, legal sets are monotone in the hand, and
+    the maximum over ALL 153 009 740 twenty-card hands of one deck is 497 (SURVEY.md App. B asked for this proof)."""
+    rng = np.random.default_rng(9)
+    deck = np.array([i // 4 for i in range(52)] + [13, 14])
+    z = np.zeros(15, np.int8)
+    for _ in range(2000):
+        h = np.bincount(rng.permutation(deck)[:rng.integers(1, 21)], minlength=15).astype(np.int8)
+        n = oracle.count_lead_closed(h)
+        assert n == len(oracle.get_moves(h, z, fast=True))
+        bigger = h.copy()
+        r = int(rng.integers(0, 15))
+        if bigger[r] < (4 if r < 13 else 1):
+            bigger[r] += 1
+            assert oracle.count_lead_closed(bigger) >= n                      # monotone
+    best, hand, visited = oracle.max_lead_moves_exhaustive(8)
+    assert visited == 153009740 and best == 497 and hand.sum() == 20
+    assert len(oracle.get_moves(hand, z)) == 497 <= oracle.MAX_LEGAL
