@@ -81,10 +81,24 @@ DDZ_DEV long long warp_sum_ll(long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
-DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {
-    v = warp_sum_ll(v);
-    if ((threadIdx.x & 31) == 0 && v != 0 && stats) atomicAdd((unsigned long long*)&stats[slot], (unsigned long long)v);
+DDZ_DEV void stat_add(int64_t* stats, int slot, long long v) {   // per-lane values are small (|v| <= a few hundred)
+    const int s = __reduce_add_sync(0xFFFFFFFFu, (int)v);
+    if ((threadIdx.x & 31) == 0 && s != 0 && stats) atomicAdd((unsigned long long*)&stats[slot], (unsigned long long)(long long)s);
 }
+// per-lane step summary (see `sf` in k_env) -> the stats vector; rewards per game.py:109-118
+DDZ_DEV void step_stats(int64_t* stats, unsigned int sf, const int32_t* rewards, int extra_err) {
+    const int over = (sf >> 2) & 1, winner = (sf >> 3) & 3;
+    stat_add(stats, 4, sf & 1);
+    stat_add(stats, 9, (sf >> 1) & 1);
+    stat_add(stats, 0, over);
+    stat_add(stats, 1, over && winner == 1);
+    stat_add(stats, 2, over && winner == 2);
+    stat_add(stats, 3, over && winner == 0);
+    stat_add(stats, 5, over ? (winner == 1 ? rewards[1] : -rewards[1]) : 0);
+    stat_add(stats, 6, over ? (winner == 1 ? -(rewards[0] + rewards[2]) : rewards[0] + rewards[2]) : 0);
+    stat_add(stats, 7, (int)((sf >> 5) & 3) + extra_err);
+}
+
 // ------------------------------------------------------------------------------------------------
 // deal
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +208,7 @@ struct StepArgs {
 };
 struct OutArgs {
     int32_t* offsets; uint64_t* actions_u64; float4* actions_f32; long long cap; float4* face;
+    int static_tiles;   // 1: the whole grid is resident at once, tile = launch position (no ticket round trip)
 };
 
 
@@ -230,18 +245,19 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
 
     // ---- 1. tile ticket: tiles are handed out in start order, so every lower tile is already running
     int t = blockIdx.x * kWarpsPerCta + wib;
-    unsigned int epoch = 0, stepno = a.stepno;
+    unsigned int epoch = 0, autostep = 0, stepno = a.stepno;   // epoch / autostep: valid in lane 0 until broadcast below
     if (EMIT) {
-        unsigned int autostep = 0;
-        if (lane == 0) { t = (int)atomicAdd(&ws.h->ticket, 1u); epoch = ws.h->epoch; autostep = ws.h->auto_step; }
-        t = __shfl_sync(FULL, t, 0);
-        epoch = __shfl_sync(FULL, epoch, 0);
-        autostep = __shfl_sync(FULL, autostep, 0);
-        if (STEP && a.stepno == DDZ_STEPNO_AUTO) stepno = autostep;
+        // Tiles must be handed out so that every lower tile is already running (the look-back waits on them): by a
+        // ticket in start order, or -- when the whole grid is resident at once -- simply by launch position, which
+        // saves a dependent round trip before the first state load.
+        if (lane == 0) {
+            if (!o.static_tiles) t = (int)atomicAdd(&ws.h->ticket, 1u);
+            epoch = ws.h->epoch; autostep = ws.h->auto_step;
+        }
+        if (!o.static_tiles) t = __shfl_sync(FULL, t, 0);
         if (lane < 5) sm.lut[lane] = make_float4(lane > 0 ? 1.f : 0.f, lane > 1 ? 1.f : 0.f, lane > 2 ? 1.f : 0.f, lane > 3 ? 1.f : 0.f);
         __syncwarp();
     }
-    const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
     if (t < nt) {
     const int b0 = t * 32, b = b0 + lane;
     const bool valid = b < B;
@@ -255,39 +271,55 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
     Masks hm{0, 0, 0, 0};
     Rule ru{true, 0, 1, 0};
     int n = 0;
-    long long d_games = 0, d_lord = 0, d_down = 0, d_up = 0, d_steps = 0, d_retl = 0, d_retf = 0, d_err = 0, d_pass = 0;
+    unsigned int sf = 0;   // per-lane step summary for the stats: bit0 stepped, bit1 pass, bit2 game over, bits3-4 winner, bits5-6 errors
     if (MODE == kRaw) {
         if (valid) {
             hand = raw_hands[b]; last = raw_lasts[b];
             hm = masks_of(hand); ru = rule_of(last); n = count_legal(hm, ru, last != 0);
         }
-    } else if (valid) {
-        StateView v = view_of(state, B);
-        int prev_off = 0, prev_end = 0;
-        if (STEP) { prev_off = a.offsets[b]; prev_end = a.offsets[b + 1]; }   // independent of the state: issued together
-        e = load_env(v, b);
+    }
+    int prev_off = 0, prev_end = 0;
+    uint64_t choice_raw = 0;
+    if (MODE != kRaw && valid) {
+        if (STEP) {   // independent of the state: all of these loads are in flight together
+            prev_off = a.offsets[b]; prev_end = a.offsets[b + 1];
+            if (a.mode == DDZ_CHOICE_MOVE) choice_raw = ((const uint64_t*)a.choice)[b];
+            else if (a.mode != DDZ_CHOICE_PHILOX) choice_raw = ((const uint32_t*)a.choice)[b];
+        }
+        e = load_env(view_of(state, B), b);
+        if (STEP && a.perm) {   // most envs will not need it this step, but an L2 prefetch of the env's next deal
+            const char* prow = reinterpret_cast<const char*>(a.perm) +   // takes the HBM latency off the re-deal path
+                               54 * ((size_t)((e.meta >> 8) % (uint32_t)a.pool_games) * B + b);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(prow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + 53));
+        }
+    }
+    if (EMIT) {   // broadcast what lane 0 read at the top -- after the state loads were issued, not before
+        epoch = __shfl_sync(FULL, epoch, 0);
+        autostep = __shfl_sync(FULL, autostep, 0);
+        if (STEP && a.stepno == DDZ_STEPNO_AUTO) stepno = autostep;
+    }
+    const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
+    if (MODE != kRaw && valid) {
         if (STEP) {
             int o_r = 0, o_cat = -1;
             float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
             if (!e.done()) {
                 const int base = prev_off, cnt = prev_end - prev_off;
                 long long idx = -1;
-                if (a.mode == DDZ_CHOICE_INDEX) idx = ((const int32_t*)a.choice)[b];
-                else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)(((const uint32_t*)a.choice)[b] % (uint32_t)cnt) : -1;
+                if (a.mode == DDZ_CHOICE_INDEX) idx = (int32_t)(uint32_t)choice_raw;
+                else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)((uint32_t)choice_raw % (uint32_t)cnt) : -1;
                 else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, stepno) % (uint32_t)cnt) : -1;
                 else {
-                    uint64_t want = ((const uint64_t*)a.choice)[b];
+                    const uint64_t want = choice_raw;
                     for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
                 }
-                if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; d_err = 1; }
+                if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; sf += 32u; }
                 else {
                     StepOut so = apply_move(e, a.actions[base + idx], a.rewards);
                     o_r = so.r; o_cat = so.cat; rw0 = so.reward[0]; rw1 = so.reward[1]; rw2 = so.reward[2];
-                    d_steps = 1; d_pass = so.pass;
-                    if (so.done) {
-                        d_games = 1; d_lord = (so.winner == 1); d_down = (so.winner == 2); d_up = (so.winner == 0);
-                        d_retl = (long long)rw1; d_retf = (long long)rw0 + (long long)rw2;
-                    }
+                    sf |= 1u | (so.pass ? 2u : 0u);
+                    if (so.done) sf |= 4u | ((unsigned int)so.winner << 3);
                 }
             }
             if (a.r) a.r[b] = (int8_t)o_r;
@@ -300,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         if (STEP) {
             if (a.perm) {   // re-deal the finished envs, the whole warp working on one of them at a time
                 const unsigned int need = __ballot_sync(FULL, valid && e.done());
-                d_err += (warp_deal(need, e, a.perm, a.lord_pile, a.pool_games, B, b, lane) >> lane) & 1u;
+                sf += ((warp_deal(need, e, a.perm, a.lord_pile, a.pool_games, B, b, lane) >> lane) & 1u) << 5;
             }
             if (valid) store_env(view_of(state, B), b, e);
         }
@@ -309,13 +341,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             hm = masks_of(hand); ru = rule_of(last); n = count_legal(hm, ru, last != 0);
         }
     }
-    if (STEP) {
-        stat_add(stats, 0, d_games); stat_add(stats, 1, d_lord); stat_add(stats, 2, d_down); stat_add(stats, 3, d_up);
-        stat_add(stats, 4, d_steps); stat_add(stats, 5, d_retl); stat_add(stats, 6, d_retf); stat_add(stats, 7, d_err);
-        stat_add(stats, 9, d_pass);
-    }
+    if (STEP && !EMIT) step_stats(stats, sf, a.rewards, 0);
     if (EMIT) {
-    // ---- 3. warp scan, publish the warp total for the look-back
+    // ---- 3. warp scan, publish the warp total for the look-back (other tiles wait on it: nothing else comes first)
     int inc = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
@@ -373,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 disagree |= (enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em) != nn);
             }
             __syncwarp();
+            if (w0 == 0) trace(t, 7);
 
             if (w0 == 0) {
                 // look-back: kLookBack windows of 32 predecessor tiles per round trip
@@ -430,14 +459,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         trace(t, 6);
     }
     }
-    stat_add(stats, 7, disagree);
+    step_stats(stats, STEP ? sf : 0u, a.rewards, disagree);
     }  // EMIT
     }  // t < nt
     if (EMIT && lane == 0) {
         const unsigned int fin = atomicAdd(&ws.h->finished, 1u);
         if (fin == nwarps - 1) {                            // the last warp of the launch re-arms the workspace
             ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = epoch + 1;
-            if (STEP) ws.h->auto_step = stepno + 1;
+            if (STEP) ws.h->auto_step = (a.stepno == DDZ_STEPNO_AUTO ? autostep : a.stepno) + 1;
             __threadfence();
         }
     }
@@ -529,7 +558,18 @@ static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts,
     const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem);
     Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
     const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, o, ws, stats, B);
+    static int resident = -1;      // CTAs of this instantiation that fit on the device at once (per process, device 0's shape)
+    if (resident < 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env<V, MODE>, kThreads, smem) != cudaSuccess)
+            return cuda_fail(cudaGetLastError(), "occupancy query");
+        resident = per_sm * sms;
+    }
+    OutArgs oo = o;
+    oo.static_tiles = (grid <= resident) ? 1 : 0;
+    k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, oo, ws, stats, B);
     DDZ_LAUNCH_CHECK("k_env");
     return 0;
 }
@@ -575,7 +615,7 @@ int ddz_observe(const void* state, void* workspace, int variant, int32_t* offset
     if (!state || !workspace || !offsets || !actions_u64 || B <= 0 || cap < 0) return DDZ_E_ARG;
     if (face && ddz_face_channels(variant) < 0) return DDZ_E_ARG;
     StepArgs a; memset(&a, 0, sizeof a);
-    OutArgs o{offsets, actions_u64, (float4*)actions_f32, cap, (float4*)face};
+    OutArgs o{offsets, actions_u64, (float4*)actions_f32, cap, (float4*)face, 0};
     return launch_env_v<kObserve>(variant, face != nullptr, const_cast<void*>(state), a, o, workspace, stats, B,
                                   (cudaStream_t)stream);
 }
@@ -602,7 +642,7 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
     StepArgs a;
     int rc = fill_step_args(a, offsets, actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
-    OutArgs o{nullptr, nullptr, nullptr, 0, nullptr};
+    OutArgs o{nullptr, nullptr, nullptr, 0, nullptr, 0};
     return launch_env<-1, kStepOnly>(state, nullptr, nullptr, a, o, nullptr, stats, B, (cudaStream_t)stream);
 }
 
@@ -621,7 +661,7 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
     int rc = fill_step_args(a, prev_offsets, prev_actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
     a.perm = perm; a.lord_pile = lord_pile; a.pool_games = perm ? pool_games : 1;
-    OutArgs o{out_offsets, out_actions_u64, (float4*)out_actions_f32, cap, (float4*)face};
+    OutArgs o{out_offsets, out_actions_u64, (float4*)out_actions_f32, cap, (float4*)face, 0};
     return launch_env_v<kStepObserve>(variant, face != nullptr, state, a, o, workspace, stats, B, (cudaStream_t)stream);
 }
 
@@ -629,7 +669,7 @@ int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspac
                     uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream) {
     if (!hands || !lasts || !workspace || !offsets || !actions_u64 || n <= 0 || cap < 0) return DDZ_E_ARG;
     StepArgs a; memset(&a, 0, sizeof a);
-    OutArgs o{offsets, actions_u64, nullptr, cap, nullptr};
+    OutArgs o{offsets, actions_u64, nullptr, cap, nullptr, 0};
     return launch_env<-1, kRaw>(nullptr, hands, lasts, a, o, workspace, stats, n, (cudaStream_t)stream);
 }
 

@@ -32,13 +32,14 @@ tr = buf.cpu().numpy().reshape(nt, 8).astype(np.float64)
 t0 = tr[:, 0].min()
 tr = (tr - t0) / 1e3    # microseconds
 tr[tr < 0] = np.nan
-names = ["start", "phaseA_end", "face_begin", "face_end", "act_begin", "lookback_end", "act_end"]
+names = ["start", "phaseA_end", "face_begin", "face_end", "act_begin", "lookback_end", "act_end", "enum0_end"]
 out = {}
 for i, nme in enumerate(names):
     col = tr[:, i]
     out[nme] = {"min": float(np.nanmin(col)), "p50": float(np.nanmedian(col)), "p90": float(np.nanpercentile(col, 90)),
                 "max": float(np.nanmax(col))}
-dur = {"phaseA": tr[:, 1] - tr[:, 0], "face_rows": tr[:, 3] - tr[:, 2], "lookback": tr[:, 5] - tr[:, 4],
+dur = {"phaseA": tr[:, 1] - tr[:, 0], "face_rows": tr[:, 3] - tr[:, 2], "enum_window0": tr[:, 7] - tr[:, 4],
+       "lookback_wait": tr[:, 5] - tr[:, 7],
        "enum_and_action_rows": tr[:, 6] - tr[:, 5], "warp_lifetime": np.maximum(tr[:, 3], tr[:, 6]) - tr[:, 0]}
 for k, v in dur.items():
     out["dur_" + k] = {"mean": float(np.nanmean(v)), "p50": float(np.nanmedian(v)), "p99": float(np.nanpercentile(v, 99)),
@@ -47,6 +48,9 @@ end = np.fmax(tr[:, 3], tr[:, 6])
 out["warp_end_percentiles_us"] = {str(q): float(np.nanpercentile(end, q)) for q in (1, 10, 25, 50, 75, 90, 99, 100)}
 out["kernel_span_us"] = float(np.nanmax(tr))
 even = np.arange(nt) % 2 == 0
+odd = np.arange(nt) % 2 == 1
+for nme, sel in (("even", ~odd), ("odd", odd)):
+    out[nme + "_tiles"] = {k: float(np.nanmean(v[sel])) for k, v in dur.items()}
 out["even_tiles_end_p50"] = float(np.nanmedian(np.maximum(tr[even, 3], tr[even, 6])))
 out["odd_tiles_end_p50"] = float(np.nanmedian(np.maximum(tr[~even, 3], tr[~even, 6])))
 print(json.dumps(out, indent=1))
