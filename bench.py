@@ -56,6 +56,15 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(envs):
+    """DRAM bytes per launch of the step kernel from the committed ncu --set full capture (same workload), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return d["traffic_bytes_per_launch"] if envs == 131072 else None
+    except Exception:
+        return None
+
+
 def bytes_per_env_step(nbar, C=CHANNELS):
     """ALGORITHMIC bytes of one env-step = one env's share of one k_env launch: state read + write,
     previous offsets (2 x 4) and chosen move (8) read, r/done/cat/reward (15) written, new offset (4), packed list
@@ -297,7 +306,8 @@ def run_ours(args):
                        "games_finished": int(gstats[0].item()),
                        "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))},
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": B * eb,
                          "algorithmic_bytes_per_env": eb, "ms_per_launch": kern_ms},
             "e2e": {"value": B * K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,

@@ -97,12 +97,12 @@ static float best_ms(F launch) {
     return best;
 }
 
-int main() {
-    const int nwarps = 4096, grid = nwarps / 4;
+int main(int argc, char** argv) {
+    const int nwarps = argc > 1 ? atoi(argv[1]) : 4096, grid = nwarps / 4;
     const size_t nvec = (size_t)nwarps * kVecPerWarp, bytes = nvec * 16;
     float4* out; CK(cudaMalloc(&out, bytes + 4096));
     CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 7680));
-    printf("{\"bytes\": %zu", bytes);
+    printf("{\"nwarps\": %d, \"bytes\": %zu", nwarps, bytes);
 #define REPORT(name, call) { float ms = best_ms([&] { call; }); printf(", \"%s_GBs\": %.0f", name, bytes / ms / 1e6); }
     REPORT("aligned512", (k_aligned<false><<<grid, 128>>>(out, nwarps)));
     REPORT("aligned512_cs", (k_aligned<true><<<grid, 128>>>(out, nwarps)));
