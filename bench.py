@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--prefill", type=int, default=150, help="untimed env-steps that bring the games to their steady-state mix")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=2, help="stream-parallel env groups per GPU (1 = one chain of launches)")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-group information run")
     return ap.parse_args()
 
 
@@ -176,13 +178,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the env has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B, K, W, G = args.envs, args.steps, args.warmup, POOL_GAMES
+    B, K, W, P, NG = args.envs, args.steps, args.warmup, POOL_GAMES, args.groups
     env0 = rank * B                                   # global env ids keep results independent of the GPU count
-    perm, lord = D.random_deals(B, seed=SEED + 1000 * rank, pool_games=G)
-    perm_d, lord_d = torch.as_tensor(perm).to(dev), torch.as_tensor(lord).to(dev)
-    env = D.BatchedEnvCooperation(B, seed=SEED, device=dev, env0=env0, max_actions_per_env=160)
-    env.prepare(perm_d, lord_d, pool_games=G)
-    env.observe()
+    perm, lord = D.random_deals(B, seed=SEED + 1000 * rank, pool_games=P)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -190,100 +188,133 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    step_kw = dict(mode=D.native.CHOICE_PHILOX, perm=perm_d, lord_pile=lord_d, pool_games=G)
     sampler = ClockSampler(local)       # samples from here to the end of the e2e region: the same kernel runs throughout
     sampler.start()
-    for _ in range(args.prefill + W):
-        env.rollout_step(**step_kw)
+
+    # ---------------- the rank's envs as NG stream-parallel groups (one group's load-only prologue and tail
+    # overlap the other group's store phase); device-resident deal pool, Philox moves on the device
+    ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=NG, seed=SEED, device=dev, env0=env0, max_actions_per_env=160)
+    ge.prepare(perm, lord, pool_games=P)
+    for _ in range(args.prefill):
+        ge.rollout_step()
+    ge.capture(steps_per_graph=2)       # the loop is launch-bound from Python: replay the ping-pong pair as a CUDA graph
+    for _ in range(max(W, 3)):
+        ge.replay()
+    ge.join()
     torch.cuda.synchronize(dev)
-    if int(env.stats[7].item()):
+    if int(ge.stats[7].item()):
         raise SystemExit("env reported errors during warm-up")
 
-    # ---------------- timed region: device-resident inputs, CUDA events on the launching (current) stream.
-    # The rollout loop is launch-bound from Python (~0.15 ms of host work per step), so the ping-pong pair of
-    # launches is captured in a CUDA graph and replayed; an odd K ends with one eager step.
-    graphed = D.GraphedRollout(env, perm_d, lord_d, G)
-    for _ in range(max(W, 3)):
-        graphed.replay()
-    torch.cuda.synchronize(dev)
-    stats0 = env.stats.clone()
-    nrep = K // 2
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(nrep + 2)]
+    # ---------------- timed region: exactly K env-steps of every env, CUDA events on the launching (current) stream
+    stats0 = ge.stats.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev[0].record()
-    for k in range(nrep):
-        graphed.replay()                    # two launches of k_env<cooperation, step+observe>
-        ev[k + 1].record()
+    e0.record()
+    ge._fork()
+    for _ in range(K // 2):
+        ge.replay()                     # per group: two launches of k_env<cooperation, step+observe>
     if K % 2:
-        env.rollout_step(**step_kw)
-    ev[nrep + 1].record()
+        ge.rollout_step()
+    ge.join()
+    e1.record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[nrep + 1])
-    kern_ms = total_ms / K                  # average launch duration of the one kernel of a step (gaps included)
-    dstats_t = (env.stats - stats0).clone()
+    total_ms = e0.elapsed_time(e1)
+    dstats_t = (ge.stats - stats0).clone()
     dstats = dstats_t.cpu().numpy()
-    if int(env.stats[7].item()):
+    if int(ge.stats[7].item()):
         raise SystemExit("env reported errors during the timed region")
     local_steps = int(dstats[4])
     assert local_steps == B * K, (local_steps, B * K)   # every env applied one move per step (finished ones re-dealt)
     nbar = float(dstats[8]) / local_steps
 
-    # ---------------- for information: the same K steps launched one by one from Python (host-bound)
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    g0.record()
-    for _ in range(K):
-        env.rollout_step(**step_kw)
-    g1.record()
-    torch.cuda.synchronize(dev)
-    eager_ms = g0.elapsed_time(g1) / K
+    # ---------------- for information: one group (a single chain of launches), graph replay and eager Python loop
+    info = {}
+    if NG > 1 and not args.no_single:
+        perm_d, lord_d = torch.as_tensor(perm).to(dev), torch.as_tensor(lord).to(dev)
+        one = D.BatchedEnvCooperation(B, seed=SEED, device=dev, env0=env0, max_actions_per_env=160)
+        one.prepare(perm_d, lord_d, pool_games=P)
+        kw = dict(perm=perm_d, lord_pile=lord_d, pool_games=P)
+        for _ in range(args.prefill):
+            one.rollout_step(**kw)
+        gr = D.GraphedRollout(one, perm_d, lord_d, P)
+        for _ in range(3):
+            gr.replay()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize(dev)
+        g0.record()
+        for _ in range(K // 2):
+            gr.replay()
+        g1.record()
+        for _ in range(K):
+            one.rollout_step(**kw)
+        g2.record()
+        torch.cuda.synchronize(dev)
+        info = {"single_group_graph_ms_per_step": g0.elapsed_time(g1) / (2 * (K // 2)),
+                "single_group_eager_python_ms_per_step": g1.elapsed_time(g2) / K}
+        del one, gr, perm_d, lord_d
+        torch.cuda.empty_cache()
 
-    # ---------------- e2e: the same env-step through the host-facing API (HostRollout) with HOST buffers every step:
-    # H2D of the step's entropy (int32 [B], pinned) and of the deal-pool refill (one slot of host-made permutations
-    # every REFILL steps = about one game length, the rate at which deals are consumed), D2H of the step's results
-    # (r, done, cat, reward) into pinned memory.  All copies are inside the timed region.
-    R, REFILL = 4, 64
+    # ---------------- e2e: the same env-step through the host-facing API (HostRollout, one per group) with HOST buffers
+    # every step: H2D of the step's entropy (int32 [B], pinned) and of the deal-pool refill (one slot of host-made
+    # permutations every REFILL steps = about one game length, the rate at which deals are consumed), D2H of the step's
+    # results (r, done, cat, reward) into pinned memory.  All copies are inside the timed region.
+    R, REFILL, Bg = 4, 64, B // NG
     rng = np.random.default_rng(SEED + rank)
-    ent_h = [torch.as_tensor(rng.integers(0, 1 << 31, B, dtype=np.int64).astype(np.int32)).pin_memory() for _ in range(R)]
+    ent_h = [[torch.as_tensor(rng.integers(0, 1 << 31, Bg, dtype=np.int64).astype(np.int32)).pin_memory() for _ in range(R)]
+             for _ in range(NG)]
     pool_h = []
     for i in range(2):
-        pp, ll = D.random_deals(B, seed=SEED + 77 + i + 1000 * rank)
+        pp, ll = D.random_deals(Bg, seed=SEED + 77 + i + 1000 * rank)
         pool_h.append((torch.as_tensor(pp).pin_memory(), torch.as_tensor(ll).pin_memory()))
-    host = D.HostRollout(env, perm_d, lord_d, G)
-    sink = 0
+    hosts = []
+    for g, env in enumerate(ge.envs):
+        with torch.cuda.stream(ge.streams[g]):
+            pg, lg, _ = ge._pool[g]
+            hosts.append(D.HostRollout(env, pg, lg, P))
+    sink = [0]
+    pending = [[None, None] for _ in range(NG)]
 
     def e2e_step(i):
-        if i % REFILL == 0:
-            pp, ll = pool_h[(i // REFILL) % 2]
-            host.refill((i // REFILL) % G, pp, ll)
-        return host.step(ent_h[i % R])
+        for g in range(NG):
+            with torch.cuda.stream(ge.streams[g]):
+                if i % REFILL == 0:
+                    pp, ll = pool_h[(i // REFILL) % 2]
+                    hosts[g].refill((i // REFILL) % P, pp, ll)
+                old = pending[g][i & 1]
+                if old is not None:                               # the host reads the results of step i-2
+                    D.HostRollout.wait(old)
+                    sink[0] += int(old.done[0]) + int(old.r[-1])
+                pending[g][i & 1] = hosts[g].step(ent_h[g][i % R])
 
-    for i in range(max(W, 3)):
+    for i in range(max(W, 4)):
         e2e_step(i)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ge.join()
     barrier()
-    stats_e0 = env.stats.clone()
-    e0.record()
-    last = None
+    stats_e0 = ge.stats.clone()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    ge._fork()
     for i in range(K):
-        last = e2e_step(i)
-    e1.record()
+        e2e_step(i)
+    for g in range(NG):
+        for res in pending[g]:
+            D.HostRollout.wait(res)
+    ge.join()
+    x1.record()
     barrier()
-    D.HostRollout.wait(last)
     clocks = sampler.stop()
-    sink += int(last.done.sum())                      # the host really reads the results
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_steps = int((env.stats - stats_e0)[4].item())
-    assert e2e_steps == B * K
-    h2d = 4 * B + (55 * B * ((K + REFILL - 1) // REFILL)) // K
-    d2h = host.results_h[0].nbytes
-    if int(env.stats[7].item()):
+    e2e_ms = x0.elapsed_time(x1)
+    e2e_K = K
+    e2e_steps = int((ge.stats - stats_e0)[4].item())
+    assert e2e_steps == B * e2e_K and sink[0] > -(1 << 40)
+    h2d = 4 * B + (55 * B * ((e2e_K + REFILL - 1) // REFILL)) // e2e_K
+    d2h = NG * hosts[0].results_h[0].nbytes
+    if int(ge.stats[7].item()):
         raise SystemExit("env reported errors during the e2e region")
 
     # ---------------- reduce over ranks: MAX of the device times, SUM of the work
     total_ms = D.sharding.max_over_ranks(total_ms, dev)
     e2e_ms = D.sharding.max_over_ranks(e2e_ms, dev)
-    kern_ms = D.sharding.max_over_ranks(kern_ms, dev)
     gstats = D.sharding.allreduce_stats(dstats_t, side_stream=torch.cuda.Stream(dev) if world > 1 else None)
     torch.cuda.synchronize(dev)
     all_steps = int(gstats[4].item())
@@ -292,28 +323,32 @@ def run_ours(args):
         peak, peak_src = peaks()
         eb = bytes_per_env_step(nbar)
         value = all_steps / (total_ms * 1e-3)
-        kern_gbs = B * eb / (kern_ms * 1e-3) / 1e9
+        step_ms = total_ms / K
+        kern_gbs = B * eb / (step_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 4 per-GPU slice: %d envs/GPU, lord-vs-random rollout (all seats uniform "
-                                   "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % B,
-                       "envs_per_gpu": B, "face_channels": CHANNELS, "mean_legal_moves": nbar,
-                       "prefill_steps": args.prefill, "pool_games": G, "parallelism": "env-shard x%d" % world,
-                       "launch": "CUDA graph replay of the 2-launch ping-pong pair", "eager_python_ms_per_step": eager_ms,
-                       "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
-                       "games_finished": int(gstats[0].item()),
-                       "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))},
+            "config": dict({"workload": "BASELINE config 4 per-GPU slice: %d envs/GPU, lord-vs-random rollout (all seats uniform "
+                                        "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % B,
+                            "envs_per_gpu": B, "env_groups_per_gpu": NG, "face_channels": CHANNELS, "mean_legal_moves": nbar,
+                            "prefill_steps": args.prefill, "pool_games": P, "parallelism": "env-shard x%d" % world,
+                            "launch": "CUDA graph replay of the 2-launch ping-pong pair, one chain per env group",
+                            "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
+                            "games_finished": int(gstats[0].item()),
+                            "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))}, **info),
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": B * eb,
-                         "algorithmic_bytes_per_env": eb, "ms_per_launch": kern_ms},
-            "e2e": {"value": B * K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
-                    "api": "HostRollout.step(entropy_host) + refill(slot, perm_host, lord_host) every %d steps; "
-                           "results (r, done, cat, reward) read back to pinned host memory every step" % REFILL},
-            "gpu_launches": K,
+                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B) if NG == 1 else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
+                         "algorithmic_bytes_per_step": B * eb, "ms_per_step": step_ms, "launches_in_flight": NG,
+                         "note": "achieved = algorithmic bytes of one step of all envs / wall time per step; the step is "
+                                 "%d concurrent launches of the same kernel (one per env group)" % NG},
+            "e2e": {"value": B * e2e_K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_K, "steps": e2e_K,
+                    "api": "HostRollout.step(entropy_host) per env group (native ddz_pipe_step: H2D entropy -> k_env -> D2H "
+                           "r/done/cat/reward on copy streams), results of step t-2 read by the host every step, "
+                           "refill(slot, perm_host, lord_host) uploads host-made deals every %d steps" % REFILL},
+            "gpu_launches": K * NG,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -665,6 +665,94 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
     return launch_env_v<kStepObserve>(variant, face != nullptr, state, a, o, workspace, stats, B, (cudaStream_t)stream);
 }
 
+// ---- host-buffer pipeline -------------------------------------------------------------------------
+struct ddz_pipe {
+    cudaStream_t h2d, d2h;
+    cudaEvent_t in_ready[2], in_free[2], kernel_done[2], out_done[2], stage_free, stage_full;
+    unsigned long long step;
+    bool stage_used;
+};
+#define DDZ_CUDA(call, what)                                   \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what);     \
+    } while (0)
+
+ddz_pipe* ddz_pipe_create(void) {
+    ddz_pipe* p = new ddz_pipe();
+    p->step = 0; p->stage_used = false;
+    bool ok = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&p->in_ready[0], &p->in_ready[1], &p->in_free[0], &p->in_free[1], &p->kernel_done[0],
+                          &p->kernel_done[1], &p->out_done[0], &p->out_done[1], &p->stage_free, &p->stage_full};
+    for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cuda_fail(cudaGetLastError(), "ddz_pipe_create"); delete p; return nullptr; }
+    return p;
+}
+void ddz_pipe_destroy(ddz_pipe* p) {
+    if (!p) return;
+    cudaStreamDestroy(p->h2d); cudaStreamDestroy(p->d2h);
+    cudaEvent_t evs[] = {p->in_ready[0], p->in_ready[1], p->in_free[0], p->in_free[1], p->kernel_done[0],
+                         p->kernel_done[1], p->out_done[0], p->out_done[1], p->stage_free, p->stage_full};
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    delete p;
+}
+int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
+                  const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                  const void* host_choice, void* dev_choice, uint64_t seed, uint64_t env0, uint32_t stepno,
+                  const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                  void* results_dev, void* results_host, size_t results_bytes,
+                  int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                  float* face, int64_t* stats, int B, void* stream) {
+    if (!p || !host_choice || !dev_choice || !results_dev || !results_host || B <= 0) return DDZ_E_ARG;
+    if (results_bytes < (size_t)B * 15) return DDZ_E_ARG;
+    cudaStream_t main_s = (cudaStream_t)stream;
+    const int k = (int)(p->step & 1);
+    const bool primed = p->step >= 2;                          // events of this parity were recorded two steps ago
+    // H2D of this step's entropy, once the kernel that last read dev_choice (two steps ago) is done
+    if (primed) DDZ_CUDA(cudaStreamWaitEvent(p->h2d, p->in_free[k], 0), "wait in_free");
+    DDZ_CUDA(cudaMemcpyAsync(dev_choice, host_choice, (size_t)B * 4, cudaMemcpyHostToDevice, p->h2d), "H2D entropy");
+    DDZ_CUDA(cudaEventRecord(p->in_ready[k], p->h2d), "record in_ready");
+    DDZ_CUDA(cudaStreamWaitEvent(main_s, p->in_ready[k], 0), "wait in_ready");
+    // results_dev alternates between two sets: the D2H that last read this set was issued two steps ago
+    if (primed) DDZ_CUDA(cudaStreamWaitEvent(main_s, p->out_done[k], 0), "wait out_done");
+    char* rd = (char*)results_dev;
+    const size_t off_reward = ((size_t)3 * B + 15) / 16 * 16;
+    int rc = ddz_rollout_step(state, workspace, variant, prev_offsets, prev_actions_u64, dev_choice, DDZ_CHOICE_MOD, seed,
+                              env0, stepno, rewards, perm, lord_pile, pool_games, (int8_t*)rd, (uint8_t*)rd + B,
+                              (int8_t*)rd + 2 * (size_t)B, (float*)(rd + off_reward), out_offsets, out_actions_u64,
+                              out_actions_f32, cap, face, stats, B, stream);
+    if (rc) return rc;
+    DDZ_CUDA(cudaEventRecord(p->kernel_done[k], main_s), "record kernel_done");
+    DDZ_CUDA(cudaEventRecord(p->in_free[k], main_s), "record in_free");
+    DDZ_CUDA(cudaStreamWaitEvent(p->d2h, p->kernel_done[k], 0), "wait kernel_done");
+    DDZ_CUDA(cudaMemcpyAsync(results_host, results_dev, results_bytes, cudaMemcpyDeviceToHost, p->d2h), "D2H results");
+    DDZ_CUDA(cudaEventRecord(p->out_done[k], p->d2h), "record out_done");
+    p->step++;
+    return 0;
+}
+int ddz_pipe_wait(ddz_pipe* p, int slot) {
+    if (!p || slot < 0 || slot > 1) return DDZ_E_ARG;
+    DDZ_CUDA(cudaEventSynchronize(p->out_done[slot]), "ddz_pipe_wait");
+    return 0;
+}
+int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot, const int8_t* host_perm,
+                    const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord, int B, void* stream) {
+    if (!p || !pool_perm_slot || !pool_lord_slot || !host_perm || !host_lord || !stage_perm || !stage_lord || B <= 0)
+        return DDZ_E_ARG;
+    cudaStream_t main_s = (cudaStream_t)stream;
+    if (p->stage_used) DDZ_CUDA(cudaStreamWaitEvent(p->h2d, p->stage_free, 0), "wait stage_free");
+    DDZ_CUDA(cudaMemcpyAsync(stage_perm, host_perm, (size_t)B * 54, cudaMemcpyHostToDevice, p->h2d), "H2D perm");
+    DDZ_CUDA(cudaMemcpyAsync(stage_lord, host_lord, (size_t)B, cudaMemcpyHostToDevice, p->h2d), "H2D lord");
+    DDZ_CUDA(cudaEventRecord(p->stage_full, p->h2d), "record stage_full");
+    DDZ_CUDA(cudaStreamWaitEvent(main_s, p->stage_full, 0), "wait stage_full");
+    DDZ_CUDA(cudaMemcpyAsync(pool_perm_slot, stage_perm, (size_t)B * 54, cudaMemcpyDeviceToDevice, main_s), "D2D perm");
+    DDZ_CUDA(cudaMemcpyAsync(pool_lord_slot, stage_lord, (size_t)B, cudaMemcpyDeviceToDevice, main_s), "D2D lord");
+    DDZ_CUDA(cudaEventRecord(p->stage_free, main_s), "record stage_free");
+    p->stage_used = true;
+    return 0;
+}
+
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,
                     uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream) {
     if (!hands || !lasts || !workspace || !offsets || !actions_u64 || n <= 0 || cap < 0) return DDZ_E_ARG;

@@ -450,6 +450,99 @@ class GraphedRollout:
         self.env._n_total = None
 
 
+class GroupedEnv:
+    """The envs of one GPU as several independent groups, each with its own stream, state and CSR outputs.
+
+    The step kernel has a load-only prologue (no stores for the first ~8 us) and a tail; a single chain of launches
+    pays both every step.  With two (or more) unsynchronised chains one group's prologue and tail overlap another
+    group's store phase (+17 % env-steps/s at 131 072 envs, profiles/r1_two_stream_experiment.json) -- the classic
+    double-buffered actor: while group A's observations are consumed, group B steps.  Global env ids (Philox stream,
+    deal rows) are those of one big batch, so every env's trajectory is independent of the grouping.
+    """
+
+    def __init__(self, env_cls, num_envs, groups=2, seed=None, device=None, env0=0, **kw):
+        if num_envs % groups:
+            raise ValueError("num_envs must be divisible by groups")
+        self.B, self.G, self.Bg = int(num_envs), int(groups), int(num_envs) // int(groups)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.G)]
+        self.envs = []
+        for g in range(self.G):
+            with torch.cuda.stream(self.streams[g]):
+                self.envs.append(env_cls(self.Bg, seed=seed, device=self.device, env0=env0 + g * self.Bg, **kw))
+        self.graphs = None
+        self._pool = None
+
+    def _fork(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join(self):
+        """make the current stream wait for every group's stream"""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            cur.wait_event(ev)
+
+    def prepare(self, perm, lord_pile, pool_games=1):
+        """perm int8 [pool_games*B,54], lord_pile int8 [pool_games*B] for the whole batch (host or device); each group
+        keeps its slice as its device-resident deal pool."""
+        P = int(pool_games)
+        perm_t = torch.as_tensor(perm).reshape(P, self.B, 54)
+        lord_t = torch.as_tensor(lord_pile).reshape(P, self.B)
+        self._pool = []
+        self._fork()
+        for g, env in enumerate(self.envs):
+            with torch.cuda.stream(self.streams[g]):
+                pg = perm_t[:, g * self.Bg:(g + 1) * self.Bg].to(self.device).contiguous()
+                lg = lord_t[:, g * self.Bg:(g + 1) * self.Bg].to(self.device).contiguous()
+                self._pool.append((pg, lg, P))
+                env.prepare(pg, lg, pool_games=P)
+                env.observe()
+        self.join()
+
+    def rollout_step(self, **kw):
+        """one fused env-step of every group, each on its own stream (Philox moves, re-deal from the group's pool)"""
+        for g, env in enumerate(self.envs):
+            with torch.cuda.stream(self.streams[g]):
+                pg, lg, P = self._pool[g]
+                env.rollout_step(perm=pg, lord_pile=lg, pool_games=P, **kw)
+
+    def capture(self, steps_per_graph=8):
+        """one CUDA graph per group with `steps_per_graph` (even) fused env-steps; replay() launches all of them"""
+        if steps_per_graph % 2:
+            raise ValueError("steps_per_graph must be even (ping-pong buffers)")
+        torch.cuda.synchronize(self.device)
+        self.graphs, self.steps_per_graph = [], int(steps_per_graph)
+        for g, env in enumerate(self.envs):
+            pg, lg, P = self._pool[g]
+            env._ensure()
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            stepno = env._stepno
+            with torch.cuda.graph(graph, stream=self.streams[g]):
+                for _ in range(self.steps_per_graph):
+                    env.rollout_step(perm=pg, lord_pile=lg, pool_games=P, auto_step=True)
+            env._stepno = stepno
+            self.graphs.append(graph)
+        torch.cuda.synchronize(self.device)
+
+    def replay(self):
+        for g, graph in enumerate(self.graphs):
+            with torch.cuda.stream(self.streams[g]):
+                graph.replay()
+            self.envs[g]._stepno += self.steps_per_graph
+            self.envs[g]._n_total = None
+
+    @property
+    def stats(self):
+        """int64 [16] summed over the groups (call join() / synchronize first)"""
+        return torch.stack([e.stats for e in self.envs]).sum(0)
+
+
 class HostRollout:
     """Rollout driven from HOST buffers: the call a host-side user makes per env-step.
 
@@ -457,7 +550,8 @@ class HostRollout:
     batched form of envi.py:83 random.choice) and gets the step's results (r, done, cat, reward) back in pinned host
     memory.  Deck permutations are host-supplied too: `refill(slot, perm, lord_pile)` uploads one slot of the
     device-resident deal pool (each env consumes one deal per game, so one slot per ~game length keeps it fresh).
-    Copies run on their own streams: the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t.
+    The per-step sequencing lives in the library (ddz_pipe_step): H2D and D2H run on the pipe's own copy streams, so
+    the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t, and a step costs one native call.
     """
 
     def __init__(self, env, perm, lord_pile, pool_games):
@@ -467,66 +561,140 @@ class HostRollout:
         self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.G, B).contiguous()
         self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
         self.results_h = [StepResults(B, "cpu", pin=True) for _ in range(2)]
-        self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(2)]
-        self.ev_k = [torch.cuda.Event() for _ in range(2)]
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]
-        self.ev_in_free = [torch.cuda.Event() for _ in range(2)]
-        self.i = 0
         self._stage = None
+        with torch.cuda.device(dev):
+            self._pipe = N.lib.ddz_pipe_create()
+        if not self._pipe:
+            raise N.DdzError("ddz_pipe_create failed: %s" % N.lib.ddz_last_error().decode())
+        self.i = 0
         env._ensure()
-        main = torch.cuda.current_stream(dev)
-        for e in self.ev_out + self.ev_in_free:
-            e.record(main)
+
+    def __del__(self):
+        pipe, self._pipe = getattr(self, "_pipe", None), None
+        if pipe and N is not None and getattr(N, "lib", None) is not None:   # module globals may be gone at interpreter exit
+            N.lib.ddz_pipe_destroy(pipe)
 
     def refill(self, slot, perm, lord_pile):
         """upload one slot of the deal pool: perm int8 [B,54], lord_pile int8 [B], pinned host memory.  The upload
         lands in a staging buffer on the copy stream (overlapping the kernels); the slot itself is replaced by a
         device-to-device copy ordered between two steps, so no kernel ever reads a half-written permutation."""
-        B, main = self.env.B, torch.cuda.current_stream(self.env.device)
+        env, B = self.env, self.env.B
         if self._stage is None:
-            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=self.env.device),
-                           torch.empty(B, dtype=torch.int8, device=self.env.device))
-            self._stage_free, self._stage_full = torch.cuda.Event(), torch.cuda.Event()
-            self._stage_free.record(main)
-        with torch.cuda.stream(self.h2d):
-            self.h2d.wait_event(self._stage_free)
-            self._stage[0].copy_(torch.as_tensor(perm).reshape(B, 54), non_blocking=True)
-            self._stage[1].copy_(torch.as_tensor(lord_pile).reshape(B), non_blocking=True)
-            self._stage_full.record(self.h2d)
-        main.wait_event(self._stage_full)
-        self.perm_d[slot].copy_(self._stage[0], non_blocking=True)
-        self.lord_d[slot].copy_(self._stage[1], non_blocking=True)
-        self._stage_free.record(main)
+            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=env.device),
+                           torch.empty(B, dtype=torch.int8, device=env.device))
+        perm, lord_pile = torch.as_tensor(perm), torch.as_tensor(lord_pile)
+        self._keep = (perm, lord_pile)
+        with torch.cuda.device(env.device):
+            N.check(N.lib.ddz_pipe_refill(self._pipe, self.perm_d[slot].data_ptr(), self.lord_d[slot].data_ptr(),
+                                          perm.data_ptr(), lord_pile.data_ptr(), self._stage[0].data_ptr(),
+                                          self._stage[1].data_ptr(), B, env._stream()), "ddz_pipe_refill")
 
     def step(self, entropy_h):
         """entropy_h: pinned int32 [B].  Returns the StepResults (pinned host views) this step will fill; they are
         valid after `wait(results)` (or any later synchronisation)."""
         env, k = self.env, self.i & 1
-        main = torch.cuda.current_stream(env.device)
-        with torch.cuda.stream(self.h2d):
-            self.h2d.wait_event(self.ev_in_free[k])          # the kernel that read entropy_d[k] two steps ago is done
-            self.entropy_d[k].copy_(entropy_h, non_blocking=True)
-            self.ev_in[k].record(self.h2d)
-        main.wait_event(self.ev_in[k])
-        main.wait_event(self.ev_out[1 - env._cur])           # the D2H that read this result set has finished
-        env.rollout_step(choice=self.entropy_d[k], mode=N.CHOICE_MOD, perm=self.perm_d, lord_pile=self.lord_d,
-                         pool_games=self.G)
-        self.ev_k[k].record(main)
-        self.ev_in_free[k].record(main)
-        res_d, res_h = env._results[env._res], self.results_h[env._res]
-        with torch.cuda.stream(self.d2h):
-            self.d2h.wait_event(self.ev_k[k])
-            res_h.buf.copy_(res_d.buf, non_blocking=True)
-            self.ev_out[env._res].record(self.d2h)
-        res_h._event = self.ev_out[env._res]
+        nxt = 1 - env._cur
+        res_d, res_h = env._results[nxt], self.results_h[k]
+        with torch.cuda.device(env.device):
+            N.check(N.lib.ddz_pipe_step(
+                self._pipe, env._p(env._state), env._p(env._ws), env.VARIANT,
+                env._p(env._offsets[env._cur]), env._p(env._actions_u64[env._cur]),
+                entropy_h.data_ptr(), self.entropy_d[k].data_ptr(), env.seed, env.env0, env._stepno,
+                env._rewards.data_ptr(), self.perm_d.data_ptr(), self.lord_d.data_ptr(), self.G,
+                res_d.buf.data_ptr(), res_h.buf.data_ptr(), res_d.nbytes,
+                env._p(env._offsets[nxt]), env._p(env._actions_u64[nxt]), env._p(env._actions_f32), env.cap,
+                env._p(env._face), env._p(env.stats), env.B, env._stream()), "ddz_pipe_step")
+        env._cur, env._res, env._fresh, env._n_total = nxt, nxt, True, None
+        env._stepno += 1
+        res_h._slot, res_h._pipe = k, self._pipe
         self.i += 1
         return res_h
 
     @staticmethod
     def wait(results):
-        results._event.synchronize()
+        N.check(N.lib.ddz_pipe_wait(results._pipe, results._slot), "ddz_pipe_wait")
         return results
+
+
+class GraphedHostRollout:
+    """HostRollout with the per-step host work captured in CUDA graphs.
+
+    One graph = two env-steps of one env (group): [H2D entropy -> k_env -> D2H results] twice, reading / writing FIXED
+    pinned host buffers.  There are `nsets` such graphs with their own pinned buffers, so the host fills set s+1 and
+    reads the results of set s-1 while set s is in flight.  Per pair of steps the host does: write 2 entropy arrays,
+    `submit(s)`, later `wait(s)` and read 2 result sets -- no per-step Python/launch overhead.  Deck permutations come
+    from the host through `refill` exactly as in HostRollout.
+    """
+
+    def __init__(self, env, perm, lord_pile, pool_games, stream=None, nsets=2):
+        self.env, self.P, self.nsets = env, int(pool_games), int(nsets)
+        dev, B = env.device, env.B
+        self.stream = stream if stream is not None else torch.cuda.Stream(dev)
+        self.perm_d = env._to_dev(perm, torch.int8).reshape(self.P, B, 54).contiguous()
+        self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.P, B).contiguous()
+        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.entropy_in = [[torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)] for _ in range(self.nsets)]
+        self.results_out = [[StepResults(B, "cpu", pin=True) for _ in range(2)] for _ in range(self.nsets)]
+        self.done_ev = [torch.cuda.Event() for _ in range(self.nsets)]
+        self._stage = None
+        self.h2d = torch.cuda.Stream(dev)
+        env._ensure()
+        torch.cuda.synchronize(dev)
+        self.graphs = []
+        stepno = env._stepno
+        self.side = torch.cuda.Stream(dev)
+        for s in range(self.nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                for k in range(2):
+                    self.entropy_d[k].copy_(self.entropy_in[s][k], non_blocking=True)
+                    env.rollout_step(choice=self.entropy_d[k], mode=N.CHOICE_MOD, perm=self.perm_d, lord_pile=self.lord_d,
+                                     pool_games=self.P, auto_step=True)
+                    # the D2H of this step's results runs on a forked branch, next to the following step's kernel
+                    fork = torch.cuda.Event()
+                    fork.record(self.stream)
+                    self.side.wait_event(fork)
+                    with torch.cuda.stream(self.side):
+                        self.results_out[s][k].buf.copy_(env._results[env._res].buf, non_blocking=True)
+                joined = torch.cuda.Event()
+                joined.record(self.side)
+                self.stream.wait_event(joined)
+            self.graphs.append(g)
+        env._stepno = stepno
+        torch.cuda.synchronize(dev)
+        for e in self.done_ev:
+            e.record(self.stream)
+
+    def refill(self, slot, perm, lord_pile):
+        """upload one slot of the deal pool (pinned host arrays) through a staging buffer; the slot is replaced by a
+        device-to-device copy on this rollout's stream, i.e. between two graph replays"""
+        B, dev = self.env.B, self.env.device
+        if self._stage is None:
+            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=dev), torch.empty(B, dtype=torch.int8, device=dev))
+            self._stage_free, self._stage_full = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(self.stream)
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(self._stage_free)
+            self._stage[0].copy_(torch.as_tensor(perm).reshape(B, 54), non_blocking=True)
+            self._stage[1].copy_(torch.as_tensor(lord_pile).reshape(B), non_blocking=True)
+            self._stage_full.record(self.h2d)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._stage_full)
+            self.perm_d[slot].copy_(self._stage[0], non_blocking=True)
+            self.lord_d[slot].copy_(self._stage[1], non_blocking=True)
+            self._stage_free.record(self.stream)
+
+    def submit(self, s):
+        """two env-steps from entropy_in[s][0..1]; results land in results_out[s][0..1] (valid after wait(s))"""
+        with torch.cuda.stream(self.stream):
+            self.graphs[s].replay()
+            self.done_ev[s].record(self.stream)
+        self.env._stepno += 2
+        self.env._n_total = None
+
+    def wait(self, s):
+        self.done_ev[s].synchronize()
+        return self.results_out[s]
 
 
 class BatchedEnvComplicated(BatchedEnv):

@@ -122,6 +122,29 @@ int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void*
 int ddz_select_actions(const float* q, const int32_t* offsets, float epsilon, uint64_t seed, uint64_t env0,
                        uint32_t stepno, int32_t* choice, int B, void* stream);
 
+/* ---- host-buffer pipeline (the e2e path): one call per env-step does, without any Python in between,
+ *   copy stream : H2D  host_choice (pinned, B x 4 bytes)  ->  dev_choice[k]            (k = step parity)
+ *   main stream : wait; ddz_rollout_step(choice = dev_choice[k], DDZ_CHOICE_MOD, results -> results_dev)
+ *   copy stream : wait; D2H  results_dev (results_bytes, contiguous r|done|cat|reward)  ->  results_host (pinned)
+ * so the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t.  The pipe object only owns two CUDA
+ * streams and a few events; every buffer stays caller-owned.  results_dev must alternate between two buffers (the
+ * caller's ping-pong sets); ddz_pipe_wait(slot) blocks the host until the D2H issued by the step with that parity
+ * (slot = step index & 1) has landed.  ddz_pipe_refill uploads one slot of the deal pool through a caller-provided
+ * staging buffer and replaces the slot with a device-to-device copy ordered between two steps. */
+typedef struct ddz_pipe ddz_pipe;
+ddz_pipe* ddz_pipe_create(void);
+void ddz_pipe_destroy(ddz_pipe* p);
+int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
+                  const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                  const void* host_choice, void* dev_choice, uint64_t seed, uint64_t env0, uint32_t stepno,
+                  const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                  void* results_dev, void* results_host, size_t results_bytes,
+                  int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                  float* face, int64_t* stats, int B, void* stream);
+int ddz_pipe_wait(ddz_pipe* p, int slot);
+int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot, const int8_t* host_perm,
+                    const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord, int B, void* stream);
+
 /* env.face only (envi.py:87-217) */
 int ddz_encode_face(const void* state, int variant, float* face, int B, void* stream);
 

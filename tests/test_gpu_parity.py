@@ -492,3 +492,71 @@ def test_dqn_lord_vs_random_matches_oracle_env(D, oracle):
     st = env.stats.cpu().numpy()
     assert np.array_equal(st[[0, 1, 2, 3, 4]], ref.stats[[0, 1, 2, 3, 4]]) and st[0] > B
     assert st[7] == 0
+
+
+def test_grouped_env_trajectories_do_not_depend_on_grouping(D, oracle):
+    """GroupedEnv: 2 and 4 stream-parallel groups (eager steps, then CUDA-graph replays) reach exactly the state a
+    single batch reaches, because Philox and the deal rows are keyed by the global env id."""
+    B, P, seed = 4096, 4, 5
+    perm, lord = D.random_deals(B, seed=3, pool_games=P)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    single = D.BatchedEnvCooperation(B, seed=seed)
+    single.prepare(pd, ld, pool_games=P)
+    steps = 6 + 3 * 8
+    for _ in range(steps):
+        single.rollout_step(perm=pd, lord_pile=ld, pool_games=P)
+    torch.cuda.synchronize()
+    want_f, want_m = single._fields()
+    for groups in (2, 4):
+        ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=groups, seed=seed)
+        ge.prepare(perm, lord, pool_games=P)
+        for _ in range(6):
+            ge.rollout_step()
+        ge.capture(steps_per_graph=8)
+        for _ in range(3):
+            ge.replay()
+        ge.join()
+        torch.cuda.synchronize()
+        f = torch.cat([e._fields()[0] for e in ge.envs], 1)
+        m = torch.cat([e._fields()[1] for e in ge.envs])
+        assert torch.equal(f, want_f) and torch.equal(m, want_m), groups
+        face = torch.cat([e.face for e in ge.envs])
+        assert torch.equal(face, single.face)
+        keep = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+        assert torch.equal(ge.stats[keep], single.stats[keep]) and int(ge.stats[7]) == 0
+
+
+def test_graphed_host_rollout_matches_oracle(D, oracle):
+    """GraphedHostRollout: [H2D entropy -> step -> D2H results] x 2 captured per graph, two buffer sets in flight."""
+    B, P = 1024, 2
+    rng = np.random.default_rng(77)
+    perm, lord = D.random_deals(B, seed=14, pool_games=P)
+    pool = [np.array(perm.reshape(P, B, 54)), np.array(lord.reshape(P, B))]
+    env = D.BatchedEnvCooperation(B)
+    env.prepare(perm, lord, pool_games=P)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=P)
+    host = D.GraphedHostRollout(env, perm, lord, P)
+    want = {}
+    for it in range(40):
+        s = it % 2
+        if it >= 2:                                   # results of the submission two pairs ago
+            res = host.wait(s)
+            for k in range(2):
+                rr, rd, rc, rrew = want.pop((it - 2, k))
+                assert np.array_equal(res[k].r.numpy(), rr) and np.array_equal(res[k].done.numpy(), rd), (it, k)
+                assert np.array_equal(res[k].cat.numpy(), rc) and np.array_equal(res[k].reward.numpy(), rrew), (it, k)
+        if it == 15:
+            p2, l2 = D.random_deals(B, seed=500)
+            host.refill(1, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory())
+            pool[0][1], pool[1][1] = p2, l2
+        for k in range(2):
+            ent = rng.integers(0, 1 << 31, B).astype(np.int32)
+            host.entropy_in[s][k].numpy()[:] = ent
+            ref.observe(want_f32=False, want_face=False)
+            want[(it, k)] = [w.copy() for w in ref.step(ent, mode=1)]
+            ref.deal(pool[0].reshape(-1, 54), pool[1].reshape(-1), only_done=True, pool_games=P)
+        host.submit(s)
+    torch.cuda.synchronize()
+    _compare_state(env, ref, 80)
+    assert int(env.stats[7].item()) == 0 and int(env.stats[4].item()) == ref.stats[4]
