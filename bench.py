@@ -189,7 +189,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local)       # samples from here to the end of the e2e region: the same kernel runs throughout
-    sampler.start()
+    if rank == 0:
+        sampler.start()
 
     # ---------------- the rank's envs as NG stream-parallel groups (one group's load-only prologue and tail
     # overlap the other group's store phase); device-resident deal pool, Philox moves on the device
@@ -308,7 +309,7 @@ def run_ours(args):
     e2e_steps = int((ge.stats - stats_e0)[4].item())
     assert e2e_steps == B * e2e_K and sink[0] > -(1 << 40)
     h2d = 4 * B + (55 * B * ((e2e_K + REFILL - 1) // REFILL)) // e2e_K
-    d2h = NG * hosts[0].results_h[0].nbytes
+    d2h = NG * hosts[0].d2h_bytes
     if int(ge.stats[7].item()):
         raise SystemExit("env reported errors during the e2e region")
 
@@ -346,7 +347,7 @@ def run_ours(args):
             "e2e": {"value": B * e2e_K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_K, "steps": e2e_K,
                     "api": "HostRollout.step(entropy_host) per env group (native ddz_pipe_step: H2D entropy -> k_env -> D2H "
-                           "r/done/cat/reward on copy streams), results of step t-2 read by the host every step, "
+                           "r/done/cat -- the reference step's return tuple -- on copy streams), results of step t-2 read by the host every step, "
                            "refill(slot, perm_host, lord_host) uploads host-made deals every %d steps" % REFILL},
             "gpu_launches": K * NG,
             "clocks": clocks,

@@ -705,7 +705,7 @@ int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
                   int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
                   float* face, int64_t* stats, int B, void* stream) {
     if (!p || !host_choice || !dev_choice || !results_dev || !results_host || B <= 0) return DDZ_E_ARG;
-    if (results_bytes < (size_t)B * 15) return DDZ_E_ARG;
+    if (results_bytes < (size_t)B * 3) return DDZ_E_ARG;       // at least r | done | cat; the reward block is optional
     cudaStream_t main_s = (cudaStream_t)stream;
     const int k = (int)(p->step & 1);
     const bool primed = p->step >= 2;                          // events of this parity were recorded two steps ago

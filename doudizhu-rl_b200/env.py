@@ -554,19 +554,24 @@ class HostRollout:
     the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t, and a step costs one native call.
     """
 
-    def __init__(self, env, perm, lord_pile, pool_games):
+    def __init__(self, env, perm, lord_pile, pool_games, fetch_reward=False):
+        """fetch_reward: also read the float32 [B,3] reward block back every step (12 of the 15 result bytes per env).
+        The reference's step returns only (r, done, cat) and derives rewards on the host (game.py:109-118), so by
+        default only r | done | cat travel over PCIe; the rewards stay available on the device (env.reward)."""
         self.env, self.G = env, int(pool_games)
         dev, B = env.device, env.B
         self.perm_d = env._to_dev(perm, torch.int8).reshape(self.G, B, 54).contiguous()
         self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.G, B).contiguous()
         self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
         self.results_h = [StepResults(B, "cpu", pin=True) for _ in range(2)]
+        self.d2h_bytes = self.results_h[0].nbytes if fetch_reward else _align(3 * B, 16)
         self._stage = None
         with torch.cuda.device(dev):
             self._pipe = N.lib.ddz_pipe_create()
         if not self._pipe:
             raise N.DdzError("ddz_pipe_create failed: %s" % N.lib.ddz_last_error().decode())
         self.i = 0
+        self._argv = None
         env._ensure()
 
     def __del__(self):
@@ -589,23 +594,47 @@ class HostRollout:
                                           perm.data_ptr(), lord_pile.data_ptr(), self._stage[0].data_ptr(),
                                           self._stage[1].data_ptr(), B, env._stream()), "ddz_pipe_refill")
 
+    def _build_args(self):
+        """Everything ddz_pipe_step needs is constant per (list parity, step parity): marshal it once."""
+        import ctypes as C
+        env = self.env
+        vp = lambda t: C.c_void_p(None if t is None else t.data_ptr())
+        self._argv = {}
+        for cur in (0, 1):
+            nxt = 1 - cur
+            for k in (0, 1):
+                self._argv[(cur, k)] = [
+                    C.c_void_p(self._pipe), vp(env._state), vp(env._ws), C.c_int(env.VARIANT),
+                    vp(env._offsets[cur]), vp(env._actions_u64[cur]),
+                    None, vp(self.entropy_d[k]), C.c_uint64(env.seed), C.c_uint64(env.env0), None,
+                    vp(env._rewards), vp(self.perm_d), vp(self.lord_d), C.c_int(self.G),
+                    vp(env._results[nxt].buf), vp(self.results_h[k].buf), C.c_size_t(self.d2h_bytes),
+                    vp(env._offsets[nxt]), vp(env._actions_u64[nxt]), vp(env._actions_f32), C.c_int64(env.cap),
+                    vp(env._face), vp(env.stats), C.c_int(env.B), None]
+        self._same_device = torch.cuda.current_device() == (env.device.index or 0)
+
     def step(self, entropy_h):
         """entropy_h: pinned int32 [B].  Returns the StepResults (pinned host views) this step will fill; they are
         valid after `wait(results)` (or any later synchronisation)."""
         env, k = self.env, self.i & 1
-        nxt = 1 - env._cur
-        res_d, res_h = env._results[nxt], self.results_h[k]
-        with torch.cuda.device(env.device):
-            N.check(N.lib.ddz_pipe_step(
-                self._pipe, env._p(env._state), env._p(env._ws), env.VARIANT,
-                env._p(env._offsets[env._cur]), env._p(env._actions_u64[env._cur]),
-                entropy_h.data_ptr(), self.entropy_d[k].data_ptr(), env.seed, env.env0, env._stepno,
-                env._rewards.data_ptr(), self.perm_d.data_ptr(), self.lord_d.data_ptr(), self.G,
-                res_d.buf.data_ptr(), res_h.buf.data_ptr(), res_d.nbytes,
-                env._p(env._offsets[nxt]), env._p(env._actions_u64[nxt]), env._p(env._actions_f32), env.cap,
-                env._p(env._face), env._p(env.stats), env.B, env._stream()), "ddz_pipe_step")
+        if self._argv is None:
+            self._build_args()
+        cur = env._cur
+        argv = self._argv[(cur, k)]
+        argv[6] = entropy_h.data_ptr()
+        argv[10] = env._stepno
+        argv[25] = torch.cuda.current_stream(env.device).cuda_stream
+        if self._same_device:
+            rc = N.lib.ddz_pipe_step(*argv)
+        else:
+            with torch.cuda.device(env.device):
+                rc = N.lib.ddz_pipe_step(*argv)
+        if rc:
+            N.check(rc, "ddz_pipe_step")
+        nxt = 1 - cur
         env._cur, env._res, env._fresh, env._n_total = nxt, nxt, True, None
         env._stepno += 1
+        res_h = self.results_h[k]
         res_h._slot, res_h._pipe = k, self._pipe
         self.i += 1
         return res_h

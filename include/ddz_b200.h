@@ -125,7 +125,8 @@ int ddz_select_actions(const float* q, const int32_t* offsets, float epsilon, ui
 /* ---- host-buffer pipeline (the e2e path): one call per env-step does, without any Python in between,
  *   copy stream : H2D  host_choice (pinned, B x 4 bytes)  ->  dev_choice[k]            (k = step parity)
  *   main stream : wait; ddz_rollout_step(choice = dev_choice[k], DDZ_CHOICE_MOD, results -> results_dev)
- *   copy stream : wait; D2H  results_dev (results_bytes, contiguous r|done|cat|reward)  ->  results_host (pinned)
+ *   copy stream : wait; D2H  results_dev (first results_bytes of the contiguous r|done|cat|pad|reward block;
+ *                       >= 3B, i.e. the reward floats are optional)  ->  results_host (pinned)
  * so the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t.  The pipe object only owns two CUDA
  * streams and a few events; every buffer stays caller-owned.  results_dev must alternate between two buffers (the
  * caller's ping-pong sets); ddz_pipe_wait(slot) blocks the host until the D2H issued by the step with that parity

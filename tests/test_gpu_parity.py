@@ -317,7 +317,7 @@ def test_host_rollout_pipeline_matches_oracle(D, oracle):
     env.prepare(perm, lord, pool_games=G)
     ref = oracle.RefBatch(B, 2)
     ref.deal(perm, lord, pool_games=G)
-    host = D.HostRollout(env, perm, lord, G)
+    host = D.HostRollout(env, perm, lord, G, fetch_reward=True)
     ents = [torch.as_tensor(rng.integers(0, 1 << 31, B).astype(np.int32)).pin_memory() for _ in range(6)]
     pending = []
     for t in range(120):
