@@ -158,8 +158,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "lord-vs-random rollout, EnvCooperation C=9, %d envs per GPU" % args.envs,
-                       "sample_envs": envs, "mean_legal_moves": nbar, "prefill_steps": warm_prefill},
+            "config": {"workload": "BASELINE config 4 per-GPU slice: %d envs/GPU, lord-vs-random rollout (all seats uniform "
+                                   "random legal move, Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode"
+                                   % args.envs,
+                       "envs_per_gpu": args.envs, "face_channels": CHANNELS, "sample_envs": envs, "mean_legal_moves": nbar,
+                       "prefill_steps": warm_prefill, "pool_games": POOL_GAMES,
+                       "note": "CPU arm: the reference's natives are absent, so this is the C oracle port of the same "
+                               "env-step (legal moves + face + action one-hots + step + re-deal) on all host threads, "
+                               "over a bounded sample of the workload"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
