@@ -560,3 +560,83 @@ def test_graphed_host_rollout_matches_oracle(D, oracle):
     torch.cuda.synchronize()
     _compare_state(env, ref, 80)
     assert int(env.stats[7].item()) == 0 and int(env.stats[4].item()) == ref.stats[4]
+
+
+# ------------------------------------------------------------------ ragged / tiny / multi-wave batches
+@pytest.mark.parametrize("B", [1, 31, 33, 100, 1000])
+def test_ragged_batch_sizes(D, oracle, B):
+    """B not a multiple of the 32-env warp tile (and smaller than one tile): partial warps, partial CTAs."""
+    P = 2
+    perm, lord = D.random_deals(B, seed=60 + B, pool_games=P)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = D.BatchedEnvComplicated(B, seed=B)
+    env.prepare(pd, ld, pool_games=P)
+    ref = oracle.RefBatch(B, 1)
+    ref.deal(perm, lord, pool_games=P)
+    for t in range(70):
+        _compare_observation(env, ref, t)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=P)
+        ref.step(mode=2, seed=B, env0=0, step=t)
+        ref.deal(perm, lord, only_done=True, pool_games=P)
+    _compare_state(env, ref, 70)
+    assert int(env.stats[7].item()) == 0
+
+
+def test_multi_wave_batch_uses_ticket_tiles(D, oracle):
+    """300 000 envs = 2344 CTAs, more than fit on the device at once: tiles come from the atomic ticket (start order)
+    instead of the launch position, and the look-back chain spans several waves.  Oracle check on a sample + CSR
+    invariants over the whole batch."""
+    B, P, seed = 300_000, 2, 8
+    perm, lord = D.random_deals(B, seed=2, pool_games=P)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = D.BatchedEnv(B, seed=seed, max_actions_per_env=128)
+    env.prepare(pd, ld, pool_games=P)
+    sample = np.sort(np.random.default_rng(1).choice(B, 600, replace=False))
+    sample[-1] = B - 1
+    sample[0] = 0
+    ref = oracle.RefBatch(len(sample), 0)
+    sp = perm.reshape(P, B, 54)[:, sample].reshape(-1, 54)
+    sl = lord.reshape(P, B)[:, sample].reshape(-1)
+    ref.deal(sp, sl, pool_games=P)
+    st = torch.as_tensor(sample).cuda()
+    for t in range(40):
+        o_off, o_au, _, o_face = ref.observe(want_f32=False)
+        off = env.offsets.to(torch.int64)
+        cnt = off[1:] - off[:-1]
+        assert int(off[0]) == 0 and (cnt >= 0).all() and env.num_actions == int(off[B])
+        assert np.array_equal(cnt[st].cpu().numpy(), np.diff(o_off))
+        lists = env.actions_packed
+        idx = torch.cat([torch.arange(int(off[b]), int(off[b + 1]), device="cuda") for b in sample[:50]])
+        want = np.concatenate([o_au[o_off[i]:o_off[i + 1]] for i in range(50)])
+        assert np.array_equal(lists[idx].cpu().numpy().view(np.uint64), want)
+        assert np.array_equal(env.face[st].cpu().numpy(), o_face)
+        if t % 10 == 0:                                    # every one-hot row is the thermometer of its packed move
+            rows = env.valid_actions()[0]
+            pick = torch.randint(0, rows.shape[0], (20000,), device="cuda")
+            mv = D.unpack_counts(lists[pick])
+            thermo = (torch.arange(4, device="cuda")[None, None, :] < mv[:, :, None]).to(torch.float32)
+            assert torch.equal(rows[pick], thermo)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=P)
+        ent = np.array([oracle.philox(seed, int(b), t) for b in sample], dtype=np.uint32)
+        ref.step(ent.view(np.int32), mode=1)
+        ref.deal(sp, sl, only_done=True, pool_games=P)
+    assert int(env.stats[7].item()) == 0
+    assert int(env.stats[4].item()) == 40 * B
+
+
+def test_all_envs_finished_and_empty_lists(D):
+    """An env that is finished and not re-dealt has no legal move, ignores steps, and still encodes a face."""
+    B = 64
+    perm, lord = D.random_deals(B, seed=4)
+    env = D.BatchedEnvCooperation(B, debug=True)
+    env.prepare(perm, lord)
+    for _ in range(400):                                   # no re-deal: every game runs to its end and stays there
+        env.rollout_step()
+    assert env.is_done.all()
+    assert env.num_actions == 0 and int(env.offsets[B]) == 0
+    before = env._state.clone()
+    r, done, cat = env.rollout_step()
+    assert torch.equal(env._state, before) and (cat == -1).all() and (r == 0).all() and done.all()
+    assert torch.isfinite(env.face).all() and env.face.shape == (B, 9, 15, 4)
+    st = env.stats.cpu().numpy()
+    assert st[0] == B and st[1] + st[2] + st[3] == B and st[7] == 0
