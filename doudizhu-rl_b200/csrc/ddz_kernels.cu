@@ -213,12 +213,12 @@ struct OutArgs {
 
 
 struct SeqWindowEmitter {  // enumerate_legal functor: keeps the moves that fall into the warp's current window
-    uint64_t* out; int pos;   // pos = index of the next move relative to the window start (may be negative)
-    DDZ_DEV void operator()(uint64_t mv) { if ((unsigned)pos < (unsigned)kWin) out[pos] = mv; pos++; }
+    uint64_t* out; int pos, win;   // pos = index of the next move relative to the window start (may be negative)
+    DDZ_DEV void operator()(uint64_t mv) { if ((unsigned)pos < (unsigned)win) out[pos] = mv; pos++; }
 };
 struct WindowEmitter {   // enumerate_legal_warp functor: move number idx of the env goes to window slot base + idx
-    uint64_t* out; int base;
-    DDZ_DEV void operator()(int idx, uint64_t mv) { const unsigned rel = (unsigned)(base + idx); if (rel < (unsigned)kWin) out[rel] = mv; }
+    uint64_t* out; int base, win;
+    DDZ_DEV void operator()(int idx, uint64_t mv) { const unsigned rel = (unsigned)(base + idx); if (rel < (unsigned)win) out[rel] = mv; }
 };
 
 struct __align__(128) WarpSmem {
@@ -380,11 +380,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         // global base -- whatever wait it has is hidden behind the enumeration; then packed list + one-hot rows out
         long long base = 0, lim = 0;
         int w0 = 0;
+        // without a face the face-row buffer is free: the window grows from kWin to kWin + 576 moves (fewer passes over
+        // long lists in ddz_legal_moves)
+        uint64_t* const wbuf = (V < 0) ? reinterpret_cast<uint64_t*>(sm.face) : sm.moves;
+        const int win = (V < 0) ? (int)(sizeof(sm.face) / 8) + kWin : kWin;
 #pragma unroll 1
         do {
-            const bool inwin = n > 0 && local < w0 + kWin && local + n > w0;
+            const bool inwin = n > 0 && local < w0 + win && local + n > w0;
             if (inwin && n <= kHeavy) {                     // short lists: one env per lane
-                SeqWindowEmitter em{sm.moves, local - w0};
+                SeqWindowEmitter em{wbuf, local - w0, win};
                 enumerate_legal(hm, ru, last != 0, em);
                 disagree |= (em.pos != local - w0 + n);
             }
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 const int rpack = __shfl_sync(FULL, (int)ru.lead | (ru.cat << 1) | (ru.len << 8) | (ru.val << 16) | ((last != 0) << 24), src);
                 sr.lead = rpack & 1; sr.cat = (rpack >> 1) & 127; sr.len = (rpack >> 8) & 255; sr.val = (rpack >> 16) & 255;
                 const int loc = __shfl_sync(FULL, local, src), nn = __shfl_sync(FULL, n, src);
-                WindowEmitter em{sm.moves, loc - w0};
+                WindowEmitter em{wbuf, loc - w0, win};
                 disagree |= (enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em) != nn);
             }
             __syncwarp();
@@ -450,11 +454,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 trace(t, 5);
             }
 
-            const int keep = (int)max(0ll, min((long long)min(kWin, total - w0), lim - w0));
-            for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = sm.moves[i];   // coalesced
-            if (o.actions_f32) write_rows<uint64_t>(o.actions_f32 + (size_t)(base + w0) * 15, keep, rl, sm.lut, sm.moves);
+            const int keep = (int)max(0ll, min((long long)min(win, total - w0), lim - w0));
+            for (int i = lane; i < keep; i += 32) o.actions_u64[base + w0 + i] = wbuf[i];   // coalesced
+            if (o.actions_f32) write_rows<uint64_t>(o.actions_f32 + (size_t)(base + w0) * 15, keep, rl, sm.lut, wbuf);
             __syncwarp();  // the moves of this window are consumed before the next window overwrites them
-            w0 += kWin;
+            w0 += win;
         } while (w0 < total);
         trace(t, 6);
     }

@@ -645,87 +645,6 @@ class HostRollout:
         return results
 
 
-class GraphedHostRollout:
-    """HostRollout with the per-step host work captured in CUDA graphs.
-
-    One graph = two env-steps of one env (group): [H2D entropy -> k_env -> D2H results] twice, reading / writing FIXED
-    pinned host buffers.  There are `nsets` such graphs with their own pinned buffers, so the host fills set s+1 and
-    reads the results of set s-1 while set s is in flight.  Per pair of steps the host does: write 2 entropy arrays,
-    `submit(s)`, later `wait(s)` and read 2 result sets -- no per-step Python/launch overhead.  Deck permutations come
-    from the host through `refill` exactly as in HostRollout.
-    """
-
-    def __init__(self, env, perm, lord_pile, pool_games, stream=None, nsets=2):
-        self.env, self.P, self.nsets = env, int(pool_games), int(nsets)
-        dev, B = env.device, env.B
-        self.stream = stream if stream is not None else torch.cuda.Stream(dev)
-        self.perm_d = env._to_dev(perm, torch.int8).reshape(self.P, B, 54).contiguous()
-        self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.P, B).contiguous()
-        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.entropy_in = [[torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)] for _ in range(self.nsets)]
-        self.results_out = [[StepResults(B, "cpu", pin=True) for _ in range(2)] for _ in range(self.nsets)]
-        self.done_ev = [torch.cuda.Event() for _ in range(self.nsets)]
-        self._stage = None
-        self.h2d = torch.cuda.Stream(dev)
-        env._ensure()
-        torch.cuda.synchronize(dev)
-        self.graphs = []
-        stepno = env._stepno
-        self.side = torch.cuda.Stream(dev)
-        for s in range(self.nsets):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
-                for k in range(2):
-                    self.entropy_d[k].copy_(self.entropy_in[s][k], non_blocking=True)
-                    env.rollout_step(choice=self.entropy_d[k], mode=N.CHOICE_MOD, perm=self.perm_d, lord_pile=self.lord_d,
-                                     pool_games=self.P, auto_step=True)
-                    # the D2H of this step's results runs on a forked branch, next to the following step's kernel
-                    fork = torch.cuda.Event()
-                    fork.record(self.stream)
-                    self.side.wait_event(fork)
-                    with torch.cuda.stream(self.side):
-                        self.results_out[s][k].buf.copy_(env._results[env._res].buf, non_blocking=True)
-                joined = torch.cuda.Event()
-                joined.record(self.side)
-                self.stream.wait_event(joined)
-            self.graphs.append(g)
-        env._stepno = stepno
-        torch.cuda.synchronize(dev)
-        for e in self.done_ev:
-            e.record(self.stream)
-
-    def refill(self, slot, perm, lord_pile):
-        """upload one slot of the deal pool (pinned host arrays) through a staging buffer; the slot is replaced by a
-        device-to-device copy on this rollout's stream, i.e. between two graph replays"""
-        B, dev = self.env.B, self.env.device
-        if self._stage is None:
-            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=dev), torch.empty(B, dtype=torch.int8, device=dev))
-            self._stage_free, self._stage_full = torch.cuda.Event(), torch.cuda.Event()
-            self._stage_free.record(self.stream)
-        with torch.cuda.stream(self.h2d):
-            self.h2d.wait_event(self._stage_free)
-            self._stage[0].copy_(torch.as_tensor(perm).reshape(B, 54), non_blocking=True)
-            self._stage[1].copy_(torch.as_tensor(lord_pile).reshape(B), non_blocking=True)
-            self._stage_full.record(self.h2d)
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(self._stage_full)
-            self.perm_d[slot].copy_(self._stage[0], non_blocking=True)
-            self.lord_d[slot].copy_(self._stage[1], non_blocking=True)
-            self._stage_free.record(self.stream)
-
-    def submit(self, s):
-        """two env-steps from entropy_in[s][0..1]; results land in results_out[s][0..1] (valid after wait(s))"""
-        with torch.cuda.stream(self.stream):
-            self.graphs[s].replay()
-            self.done_ev[s].record(self.stream)
-        self.env._stepno += 2
-        self.env._n_total = None
-
-    def wait(self, s):
-        self.done_ev[s].synchronize()
-        return self.results_out[s]
-
-
 class BatchedEnvComplicated(BatchedEnv):
     """envi.py:160-178, C=7"""
     VARIANT = N.FACE_COMPLICATED

@@ -526,42 +526,6 @@ def test_grouped_env_trajectories_do_not_depend_on_grouping(D, oracle):
         assert torch.equal(ge.stats[keep], single.stats[keep]) and int(ge.stats[7]) == 0
 
 
-def test_graphed_host_rollout_matches_oracle(D, oracle):
-    """GraphedHostRollout: [H2D entropy -> step -> D2H results] x 2 captured per graph, two buffer sets in flight."""
-    B, P = 1024, 2
-    rng = np.random.default_rng(77)
-    perm, lord = D.random_deals(B, seed=14, pool_games=P)
-    pool = [np.array(perm.reshape(P, B, 54)), np.array(lord.reshape(P, B))]
-    env = D.BatchedEnvCooperation(B)
-    env.prepare(perm, lord, pool_games=P)
-    ref = oracle.RefBatch(B, 2)
-    ref.deal(perm, lord, pool_games=P)
-    host = D.GraphedHostRollout(env, perm, lord, P)
-    want = {}
-    for it in range(40):
-        s = it % 2
-        if it >= 2:                                   # results of the submission two pairs ago
-            res = host.wait(s)
-            for k in range(2):
-                rr, rd, rc, rrew = want.pop((it - 2, k))
-                assert np.array_equal(res[k].r.numpy(), rr) and np.array_equal(res[k].done.numpy(), rd), (it, k)
-                assert np.array_equal(res[k].cat.numpy(), rc) and np.array_equal(res[k].reward.numpy(), rrew), (it, k)
-        if it == 15:
-            p2, l2 = D.random_deals(B, seed=500)
-            host.refill(1, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory())
-            pool[0][1], pool[1][1] = p2, l2
-        for k in range(2):
-            ent = rng.integers(0, 1 << 31, B).astype(np.int32)
-            host.entropy_in[s][k].numpy()[:] = ent
-            ref.observe(want_f32=False, want_face=False)
-            want[(it, k)] = [w.copy() for w in ref.step(ent, mode=1)]
-            ref.deal(pool[0].reshape(-1, 54), pool[1].reshape(-1), only_done=True, pool_games=P)
-        host.submit(s)
-    torch.cuda.synchronize()
-    _compare_state(env, ref, 80)
-    assert int(env.stats[7].item()) == 0 and int(env.stats[4].item()) == ref.stats[4]
-
-
 # ------------------------------------------------------------------ ragged / tiny / multi-wave batches
 @pytest.mark.parametrize("B", [1, 31, 33, 100, 1000])
 def test_ragged_batch_sizes(D, oracle, B):
