@@ -1,0 +1,82 @@
+"""Payload -> device state ingest.
+
+The reference's web bot rebuilds `face` / `valid_actions` from a JSON payload instead of a live env
+(server/core.py:26-67, wire format server/client.py:6-24):
+
+    {'role_id': 0|1|2,                      # 0 = up, 1 = lord, 2 = down: the player to move
+     'cur_cards': [card values 3..17],      # its hand
+     'history':    {0: [...], 1: [...], 2: [...]},   # everything each role has played
+     'last_taken': {0: [...], 1: [...], 2: [...]},   # each role's most recent hand-out ([] = pass)
+     'left':       {0: n0, 1: n1, 2: n2}}            # cards left per role
+
+`env_from_payloads` packs a batch of such payloads into the state of a BatchedEnv*, after which `env.face` and
+`env.valid_actions()` are produced by the same kernels as for a live game.  The other two players' hands are unknown:
+only their SIZES enter the features (get_state_prob_manual, server/core.py:27), so they are filled with placeholder
+cards of the right count.
+"""
+import numpy as np
+import torch
+
+from .env import BatchedEnvCooperationSimplify, pack_counts
+
+
+def _counts(cards):
+    c = np.zeros(15, np.int64)
+    for v in cards:
+        c[int(v) - 3] += 1
+    return c
+
+
+def _placeholder(n):
+    """any hand with n cards (n <= 54): only its size is ever used"""
+    c = np.zeros(15, np.int64)
+    for r in range(15):
+        take = min(4 if r < 13 else 1, n)
+        c[r] = take
+        n -= take
+    if n:
+        raise ValueError("a player cannot hold that many cards")
+    return c
+
+
+def payload_arrays(payloads):
+    """list of payload dicts -> (role [B], hand [B,15], history [B,3,15], last_taken [B,3,15], left [B,3]) int64"""
+    B = len(payloads)
+    role = np.zeros(B, np.int64)
+    hand = np.zeros((B, 15), np.int64)
+    hist = np.zeros((B, 3, 15), np.int64)
+    last = np.zeros((B, 3, 15), np.int64)
+    left = np.zeros((B, 3), np.int64)
+    for b, p in enumerate(payloads):
+        role[b] = int(p["role_id"])
+        hand[b] = _counts(p["cur_cards"])
+        for q in range(3):
+            hist[b, q] = _counts(p["history"][q] if q in p["history"] else p["history"][str(q)])
+            last[b, q] = _counts(p["last_taken"][q] if q in p["last_taken"] else p["last_taken"][str(q)])
+            left[b, q] = int(p["left"][q] if q in p["left"] else p["left"][str(q)])
+    return role, hand, hist, last, left
+
+
+def env_from_arrays(role, hand, hist, last, left, env_cls=BatchedEnvCooperationSimplify, **kw):
+    role, hand, hist, last, left = (np.asarray(x, np.int64) for x in (role, hand, hist, last, left))
+    B = len(role)
+    if ((role < 0) | (role > 2)).any() or (hand < 0).any() or (hand > 4).any() or (hist.sum(1) > 4).any():
+        raise ValueError("bad payload: role_id must be 0..2 and no rank can appear more than four times")
+    env = env_cls(B, **kw)
+    hands = np.zeros((B, 3, 15), np.int64)
+    for b in range(B):
+        for q in range(3):
+            hands[b, q] = hand[b] if q == role[b] else _placeholder(int(left[b, q]))
+    dev = env.device
+    f, meta = env._fields()
+    f[0:3] = pack_counts(torch.as_tensor(hands).to(dev)).t()
+    f[3:6] = pack_counts(torch.as_tensor(hist).to(dev)).t()
+    f[6:9] = pack_counts(torch.as_tensor(last).to(dev)).t()
+    meta.copy_(torch.as_tensor(role, dtype=torch.int32).to(dev))      # role to move, not done, no deals consumed
+    env._fresh = False
+    return env
+
+
+def env_from_payloads(payloads, env_cls=BatchedEnvCooperationSimplify, **kw):
+    """BatchedEnv* whose env b is the position described by payloads[b] (server/core.py Predictor.face / valid_actions)"""
+    return env_from_arrays(*payload_arrays(payloads), env_cls=env_cls, **kw)

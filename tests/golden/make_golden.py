@@ -14,6 +14,8 @@ What is pinned, and by which reference code:
   envi_trace.npz   the UNMODIFIED envi.py (all four Env classes, envi.py:16-217) run on top of the oracle's
                    stand-ins for the absent natives (oracle/pyshim), random play from a fixed index stream
   converters.npz   envi.py:118-157 arr2cards / cards2arr / batch_arr2onehot / onehot2arr samples
+  core_payloads.npz  server/core.py:26-67 Predictor.face / Predictor.valid_actions (unmodified, over oracle/pyshim) on the
+                   example payloads of server/client.py and on payloads cut from random games
 
 Nothing of the reference is copied into the repo: only input/output vectors are stored.
 """
@@ -202,6 +204,59 @@ save("envi_trace.npz", perms=np.array(perms), seed=np.int64(SEED),
      face_cooperation=np.array(faces[2]), face_simplify=np.array(faces[3]),
      history=np.array(hist_rows, np.int8), recent=np.array(recent_rows, np.int8),
      **{k: np.array(v) for k, v in rec.items()})
+
+# ------------------------------------------------------------------ server/core.py payload path
+import ast  # noqa: E402
+import server.core as core  # noqa: E402
+
+pred = core.Predictor.__new__(core.Predictor)      # __init__ would load absent checkpoints; face/valid_actions need only this
+pred.mock_env = envi.Env(seed=0)
+payloads = []
+tree = ast.parse(open(os.path.join(REF, "server", "client.py"), encoding="utf-8").read())
+for node in tree.body:
+    if isinstance(node, ast.Assign) and isinstance(node.value, ast.Dict) and node.targets[0].id.startswith("payload"):
+        payloads.append(ast.literal_eval(node.value))
+n_client = len(payloads)
+# positions cut from random games played on the oracle-backed envi.Env
+shim_env.reset_deal_stream(1000)
+e = envi.EnvCooperationSimplify()
+prng = np.random.default_rng(99)
+for g in range(30):
+    e.reset(); e.prepare()
+    done, hist_cards, last_cards = False, {0: [], 1: [], 2: []}, {0: [], 1: [], 2: []}
+    while not done:
+        role = e.get_role_ID() - 1
+        if prng.random() < 0.35:
+            payloads.append({"role_id": role, "cur_cards": [int(c) for c in e.get_curr_handcards()],
+                             "history": {q: list(hist_cards[q]) for q in range(3)},
+                             "last_taken": {q: list(last_cards[q]) for q in range(3)},
+                             "left": {q: int(e.left[q]) for q in range(3)}})
+        acts = e.valid_actions(tensor=False)
+        a = acts[prng.integers(len(acts))]
+        cards = [int(c) for c in envi.Env.arr2cards(a)]
+        hist_cards[role] += cards
+        last_cards[role] = cards
+        _, done, _ = e.step_manual(envi.Env.batch_arr2onehot([a])[0])
+faces, acts_rows, acts_off = [], [], [0]
+for p in payloads:
+    faces.append(pred.face(**p).numpy())
+    _, at = pred.valid_actions(**p)
+    acts_rows.append(at.numpy())
+    acts_off.append(acts_off[-1] + at.shape[0])
+sys.path.insert(0, os.path.join(ROOT))
+def _cnt(cards):
+    c = np.zeros(15, np.int8)
+    for v in cards:
+        c[int(v) - 3] += 1
+    return c
+save("core_payloads.npz", n_client=np.int64(n_client),
+     role=np.array([p["role_id"] for p in payloads], np.int8),
+     hand=np.array([_cnt(p["cur_cards"]) for p in payloads]),
+     history=np.array([[_cnt(p["history"][q]) for q in range(3)] for p in payloads]),
+     last_taken=np.array([[_cnt(p["last_taken"][q]) for q in range(3)] for p in payloads]),
+     left=np.array([[p["left"][q] for q in range(3)] for p in payloads], np.int8),
+     face=np.array(faces, np.float32), actions=np.concatenate(acts_rows).astype(np.float32),
+     actions_off=np.array(acts_off, np.int64))
 
 # ------------------------------------------------------------------ converters
 arrs = np.array([rand_hand(int(rng.integers(0, 21))) for _ in range(64)], np.int8)

@@ -604,3 +604,44 @@ def test_all_envs_finished_and_empty_lists(D):
     assert torch.isfinite(env.face).all() and env.face.shape == (B, 9, 15, 4)
     st = env.stats.cpu().numpy()
     assert st[0] == B and st[1] + st[2] + st[3] == B and st[7] == 0
+
+
+def test_payload_ingest_matches_reference_predictor(D, golden):
+    """payloads in the wire format of server/client.py -> device state -> face / valid_actions equal to
+    what the reference's own Predictor.face / Predictor.valid_actions (server/core.py:26-67) computed for them."""
+    g = golden.core_payloads
+    env = D.env_from_arrays(g["role"], g["hand"], g["history"], g["last_taken"], g["left"], debug=True)
+    assert np.array_equal(env.face.cpu().numpy(), g["face"])
+    acts, offs = env.valid_actions()
+    assert np.array_equal(offs.cpu().numpy().astype(np.int64), g["actions_off"])
+    assert np.array_equal(acts.cpu().numpy(), g["actions"])
+    # and through the dict form of the wire format
+    def cards(c):
+        return [r + 3 for r in range(15) for _ in range(int(c[r]))]
+    payloads = [{"role_id": int(g["role"][b]), "cur_cards": cards(g["hand"][b]),
+                 "history": {q: cards(g["history"][b, q]) for q in range(3)},
+                 "last_taken": {str(q): cards(g["last_taken"][b, q]) for q in range(3)},
+                 "left": {q: int(g["left"][b, q]) for q in range(3)}} for b in range(40)]
+    env2 = D.env_from_payloads(payloads)
+    assert np.array_equal(env2.face.cpu().numpy(), g["face"][:40])
+    with pytest.raises(ValueError):
+        D.env_from_arrays([3], g["hand"][:1], g["history"][:1], g["last_taken"][:1], g["left"][:1])
+
+
+def test_config1_thousand_seeded_games_same_winners_as_oracle(D, oracle):
+    """BASELINE config 1/2 cross-check: the 1000 games of the documented default deal stream, random play from the Philox
+    stream, run to the end on the GPU env and on the oracle: same winner in every game, same number of decisions."""
+    n = 1000
+    env = D.BatchedEnv(n, seed=20260101)
+    env.prepare()                                   # no arguments: default_deals(0, n)
+    perm, lord = D.default_deals(0, n)
+    ref = oracle.RefBatch(n, 0)
+    ref.deal(perm, lord)
+    for t in range(200):
+        env.rollout_step()
+        ref.observe(want_f32=False, want_face=False)
+        ref.step(mode=2, seed=20260101, env0=0, step=t)
+    assert env.is_done.all() and ref.envs["done"].all()
+    assert np.array_equal(env.winner.cpu().numpy(), ref.envs["winner"])
+    st = env.stats.cpu().numpy()
+    assert np.array_equal(st[[0, 1, 2, 3, 4, 9]], ref.stats[[0, 1, 2, 3, 4, 9]]) and st[0] == n

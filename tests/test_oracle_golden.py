@@ -182,3 +182,52 @@ def test_max_legal_bound_is_proved_exhaustively(oracle):
     best, hand, visited = oracle.max_lead_moves_exhaustive(8)
     assert visited == 153009740 and best == 497 and hand.sum() == 20
     assert len(oracle.get_moves(hand, z)) == 497 <= oracle.MAX_LEGAL
+
+
+def test_core_payload_path_matches_predictor(oracle, golden):
+    """server/core.py:26-67 (Predictor.face / valid_actions on a JSON payload): the oracle, loaded with the payload's
+    position, produces the same 6-channel face and the same legal-action tensor as the reference's unmodified code."""
+    g = golden.core_payloads
+    n = len(g["role"])
+    assert int(g["n_client"]) >= 2 and n > 100
+    rb = oracle.RefBatch(n, 3)
+    rb.envs["cur"] = g["role"]
+    rb.envs["hist"] = g["history"]
+    rb.envs["recent"] = g["last_taken"]
+    hands = np.zeros((n, 3, 15), np.int8)
+    for b in range(n):
+        for q in range(3):
+            if q == g["role"][b]:
+                hands[b, q] = g["hand"][b]
+            else:                                            # unknown cards: only the SIZE enters the features
+                left, c = int(g["left"][b, q]), np.zeros(15, np.int8)
+                for r in range(15):
+                    c[r] = min(4 if r < 13 else 1, left); left -= c[r]
+                hands[b, q] = c
+    rb.envs["hand"] = hands
+    off, au, af, face = rb.observe(fast=False)
+    assert np.array_equal(face, g["face"])
+    assert np.array_equal(off.astype(np.int64), g["actions_off"])
+    assert np.array_equal(af, g["actions"])
+
+
+def test_config1_thousand_seeded_games_random_play(oracle):
+    """BASELINE config 1 on the oracle: 1000 games from the documented deal stream (PCG64(20260101+g), lord_pile 0), all
+    seats uniform random.  The dynamics must reproduce what SURVEY.md 3.3 / BASELINE.md 3 measured independently on the
+    reference's own action space: about 61.8 decisions per game, about 5.6 legal moves per decision, 51 % passes."""
+    import ddz_b200 as D
+    n = 1000
+    perm, lord = D.default_deals(0, n)
+    rb = oracle.RefBatch(n, 0)
+    rb.deal(perm, lord)
+    moves = 0
+    for t in range(200):
+        off, _, _, _ = rb.observe(want_f32=False, want_face=False)
+        moves += int(off[n])
+        rb.step(mode=2, seed=20260101, env0=0, step=t)
+        if rb.envs["done"].all():
+            break
+    st = rb.stats
+    assert st[0] == n and st[1] + st[2] + st[3] == n
+    per_game, nbar, passes = st[4] / n, moves / st[4], st[9] / st[4]
+    assert 58 < per_game < 66 and 5.0 < nbar < 6.2 and 0.47 < passes < 0.55, (per_game, nbar, passes)
