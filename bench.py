@@ -30,6 +30,7 @@ UNIT = "env-steps/s"
 VARIANT, CHANNELS = 2, 9            # EnvCooperation
 STATE_BYTES = 76                    # 9 x uint64 + uint32 per env (include/ddz_b200.h)
 POOL_GAMES = 8
+STATS_EVERY = 64                    # env-steps between two statistics all-reduces (multi-GPU runs)
 SEED = 20260101
 
 
@@ -215,14 +216,30 @@ def run_ours(args):
     # ---------------- timed region: exactly K env-steps of every env, CUDA events on the launching (current) stream
     stats0 = ge.stats.clone()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    if side is not None:                # warm the collective up on its stream
+        with torch.cuda.stream(side):
+            dist.all_reduce(ge.stats.clone())
+        side.synchronize()
     barrier()
     e0.record()
     ge._fork()
-    for _ in range(K // 2):
+    reduced = []
+    for i in range(K // 2):
         ge.replay()                     # per group: two launches of k_env<cooperation, step+observe>
+        if side is not None and (2 * i) % STATS_EVERY == 0:
+            # the path's only collective: win/return statistics, all-reduced on a side stream while the envs keep
+            # stepping (reference game.py:209-226 logs these counters every log_every episodes)
+            side.wait_stream(ge.streams[0])
+            with torch.cuda.stream(side):
+                snap = torch.stack([e.stats for e in ge.envs]).sum(0)
+                dist.all_reduce(snap)
+                reduced.append(snap)
     if K % 2:
         ge.rollout_step()
     ge.join()
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
@@ -341,6 +358,9 @@ def run_ours(args):
                             "envs_per_gpu": B, "env_groups_per_gpu": NG, "face_channels": CHANNELS, "mean_legal_moves": nbar,
                             "prefill_steps": args.prefill, "pool_games": P, "parallelism": "env-shard x%d" % world,
                             "launch": "CUDA graph replay of the 2-launch ping-pong pair, one chain per env group",
+                            "collectives": ("none (single GPU)" if world == 1 else
+                                            "stats all-reduce (int64[16], NCCL) every %d steps on a side stream, inside the timed region"
+                                            % STATS_EVERY),
                             "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
                             "games_finished": int(gstats[0].item()),
                             "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))}, **info),
