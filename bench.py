@@ -59,11 +59,14 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(envs):
-    """DRAM bytes per launch of the step kernel from the committed ncu --set full capture (same workload), or None."""
+def ncu_traffic(envs, groups):
+    """DRAM bytes per step (all launches of the step) from the committed ncu --set full captures of the same workload,
+    or None when there is no capture for this shape."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return d["traffic_bytes_per_launch"] if envs == 131072 else None
+        if envs != 131072:
+            return None
+        return {1: d["single_group"], 2: d["two_groups"]}[groups]["traffic_bytes_per_step"]
     except Exception:
         return None
 
@@ -365,11 +368,17 @@ def run_ours(args):
                             "games_finished": int(gstats[0].item()),
                             "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))}, **info),
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B) if NG == 1 else None,
+                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B, NG),
                          "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
                          "algorithmic_bytes_per_step": B * eb, "ms_per_step": step_ms, "launches_in_flight": NG,
                          "note": "achieved = algorithmic bytes of one step of all envs / wall time per step; the step is "
-                                 "%d concurrent launches of the same kernel (one per env group)" % NG},
+                                 "%d concurrent launches of the same kernel (one per env group); traffic = ncu DRAM bytes "
+                                 "of those launches (profiles/r1_traffic.json)" % NG,
+                         "single_launch": ({"ms_per_launch": info["single_group_graph_ms_per_step"],
+                                            "achieved": B * eb / (info["single_group_graph_ms_per_step"] * 1e-3) / 1e9,
+                                            "frac": B * eb / (info["single_group_graph_ms_per_step"] * 1e-3) / 1e9 / peak,
+                                            "note": "one launch over all %d envs, one chain (no env groups)" % B}
+                                           if "single_group_graph_ms_per_step" in info else None)},
             "e2e": {"value": B * e2e_K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_K, "steps": e2e_K,
                     "api": "HostRollout.step(entropy_host) per env group (native ddz_pipe_step: H2D entropy -> k_env -> D2H "
