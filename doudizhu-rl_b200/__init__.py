@@ -7,12 +7,13 @@ importlib.import_module("doudizhu-rl_b200").
 from . import _native as native  # raises ImportError when libddz_b200.so has not been built
 from . import sharding
 from .agent import BatchedGreedyPolicy
+from .trainer import ReplayBuffer, TransitionCollector, td_step
 from .ingest import env_from_payloads, env_from_arrays, payload_arrays
 from .env import (GraphedRollout, GroupedEnv, HostRollout, StepResults, BatchedEnv, BatchedEnvComplicated, BatchedEnvCooperation, BatchedEnvCooperationSimplify,
                   Env, EnvComplicated, EnvCooperation, EnvCooperationSimplify,
                   MoveGenerator, get_moves, pack_counts, unpack_counts, default_deals, random_deals,
                   VARIANT_CHANNELS, DEFAULT_REWARDS)
 
-__all__ = ["native", "sharding", "BatchedGreedyPolicy", "env_from_payloads", "env_from_arrays", "payload_arrays", "GraphedRollout", "GroupedEnv", "HostRollout", "StepResults", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
+__all__ = ["native", "sharding", "BatchedGreedyPolicy", "ReplayBuffer", "TransitionCollector", "td_step", "env_from_payloads", "env_from_arrays", "payload_arrays", "GraphedRollout", "GroupedEnv", "HostRollout", "StepResults", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
            "Env", "EnvComplicated", "EnvCooperation", "EnvCooperationSimplify", "MoveGenerator", "get_moves", "pack_counts",
            "unpack_counts", "default_deals", "random_deals", "VARIANT_CHANNELS", "DEFAULT_REWARDS"]

@@ -14,6 +14,8 @@ What is pinned, and by which reference code:
   envi_trace.npz   the UNMODIFIED envi.py (all four Env classes, envi.py:16-217) run on top of the oracle's
                    stand-ins for the absent natives (oracle/pyshim), random play from a fixed index stream
   converters.npz   envi.py:118-157 arr2cards / cards2arr / batch_arr2onehot / onehot2arr samples
+  game_transitions.npz  the UNMODIFIED game.py Game.play (lord training, all three seats agents) with a stub DQN that records
+                   every perceive(s0, a0, r, s1, a1, done) call: pins the delayed-feedback transition assembly
   core_payloads.npz  server/core.py:26-67 Predictor.face / Predictor.valid_actions (unmodified, over oracle/pyshim) on the
                    example payloads of server/client.py and on payloads cut from random games
 
@@ -257,6 +259,70 @@ save("core_payloads.npz", n_client=np.int64(n_client),
      left=np.array([[p["left"][q] for q in range(3)] for p in payloads], np.int8),
      face=np.array(faces, np.float32), actions=np.concatenate(acts_rows).astype(np.float32),
      actions_off=np.array(acts_off, np.int64))
+
+# ------------------------------------------------------------------ game.py transition assembly
+import tempfile  # noqa: E402
+import config as ref_config  # noqa: E402
+_tmp = tempfile.mkdtemp()
+ref_config.LOG_DIR, ref_config.WIN_DIR, ref_config.MODEL_DIR = (os.path.join(_tmp, d) for d in ("logs", "win", "models"))
+import game as ref_game  # noqa: E402
+
+TSEED = 4711
+STEP = [0]          # env-steps played so far in the current game
+GAME = [0]
+RECORDS = []
+
+
+class _StubNet:
+    def load(self, *a): pass
+    def save(self, *a): pass
+
+
+class StubDQN:
+    """stands in for dqn.DQNFirst: picks legal move number philox(TSEED, game, 2*step + kind) % N, records perceive()"""
+    def __init__(self, net_cls):
+        self.policy_net, self.target_net, self.epsilon = _StubNet(), _StubNet(), 0.0
+        self.is_lord = net_cls == "lord"
+
+    def _pick(self, actions, kind):
+        return actions[O.philox(TSEED, GAME[0], 2 * STEP[0] + kind) % actions.shape[0]]
+
+    def e_greedy_action(self, face, actions):          # the lord's move (it is the only seat in training)
+        return self._pick(actions, 0)
+
+    def greedy_action(self, face, actions):            # farmers: their move; lord: the a1 of Game.feedback (game.py:125)
+        return self._pick(actions, 1 if self.is_lord else 0)
+
+    def perceive(self, s0, a0, r, s1, a1, done):
+        RECORDS.append((GAME[0], s0.numpy().copy(), a0.numpy().copy(), float(r), s1.numpy().copy(), a1.numpy().copy(), bool(done)))
+        return None
+
+    def update_epsilon(self, episode): pass
+    def update_target(self, episode): pass
+
+
+class CountingEnv(envi.EnvCooperation):
+    def step_manual(self, onehot_cards):
+        out = super().step_manual(onehot_cards)
+        STEP[0] += 1
+        return out
+
+
+NG_T = 40
+shim_env.reset_deal_stream(5000)
+gm = ref_game.Game(CountingEnv, {"lord": "lord", "down": "down", "up": "up"}, {"lord": StubDQN, "down": StubDQN, "up": StubDQN},
+                   train_dict={"lord": True, "down": False, "up": False})
+tperms = []
+for g in range(NG_T):
+    GAME[0], STEP[0] = g, 0
+    tperms.append(np.random.Generator(np.random.PCG64(SEED + 5000 + g)).permutation(54).astype(np.int8))
+    gm.play()
+save("game_transitions.npz", seed=np.int64(TSEED), perms=np.array(tperms),
+     game=np.array([r[0] for r in RECORDS], np.int32), s0=np.array([r[1] for r in RECORDS], np.float32),
+     a0=np.array([r[2] for r in RECORDS], np.float32), r=np.array([r[3] for r in RECORDS], np.float32),
+     s1=np.array([r[4] for r in RECORDS], np.float32), a1=np.array([r[5] for r in RECORDS], np.float32),
+     done=np.array([r[6] for r in RECORDS], np.uint8), lord_wins=np.int64(gm.lord_total_wins),
+     farmer_wins=np.int64(gm.up_total_wins + gm.down_total_wins))
 
 # ------------------------------------------------------------------ converters
 arrs = np.array([rand_hand(int(rng.integers(0, 21))) for _ in range(64)], np.int8)

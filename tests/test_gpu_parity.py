@@ -645,3 +645,83 @@ def test_config1_thousand_seeded_games_same_winners_as_oracle(D, oracle):
     assert np.array_equal(env.winner.cpu().numpy(), ref.envs["winner"])
     st = env.stats.cpu().numpy()
     assert np.array_equal(st[[0, 1, 2, 3, 4, 9]], ref.stats[[0, 1, 2, 3, 4, 9]]) and st[0] == n
+
+
+# ------------------------------------------------------------------ trainer driver pieces
+def test_transition_assembly_matches_reference_game_loop(D, oracle, golden):
+    """TransitionCollector vs the perceive() calls the UNMODIFIED game.py (Game.play, lord in training, all seats driven by
+    a recorded index stream) made on the same 40 deals: same (s0, a0, r, s1, a1, done), game by game, in order."""
+    g = golden.game_transitions
+    seed, perms = int(g["seed"]), g["perms"]
+    B = len(perms)
+    env = D.BatchedEnvCooperation(B, debug=True)
+    env.prepare(perms, np.zeros(B, np.int8))
+    col = D.TransitionCollector(env, role=1, reward=100.0)
+    got = [[] for _ in range(B)]
+
+    def take(out):
+        s0, a0, r, s1, a1, done, idx = (x.cpu().numpy() for x in out)
+        for i, b in enumerate(idx):
+            got[b].append((s0[i], a0[i], float(r[i]), s1[i], a1[i], bool(done[i])))
+
+    for t in range(200):
+        acts, offs = env.valid_actions()
+        off = offs.cpu().numpy().astype(np.int64)
+        cnt = np.diff(off)
+        k0 = np.array([oracle.philox(seed, b, 2 * t) % cnt[b] if cnt[b] else 0 for b in range(B)])
+        k1 = np.array([oracle.philox(seed, b, 2 * t + 1) % cnt[b] if cnt[b] else 0 for b in range(B)])
+        live = torch.as_tensor(cnt > 0).cuda()[:, None, None]
+        rows0 = acts[torch.as_tensor(np.minimum(off[:-1] + k0, max(off[-1] - 1, 0))).cuda()] * live
+        rows1 = acts[torch.as_tensor(np.minimum(off[:-1] + k1, max(off[-1] - 1, 0))).cuda()] * live
+        take(col.on_turn(rows0, rows1))
+        was_done = env.is_done.clone()
+        env.step(k0.astype(np.int32))
+        env.observe()
+        take(col.on_step_done(env.is_done & ~was_done))
+        if bool(env.is_done.all()):
+            break
+    assert bool(env.is_done.all())
+    n = 0
+    for b in range(B):
+        rows = np.flatnonzero(g["game"] == b)
+        assert len(got[b]) == len(rows), (b, len(got[b]), len(rows))
+        for j, row in enumerate(rows):
+            s0, a0, r, s1, a1, done = got[b][j]
+            assert np.array_equal(s0, g["s0"][row]) and np.array_equal(a0, g["a0"][row]), (b, j)
+            assert r == g["r"][row] and done == bool(g["done"][row]), (b, j)
+            assert np.array_equal(s1, g["s1"][row]) and np.array_equal(a1, g["a1"][row]), (b, j)
+            n += 1
+    assert n == len(g["game"]) > 300
+    st = env.stats.cpu().numpy()
+    assert st[1] == int(g["lord_wins"]) and st[2] + st[3] == int(g["farmer_wins"])
+
+
+def test_replay_buffer_and_td_step(D):
+    from qnet_like import QNetLike
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    rb = D.ReplayBuffer(100, 9, dev)
+    mk = lambda n, base: (torch.full((n, 9, 15, 4), base, device=dev), torch.full((n, 15, 4), base, device=dev),
+                          torch.full((n,), base, device=dev), torch.full((n, 9, 15, 4), base + 0.5, device=dev),
+                          torch.zeros((n, 15, 4), device=dev), torch.zeros(n, device=dev))
+    rb.append(*mk(60, 1.0))
+    assert len(rb) == 60
+    rb.append(*mk(70, 2.0))                          # wraps: the 30 oldest entries are overwritten, like deque(maxlen)
+    assert len(rb) == 100
+    assert int((rb.r == 1.0).sum()) == 30 and int((rb.r == 2.0).sum()) == 70
+    batch = rb.sample(32)
+    assert batch[0].shape == (32, 9, 15, 4) and batch[2].shape == (32, 1)
+    # td_step == the reference's arithmetic (dqn.py:39-47)
+    policy, target = QNetLike(9).to(dev), QNetLike(9).to(dev)
+    target.load_state_dict(policy.state_dict())
+    opt = torch.optim.Adam(policy.parameters(), 1e-3)
+    s0, a0, r, s1, a1, done = (torch.rand(64, 9, 15, 4, device=dev), torch.rand(64, 15, 4, device=dev).round(),
+                               torch.randn(64, 1, device=dev), torch.rand(64, 9, 15, 4, device=dev),
+                               torch.rand(64, 15, 4, device=dev).round(), (torch.rand(64, 1, device=dev) < 0.3).float())
+    with torch.no_grad():
+        want = torch.nn.MSELoss()(r + (1 - done) * 0.95 * target(s1, a1), policy(s0, a0))
+    first = D.td_step(policy, target, opt, (s0, a0, r, s1, a1, done), 0.95)
+    assert torch.allclose(first, want, rtol=1e-5)
+    for _ in range(30):
+        last = D.td_step(policy, target, opt, (s0, a0, r, s1, a1, done), 0.95)
+    assert last < first
