@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddz_b200 as D
 
-B, G = 131072, 8
+B, G = (int(sys.argv[1]) if len(sys.argv) > 1 else 131072), 8
 perm, lord = D.random_deals(B, seed=1, pool_games=G)
 pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
 env = D.BatchedEnvCooperation(B, seed=3, max_actions_per_env=160)
