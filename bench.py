@@ -302,16 +302,15 @@ def run_ours(args):
     pending = [[None, None] for _ in range(NG)]
 
     def e2e_step(i):
-        for g in range(NG):
-            with torch.cuda.stream(ge.streams[g]):
-                if i % REFILL == 0:
-                    pp, ll = pool_h[(i // REFILL) % 2]
-                    hosts[g].refill((i // REFILL) % P, pp, ll)
-                old = pending[g][i & 1]
-                if old is not None:                               # the host reads the results of step i-2
-                    D.HostRollout.wait(old)
-                    sink[0] += int(old.done[0]) + int(old.r[-1])
-                pending[g][i & 1] = hosts[g].step(ent_h[g][i % R])
+        for g in range(NG):                                       # each HostRollout issues on its group's stream
+            if i % REFILL == 0:
+                pp, ll = pool_h[(i // REFILL) % 2]
+                hosts[g].refill((i // REFILL) % P, pp, ll)
+            old = pending[g][i & 1]
+            if old is not None:                                   # the host reads the results of step i-2
+                D.HostRollout.wait(old)
+                sink[0] += int(old.done_np[0]) + int(old.r_np[-1])
+            pending[g][i & 1] = hosts[g].step(ent_h[g][i % R])
 
     for i in range(max(W, 4)):
         e2e_step(i)

@@ -70,6 +70,8 @@ class StepResults:
         self.done = self.buf[B:2 * B]
         self.cat = self.buf[2 * B:3 * B].view(torch.int8)
         self.reward = self.buf[self.off_reward:].view(torch.float32).view(B, 3)
+        if pin:   # host copies: numpy views of the same pinned memory, for cheap per-step reads
+            self.r_np, self.done_np, self.cat_np, self.reward_np = (t.numpy() for t in (self.r, self.done, self.cat, self.reward))
 
 
 class BatchedEnv:
@@ -572,6 +574,7 @@ class HostRollout:
             raise N.DdzError("ddz_pipe_create failed: %s" % N.lib.ddz_last_error().decode())
         self.i = 0
         self._argv = None
+        self._main = torch.cuda.current_stream(dev)      # every step is issued on the stream current at construction
         env._ensure()
 
     def __del__(self):
@@ -592,7 +595,7 @@ class HostRollout:
         with torch.cuda.device(env.device):
             N.check(N.lib.ddz_pipe_refill(self._pipe, self.perm_d[slot].data_ptr(), self.lord_d[slot].data_ptr(),
                                           perm.data_ptr(), lord_pile.data_ptr(), self._stage[0].data_ptr(),
-                                          self._stage[1].data_ptr(), B, env._stream()), "ddz_pipe_refill")
+                                          self._stage[1].data_ptr(), B, self._main.cuda_stream), "ddz_pipe_refill")
 
     def _build_args(self):
         """Everything ddz_pipe_step needs is constant per (list parity, step parity): marshal it once."""
@@ -610,7 +613,7 @@ class HostRollout:
                     vp(env._rewards), vp(self.perm_d), vp(self.lord_d), C.c_int(self.G),
                     vp(env._results[nxt].buf), vp(self.results_h[k].buf), C.c_size_t(self.d2h_bytes),
                     vp(env._offsets[nxt]), vp(env._actions_u64[nxt]), vp(env._actions_f32), C.c_int64(env.cap),
-                    vp(env._face), vp(env.stats), C.c_int(env.B), None]
+                    vp(env._face), vp(env.stats), C.c_int(env.B), C.c_void_p(self._main.cuda_stream)]
         self._same_device = torch.cuda.current_device() == (env.device.index or 0)
 
     def step(self, entropy_h):
@@ -623,7 +626,6 @@ class HostRollout:
         argv = self._argv[(cur, k)]
         argv[6] = entropy_h.data_ptr()
         argv[10] = env._stepno
-        argv[25] = torch.cuda.current_stream(env.device).cuda_stream
         if self._same_device:
             rc = N.lib.ddz_pipe_step(*argv)
         else:

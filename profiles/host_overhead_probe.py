@@ -25,12 +25,11 @@ for mode in ("submit_only", "with_wait_and_read"):
     for i in range(N):
         h0 = time.perf_counter()
         for g in range(NG):
-            with torch.cuda.stream(ge.streams[g]):
-                old = pending[g][i & 1]
-                if mode != "submit_only" and old is not None:
-                    D.HostRollout.wait(old)
-                    x = int(old.done[0]) + int(old.r[-1])
-                pending[g][i & 1] = hosts[g].step(ent[g][i % 4])
+            old = pending[g][i & 1]
+            if mode != "submit_only" and old is not None:
+                D.HostRollout.wait(old)
+                x = int(old.done_np[0]) + int(old.r_np[-1])
+            pending[g][i & 1] = hosts[g].step(ent[g][i % 4])
         host += time.perf_counter() - h0
     t_issue = time.perf_counter() - t0
     torch.cuda.synchronize()
