@@ -152,7 +152,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    envs = 1024 * threads
+    envs = 4096 * threads
     warm_prefill = 100
     # W warm-up steps then exactly K timed steps, each one env-step of the bounded sample of `envs` envs
     n, sec, stats = cpu_rollout(envs, warm_prefill + args.warmup, args.steps, threads)

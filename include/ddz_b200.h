@@ -65,7 +65,7 @@ extern "C" {
 int ddz_abi_version(void);
 int ddz_face_channels(int variant);          /* 4 / 7 / 9 / 6, or DDZ_E_ARG */
 size_t ddz_state_bytes(int B);
-/* Scratch for observe / rollout_step / legal_moves (n <= B): tile ticket + one look-back word per CTA.
+/* Scratch for observe / rollout_step / legal_moves (n <= B): tile ticket + one look-back word per 32-env tile.
  * The caller zero-fills it ONCE after allocation; every launch re-arms it.  One workspace per stream:
  * two launches that share a workspace must not run concurrently. */
 size_t ddz_workspace_bytes(int B);
