@@ -3,17 +3,22 @@
 // k_env<V, MODE> is the whole env-step in ONE launch.  The unit of work is a WARP: warp <-> 32 consecutive envs
 // (lane <-> env for the rule work, the whole warp for the output).  Warps never synchronise with each other; a CTA is
 // only a container of kWarpsPerCta independent warps.
-//   1. tile ticket (atomic) -> first env; load the packed state (SoA, coalesced)
+//   1. tile id = launch position when the whole grid is resident at once, else an atomic ticket in start order;
+//      coalesced SoA load of the packed state (+ previous offsets / choice, all in flight together)
 //   2. [MODE step] pick the move (index / entropy % N / Philox % N / explicit), apply it, terminal + rewards,
-//      [re-deal finished envs from the host-supplied permutation pool], store the state
+//      [re-deal finished envs from the host-supplied permutation pool, the whole warp working on one deal at a time],
+//      store the state
 //   3. count legal moves (closed form: popc x binomial), warp exclusive scan (shfl), publish the warp total for the
 //      decoupled look-back that turns per-warp totals into global CSR offsets without a second pass over the state
 //   4. face rows: the C count planes of every env go to shared memory; lanes 0..29 are (row parity, rank) pairs, so
 //      one warp instruction writes two whole 240-byte rows as 30 coalesced 128-bit streaming stores (st.global.cs),
 //      each value coming from a 5-entry thermometer LUT
-//   5. look-back (its latency is hidden behind 4) -> global base, offsets
-//   6. enumerate the legal moves in canonical order into shared memory (windows of kWin moves), write the packed
-//      list (coalesced) and the action rows (same row writer as the face)
+//   5. enumerate the legal moves in canonical order into a shared-memory window: short lists one env per lane, long
+//      lists (> kHeavy moves) by the whole warp (lane j = j-th rank / j-th chunk of kicker sets, found by unranking)
+//   6. look-back (kLookBack windows of 32 predecessor tiles per round trip; any wait is hidden behind 4 or 5)
+//      -> global base, offsets; packed list (coalesced) and the action rows (same row writer as the face)
+//   Odd tiles run 5-6 before 4, even tiles 4 before 5-6: about half of an SM's warps stream rows while the other half
+//   does rule work.
 // Stores are fire-and-forget: no staging tiles, no waits.  Nothing is re-read from HBM: algorithmic bytes == DRAM
 // traffic (profiles/).  Two earlier variants that staged rows in shared memory and pushed them with TMA bulk stores
 // (cp.async.bulk) measured slower (profiles/r1b*, r1c*): the path is nowhere near issue-bound, what it
