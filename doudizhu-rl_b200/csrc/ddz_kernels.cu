@@ -39,8 +39,23 @@ constexpr int kWarpsPerCta = kThreads / 32;
 constexpr int kEnvs = kThreads;                  // envs per CTA for the simple thread-per-env kernels
 constexpr int kWin = 320;                        // legal moves staged per window (one warp)
 constexpr int kMinCtasPerSm = 7;                 // 28 warps per SM (one wave at 131 072 envs): <= 72 registers
-constexpr int kHeavy = 32;                       // envs with more legal moves than this are expanded by the whole warp
-constexpr int kLookBack = 4;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
+#ifdef DDZ_PLAIN_STORES
+#define DDZ_STORE(p, v) (*(p) = (v))
+#else
+#define DDZ_STORE(p, v) __stcs((p), (v))
+#endif
+#ifndef DDZ_HEAVY
+#define DDZ_HEAVY 32
+#endif
+#ifndef DDZ_ROW_UNROLL
+#define DDZ_ROW_UNROLL 4
+#endif
+#ifndef DDZ_LOOKBACK
+#define DDZ_LOOKBACK 4
+#endif
+constexpr int kRowUnroll = DDZ_ROW_UNROLL;               // row-writer iterations in flight per lane
+constexpr int kHeavy = DDZ_HEAVY;                       // envs with more legal moves than this are expanded by the whole warp
+constexpr int kLookBack = DDZ_LOOKBACK;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
 
 enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
 
@@ -152,22 +167,22 @@ template <>
 DDZ_DEV void write_rows<FaceRow>(float4* __restrict__ gdst, int nrows, const RowLane& rl, const float4* __restrict__ lut,
                                  const FaceRow* __restrict__ rows) {
     float4* dst = gdst + (rl.first & 1) * 15 + rl.k;
-#pragma unroll 4
+#pragma unroll (kRowUnroll)
     for (int r = rl.first; r < nrows; r += 2, dst += 30) {
         const float4 raw = *reinterpret_cast<const float4*>(&rows[r]);
         const uint64_t packed = ((uint64_t)__float_as_uint(raw.y) << 32) | __float_as_uint(raw.x);
         const float s = raw.z;
         float4 q = rl.thermo(packed, lut);
         q.x *= s; q.y *= s; q.z *= s; q.w *= s;
-        __stcs(dst, q);
+        DDZ_STORE(dst, q);
     }
 }
 template <>
 DDZ_DEV void write_rows<uint64_t>(float4* __restrict__ gdst, int nrows, const RowLane& rl, const float4* __restrict__ lut,
                                   const uint64_t* __restrict__ rows) {
     float4* dst = gdst + (rl.first & 1) * 15 + rl.k;
-#pragma unroll 4
-    for (int r = rl.first; r < nrows; r += 2, dst += 30) __stcs(dst, rl.thermo(rows[r], lut));
+#pragma unroll (kRowUnroll)
+    for (int r = rl.first; r < nrows; r += 2, dst += 30) DDZ_STORE(dst, rl.thermo(rows[r], lut));
 }
 
 template <int V> struct FaceCfg;
