@@ -393,6 +393,90 @@ DDZ_DEV int enumerate_legal_warp(const Masks& m, const Rule& ru, bool has_last, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// idx-th legal move in canonical order WITHOUT enumerating the list: walk the categories with their closed-form
+// counts, then unrank inside the one group that holds it (O(#groups), not O(#moves)).  idx must be < count_legal.
+// Used by the playout kernel (a random rollout needs one move per decision, not the list).
+// ------------------------------------------------------------------------------------------------
+template <int MULT, int LMIN, int LMAX>
+DDZ_DEV bool select_line(uint32_t src, const Rule& ru, int cat, int& idx, uint64_t& mv) {
+    const uint32_t R = src & kLineMask;
+    uint32_t t = R;
+#pragma unroll
+    for (int L = 2; L <= LMIN; L++) t &= R >> (L - 1);
+    t &= ru.from(cat);
+    const bool same = !ru.lead && cat == ru.cat;
+    while (t) {
+        const int s = __ffs(t) - 1; t &= t - 1;
+        const int maxL = min(__ffs(~(R >> s)) - 1, LMAX);
+        const int c = same ? ((ru.len >= LMIN && ru.len <= maxL) ? 1 : 0) : (maxL - LMIN + 1);
+        if (idx < c) { const int L = same ? ru.len : LMIN + idx; mv = pack_move(((1u << L) - 1u) << s, MULT, 0, 0); return true; }
+        idx -= c;
+    }
+    return false;
+}
+template <int LMAX, int KMULT>
+DDZ_DEV bool select_plane(uint32_t g3, uint32_t kicksrc, const Rule& ru, int cat, int& idx, uint64_t& mv) {
+    const uint32_t R = g3 & kLineMask;
+    uint32_t t = R & (R >> 1) & ru.from(cat);
+    while (t) {
+        const int s = __ffs(t) - 1; t &= t - 1;
+        uint32_t run = 3u << s;
+        for (int L = 2; L <= LMAX; L++, run |= run << 1) {
+            if ((R & run) != run) break;
+            if (!ru.len_ok(cat, L)) continue;
+            const uint32_t S = kicksrc & ~run;
+            const int c = binom(__popc(S), L);
+            if (idx < c) { mv = pack_move(run, 3, unrank_combo(S, L, idx), KMULT); return true; }
+            idx -= c;
+        }
+    }
+    return false;
+}
+template <int KMULT>
+DDZ_DEV bool select_four_two(uint32_t mains, uint32_t kicksrc, int nk, int& idx, uint64_t& mv) {
+    const int per = binom(nk - 1, 2), c = __popc(mains) * per;     // every bomb rank is itself in kicksrc
+    if (idx >= c) { idx -= c; return false; }
+    const int mi = idx / per;
+    const uint32_t main = nth_bit(mains, mi);
+    mv = pack_move(main, 4, unrank_combo(kicksrc & ~main, 2, idx - mi * per), KMULT);
+    return true;
+}
+DDZ_DEV uint64_t select_legal(const Masks& m, const Rule& ru, bool has_last, int idx) {
+    if (m.g1 == 0) return 0ull;
+    if (!ru.lead) { if (idx == 0) return 0ull; idx--; }
+    uint64_t mv = 0;
+    const int n1 = __popc(m.g1), n2 = __popc(m.g2);
+#define DDZ_SELECT_RANKS(CAT, MASK, MULT)                                                     \
+    if (ru.allowed(CAT)) {                                                                    \
+        const uint32_t mk = (MASK) & ru.from(CAT); const int c = __popc(mk);                  \
+        if (idx < c) return pack_move(nth_bit(mk, idx), MULT, 0, 0);                          \
+        idx -= c;                                                                             \
+    }
+    DDZ_SELECT_RANKS(1, m.g1, 1) DDZ_SELECT_RANKS(2, m.g2, 2) DDZ_SELECT_RANKS(3, m.g3, 3) DDZ_SELECT_RANKS(4, m.g4, 4)
+#undef DDZ_SELECT_RANKS
+#define DDZ_SELECT_MAIN_PLUS_ONE(CAT, KSRC, NK, KMULT)                                        \
+    if (ru.allowed(CAT)) {                                                                    \
+        const uint32_t mains = m.g3 & ru.from(CAT); const int nk = (NK) - 1, c = __popc(mains) * nk; \
+        if (idx < c) {                                                                        \
+            const int mi = idx / nk; const uint32_t main = nth_bit(mains, mi);                \
+            return pack_move(main, 3, nth_bit((KSRC) & ~main, idx - mi * nk), KMULT);         \
+        }                                                                                     \
+        idx -= c;                                                                             \
+    }
+    DDZ_SELECT_MAIN_PLUS_ONE(5, m.g1, n1, 1) DDZ_SELECT_MAIN_PLUS_ONE(6, m.g2, n2, 2)
+#undef DDZ_SELECT_MAIN_PLUS_ONE
+    if (ru.allowed(7) && select_line<1, 5, 12>(m.g1, ru, 7, idx, mv)) return mv;
+    if (ru.allowed(8) && select_line<2, 3, 10>(m.g2, ru, 8, idx, mv)) return mv;
+    if (ru.allowed(9) && select_line<3, 2, 6>(m.g3, ru, 9, idx, mv)) return mv;
+    if (ru.allowed(10) && select_plane<5, 1>(m.g3, m.g1, ru, 10, idx, mv)) return mv;
+    if (ru.allowed(11) && select_plane<4, 2>(m.g3, m.g2, ru, 11, idx, mv)) return mv;
+    if (ru.allowed(12) && (m.g1 & kRocket) == kRocket) { if (idx == 0) return pack_move(kRocket, 1, 0, 0); idx--; }
+    if (ru.allowed(13) && select_four_two<1>(m.g4 & ru.from(13), m.g1, n1, idx, mv)) return mv;
+    if (ru.allowed(14) && select_four_two<2>(m.g4 & ru.from(14), m.g2, n2, idx, mv)) return mv;
+    return ~0ull;   // idx out of range
+}
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10, counter (env_lo, env_hi, step, 0), key (seed_lo, seed_hi): the action-index stream
 // ------------------------------------------------------------------------------------------------
 DDZ_DEV uint32_t philox(uint64_t seed, uint64_t env, uint32_t step) {

@@ -533,6 +533,55 @@ __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restri
     }
 }
 
+// idx-th legal move of n independent (hand, last) pairs in closed form (no list): the building block of the playout
+__global__ void __launch_bounds__(256) k_kth_moves(const uint64_t* __restrict__ hands, const uint64_t* __restrict__ lasts,
+                                                   const int32_t* __restrict__ idx, uint64_t* __restrict__ moves,
+                                                   int32_t* __restrict__ counts, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t hand = hands[i], last = lasts[i];
+    const Masks m = masks_of(hand);
+    const Rule ru = rule_of(last);
+    const int c = count_legal(m, ru, last != 0);
+    if (counts) counts[i] = c;
+    const int k = idx[i];
+    moves[i] = (k >= 0 && k < c) ? select_legal(m, ru, last != 0, k) : ~0ull;
+}
+
+// Random playout (the default policy of the reference's MCTS, server/mcts/default_policy.py:4-10: "play random legal
+// moves until the game ends"): every lane plays ITS env forward for up to max_steps decisions, move number
+// philox(seed, env, stepno0 + t) % N of the canonical list each time -- the same stream the stepping API uses, so a
+// playout equals max_steps calls of ddz_rollout_step without re-deal.  No lists, no features, no inter-env traffic:
+// the state stays in registers, one load and one store per env.
+__global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0,
+                                                 int32_t rw0, int32_t rw1, int32_t rw2, int32_t* __restrict__ steps_taken,
+                                                 int64_t* stats, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t rewards[3] = {rw0, rw1, rw2};
+    int steps = 0, passes = 0, over = 0, winner = 0;
+    if (b < B) {
+        const StateView v = view_of(state, B);
+        Env e = load_env(v, b);
+        for (int t = 0; t < max_steps && !e.done(); t++) {
+            const uint64_t hand = hand_to_move(e), last = trick_of(e);
+            const Masks m = masks_of(hand);
+            const Rule ru = rule_of(last);
+            const int n = count_legal(m, ru, last != 0);
+            if (n <= 0) break;
+            const int k = (int)(philox(seed, env0 + (uint64_t)b, stepno0 + (uint32_t)t) % (uint32_t)n);
+            const StepOut so = apply_move(e, select_legal(m, ru, last != 0, k), rewards);
+            steps++; passes += so.pass;
+            if (so.done) { over = 1; winner = so.winner; }
+        }
+        store_env(v, b, e);
+        if (steps_taken) steps_taken[b] = steps;
+    }
+    stat_add(stats, 4, steps); stat_add(stats, 9, passes); stat_add(stats, 0, over);
+    stat_add(stats, 1, over && winner == 1); stat_add(stats, 2, over && winner == 2); stat_add(stats, 3, over && winner == 0);
+    stat_add(stats, 5, over ? (winner == 1 ? rw1 : -rw1) : 0);
+    stat_add(stats, 6, over ? (winner == 1 ? -(rw0 + rw2) : rw0 + rw2) : 0);
+}
+
 // Batched dqn.py:50-71: per env, the index of the best-scoring legal move (first maximum, like torch.argmax), or with
 // probability epsilon a uniformly random one (e_greedy_action).  One lane per env; segments are short (mean 5.6).
 __global__ void __launch_bounds__(256) k_select_actions(const float* __restrict__ q, const int32_t* __restrict__ offsets,
@@ -793,6 +842,25 @@ int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void*
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_encode_actions<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(actions_u64, n, (float4*)out);
     DDZ_LAUNCH_CHECK("k_encode_actions");
+    return 0;
+}
+
+int ddz_kth_moves(const uint64_t* hands, const uint64_t* lasts, const int32_t* idx, uint64_t* moves, int32_t* counts,
+                  int n, void* stream) {
+    if (!hands || !lasts || !idx || !moves || n <= 0) return DDZ_E_ARG;
+    k_kth_moves<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hands, lasts, idx, moves, counts, n);
+    DDZ_LAUNCH_CHECK("k_kth_moves");
+    return 0;
+}
+
+int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
+                int32_t* steps_taken, int64_t* stats, int B, void* stream) {
+    static const int32_t defR[3] = {50, 100, 50};
+    if (!state || B <= 0 || max_steps < 0) return DDZ_E_ARG;
+    const int32_t* R = rewards ? rewards : defR;
+    k_playout<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(state, max_steps, seed, env0, stepno0, R[0], R[1], R[2],
+                                                                   steps_taken, stats, B);
+    DDZ_LAUNCH_CHECK("k_playout");
     return 0;
 }
 

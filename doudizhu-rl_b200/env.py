@@ -293,6 +293,19 @@ class BatchedEnv:
         self._stepno += 1
         return self.r, self.done, self.cat
 
+    def playout(self, max_steps=256):
+        """Random playout of every env (MCTS default policy, server/mcts/default_policy.py:4-10): up to max_steps random
+        legal moves per env or to the end of its game, Philox stream continued from the env's step counter.  One launch,
+        no lists / features written.  Returns int32 [B] decisions played; winners are in `winner`, counters in `stats`."""
+        steps = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_playout(self._p(self._state), int(max_steps), self.seed, self.env0, self._stepno,
+                                      self._rewards.data_ptr(), steps.data_ptr(), self._p(self.stats), self.B,
+                                      self._stream()), "ddz_playout")
+        self._fresh = False
+        self._stepno += int(max_steps)
+        return steps
+
     def _check_errors(self, what):
         if self.debug:
             err = int(self.stats[7].item())
@@ -684,6 +697,22 @@ class MoveGenerator:
                                           self.stats.data_ptr(), self.n,
                                           torch.cuda.current_stream(self.device).cuda_stream), "ddz_legal_moves")
         return self.actions, self.offsets
+
+
+def kth_moves(hands, lasts, idx, device=None):
+    """idx[i]-th move of r.get_moves(hands[i], lasts[i]) without building the lists: (packed int64 [n], counts int32 [n])."""
+    if not torch.cuda.is_available():
+        raise N.DdzError("kth_moves needs a CUDA device")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    h = pack_counts(torch.as_tensor(np.asarray(hands)).reshape(-1, 15).to(dev)).contiguous()
+    l = pack_counts(torch.as_tensor(np.asarray(lasts)).reshape(-1, 15).to(dev)).contiguous()
+    k = torch.as_tensor(np.asarray(idx), dtype=torch.int32).to(dev).contiguous()
+    out = torch.zeros(h.numel(), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(h.numel(), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ddz_kth_moves(h.data_ptr(), l.data_ptr(), k.data_ptr(), out.data_ptr(), cnt.data_ptr(), h.numel(),
+                                    torch.cuda.current_stream(dev).cuda_stream), "ddz_kth_moves")
+    return out, cnt
 
 
 def get_moves(hands, lasts, device=None):

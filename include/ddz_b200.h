@@ -112,6 +112,18 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,
                     uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream);
 
+/* idx[i]-th move of r.get_moves(hands[i], lasts[i]) in closed form, without building the list (moves[i] = ~0 when idx is
+ * out of range); counts (optional) = the list lengths. */
+int ddz_kth_moves(const uint64_t* hands, const uint64_t* lasts, const int32_t* idx, uint64_t* moves, int32_t* counts,
+                  int n, void* stream);
+
+/* Random playout = the default policy of the reference's MCTS (server/mcts/default_policy.py:4-10, random legal moves
+ * until the game ends): plays every env forward for up to max_steps decisions (or to its end), move number
+ * philox(seed, env0+b, stepno0+t) % N each time -- exactly what max_steps calls of ddz_rollout_step(DDZ_CHOICE_PHILOX)
+ * without re-deal would do, but with no lists or features written.  steps_taken int32[B] may be NULL. */
+int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
+                int32_t* steps_taken, int64_t* stats, int B, void* stream);
+
 /* Env.batch_arr2onehot over packed moves (envi.py:113,140-146): out float32[n][15][4] */
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream);
 

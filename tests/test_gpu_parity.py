@@ -725,3 +725,68 @@ def test_replay_buffer_and_td_step(D):
     for _ in range(30):
         last = D.td_step(policy, target, opt, (s0, a0, r, s1, a1, done), 0.95)
     assert last < first
+
+
+# ------------------------------------------------------------------ k-th move in closed form + random playouts (8f rank 4)
+def test_kth_moves_equal_the_enumerated_lists(D, oracle, golden):
+    """select_legal: the idx-th move computed from counts + unranking == the idx-th entry of the enumerated list, for
+    every index of every golden / adversarial / random (hand, last) pair."""
+    g = golden.legal_sets
+    rng = np.random.default_rng(17)
+    hands = np.concatenate([g["hands"], _rand_hands(rng, 1500)])
+    z = np.zeros(15, np.int8)
+    lasts = [l for l in g["lasts"]]
+    for i in range(1500):
+        if i % 2:
+            om = oracle.get_moves(_rand_hands(rng, 1, 2, 21)[0], z, fast=True)
+            lasts.append(om[rng.integers(len(om))])
+        else:
+            lasts.append(z)
+    lasts = np.array(lasts, np.int8)
+    packed, offsets = D.get_moves(hands, lasts)
+    packed, off = packed.cpu().numpy(), offsets.cpu().numpy().astype(np.int64)
+    owner = np.repeat(np.arange(len(hands)), np.diff(off))
+    idx = np.arange(len(packed)) - off[owner]
+    got, cnt = D.kth_moves(hands[owner], lasts[owner], idx)
+    assert np.array_equal(got.cpu().numpy(), packed)
+    assert np.array_equal(cnt.cpu().numpy(), np.diff(off)[owner])
+    bad, _ = D.kth_moves(hands[:100], lasts[:100], np.diff(off)[:100])          # one past the end
+    assert (bad.cpu().numpy() == -1).all()
+
+
+def test_playout_equals_step_by_step_rollout(D, oracle):
+    """ddz_playout (one launch, no lists) == stepping the same envs move by move with the same Philox stream: the MCTS
+    default policy (server/mcts/default_policy.py:4-10) as a primitive."""
+    B, seed = 3000, 31337
+    perm, lord = D.random_deals(B, seed=15)
+    env = D.BatchedEnv(B, seed=seed, env0=500)
+    env.prepare(perm, lord)
+    for _ in range(7):                                   # start from mid-game positions, step counter at 7
+        env.rollout_step()
+    ref = oracle.RefBatch(B, 0)
+    ref.deal(perm, lord)
+    for t in range(7):
+        ref.observe(want_f32=False, want_face=False)
+        ref.step(mode=2, seed=seed, env0=500, step=t)
+    _compare_state(env, ref, 7)
+    steps = env.playout(max_steps=20)                    # a bounded playout first ...
+    taken = np.zeros(B, np.int64)
+    for t in range(7, 27):
+        ref.observe(want_f32=False, want_face=False)
+        before = ref.envs["done"].copy()
+        ref.step(mode=2, seed=seed, env0=500, step=t)
+        taken += (before == 0)
+    _compare_state(env, ref, 27)
+    assert np.array_equal(steps.cpu().numpy(), taken)
+    env.playout(max_steps=300)                           # ... then to the end of every game
+    for t in range(27, 327):
+        ref.observe(want_f32=False, want_face=False)
+        ref.step(mode=2, seed=seed, env0=500, step=t)
+        if ref.envs["done"].all():
+            break
+    assert env.is_done.all()
+    assert np.array_equal(env.winner.cpu().numpy(), ref.envs["winner"])
+    _f, _m = ref.export()
+    assert np.array_equal(env._fields()[0].cpu().numpy().view(np.uint64), _f)
+    st = env.stats.cpu().numpy()
+    assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 9]], ref.stats[[0, 1, 2, 3, 4, 5, 6, 9]]) and st[7] == 0
