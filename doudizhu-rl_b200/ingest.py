@@ -57,16 +57,23 @@ def payload_arrays(payloads):
     return role, hand, hist, last, left
 
 
-def env_from_arrays(role, hand, hist, last, left, env_cls=BatchedEnvCooperationSimplify, **kw):
+def env_from_arrays(role, hand, hist, last, left, env_cls=BatchedEnvCooperationSimplify, hands=None, **kw):
+    """hands (optional, int [B,3,15]): every role's real hand, for full-information positions such as the payload of the
+    reference's MCTS bot (`hand_card`, server/mcts/interface.py:19-27); without it the other players get placeholders."""
     role, hand, hist, last, left = (np.asarray(x, np.int64) for x in (role, hand, hist, last, left))
     B = len(role)
     if ((role < 0) | (role > 2)).any() or (hand < 0).any() or (hand > 4).any() or (hist.sum(1) > 4).any():
         raise ValueError("bad payload: role_id must be 0..2 and no rank can appear more than four times")
     env = env_cls(B, **kw)
-    hands = np.zeros((B, 3, 15), np.int64)
-    for b in range(B):
-        for q in range(3):
-            hands[b, q] = hand[b] if q == role[b] else _placeholder(int(left[b, q]))
+    if hands is not None:
+        hands = np.asarray(hands, np.int64).reshape(B, 3, 15)
+        if (hands[np.arange(B), role] != hand).any():
+            raise ValueError("hands[b, role_id] must equal cur_cards")
+    else:
+        hands = np.zeros((B, 3, 15), np.int64)
+        for b in range(B):
+            for q in range(3):
+                hands[b, q] = hand[b] if q == role[b] else _placeholder(int(left[b, q]))
     dev = env.device
     f, meta = env._fields()
     f[0:3] = pack_counts(torch.as_tensor(hands).to(dev)).t()
@@ -80,3 +87,26 @@ def env_from_arrays(role, hand, hist, last, left, env_cls=BatchedEnvCooperationS
 def env_from_payloads(payloads, env_cls=BatchedEnvCooperationSimplify, **kw):
     """BatchedEnv* whose env b is the position described by payloads[b] (server/core.py Predictor.face / valid_actions)"""
     return env_from_arrays(*payload_arrays(payloads), env_cls=env_cls, **kw)
+
+
+def evaluate_moves(role, hands, hist, last, sims=256, seed=1, env_cls=None, device=None):
+    """Flat Monte-Carlo evaluation of ONE full-information position (the job of the reference's MCTS bot,
+    server/mcts/interface.py:15-45, with its random default policy but without the UCT tree): every legal move of the
+    player to move is followed by `sims` random playouts to the end of the game (ddz_playout); returns
+    (moves int64 [N,15], win_rate float [N]) where a win is a win of the mover's side."""
+    from .env import BatchedEnv, unpack_counts
+    env_cls = env_cls or BatchedEnv
+    role = int(role)
+    hands = np.asarray(hands, np.int64).reshape(3, 15)
+    one = env_from_arrays([role], [hands[role]], [hist], [last], [hands.sum(1)], env_cls=env_cls, hands=[hands], device=device)
+    moves = unpack_counts(one.actions_packed).cpu().numpy()
+    n = len(moves)
+    B = n * int(sims)
+    env = env_from_arrays([role] * B, [hands[role]] * B, [hist] * B, [last] * B, [hands.sum(1)] * B, env_cls=env_cls,
+                          hands=[hands] * B, seed=seed, device=device)
+    first = torch.arange(n, device=env.device, dtype=torch.int32).repeat_interleave(int(sims))
+    env.step(first)                       # env i plays move i // sims ...
+    env.playout(max_steps=400)            # ... then everybody plays randomly to the end
+    winner = env.winner.reshape(n, int(sims))
+    mine = (winner == 1) if role == 1 else (winner != 1)
+    return moves, mine.float().mean(1).cpu().numpy()

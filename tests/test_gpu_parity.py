@@ -790,3 +790,35 @@ def test_playout_equals_step_by_step_rollout(D, oracle):
     assert np.array_equal(env._fields()[0].cpu().numpy().view(np.uint64), _f)
     st = env.stats.cpu().numpy()
     assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 9]], ref.stats[[0, 1, 2, 3, 4, 5, 6, 9]]) and st[7] == 0
+
+
+def test_flat_monte_carlo_move_evaluation(D, oracle):
+    """evaluate_moves (the MCTS bot's job with playouts instead of a tree): a move that empties the hand wins every
+    playout; win rates agree with playouts stepped on the oracle within sampling noise."""
+    z = np.zeros(15, np.int64)
+    hands = np.zeros((3, 15), np.int64)
+    hands[1, [0, 1, 2, 3, 4]] = 1          # lord: 3 4 5 6 7  -> the straight ends the game at once
+    hands[2, [5, 5 + 1]] = 2               # down: 88 99
+    hands[0, [10, 11, 12]] = [1, 2, 1]     # up:   K AA 2
+    hist = np.zeros((3, 15), np.int64)
+    moves, win = D.evaluate_moves(1, hands, hist, np.zeros((3, 15), np.int64), sims=512, seed=5)
+    straight = np.array([1] * 5 + [0] * 10)
+    i = int(np.flatnonzero((moves == straight).all(1))[0])
+    assert win[i] == 1.0 and len(moves) == 6                 # five singles + the straight
+    assert (win[np.arange(len(moves)) != i] < 1.0).all()
+    # cross-check one move's win rate against the oracle driven with its own random stream
+    j = 0
+    rng = np.random.default_rng(0)
+    wins, n = 0, 400
+    for _ in range(n):
+        rb = oracle.RefBatch(1, 0)
+        rb.envs["hand"][0] = hands
+        rb.envs["cur"] = 1
+        first = True
+        while not rb.envs["done"][0]:
+            off, _, _, _ = rb.observe(want_f32=False, want_face=False)
+            k = j if first else int(rng.integers(off[1]))
+            first = False
+            rb.step(np.array([k], np.int32), mode=0)
+        wins += int(rb.envs["winner"][0] == 1)
+    assert abs(wins / n - win[j]) < 0.09                     # 3 sigma of two binomial estimates
