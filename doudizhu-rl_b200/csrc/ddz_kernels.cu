@@ -34,11 +34,14 @@
 
 namespace ddz {
 
-constexpr int kThreads = 128;                    // threads per CTA
+#ifndef DDZ_THREADS
+#define DDZ_THREADS 128
+#endif
+constexpr int kThreads = DDZ_THREADS;            // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
-constexpr int kEnvs = kThreads;                  // envs per CTA for the simple thread-per-env kernels
+constexpr int kEnvs = 128;                       // envs per CTA for the simple thread-per-env kernels
 constexpr int kWin = 320;                        // legal moves staged per window (one warp)
-constexpr int kMinCtasPerSm = 7;                 // 28 warps per SM (one wave at 131 072 envs): <= 72 registers
+constexpr int kMinCtasPerSm = 28 / kWarpsPerCta;  // 28 warps per SM (one wave at 131 072 envs): <= 72 registers
 #ifdef DDZ_PLAIN_STORES
 #define DDZ_STORE(p, v) (*(p) = (v))
 #else
