@@ -822,3 +822,31 @@ def test_flat_monte_carlo_move_evaluation(D, oracle):
             rb.step(np.array([k], np.int32), mode=0)
         wins += int(rb.envs["winner"][0] == 1)
     assert abs(wins / n - win[j]) < 0.09                     # 3 sigma of two binomial estimates
+
+
+def test_step_manual_rejects_a_move_that_is_not_legal(D):
+    """envi.py:63-70 step_manual with a one-hot that is not among valid_actions(): refused, flagged, state untouched."""
+    B = 32
+    perm, lord = D.random_deals(B, seed=77)
+    env = D.BatchedEnv(B)
+    env.prepare(perm, lord)
+    before = env._state.clone()
+    acts, offs = env.valid_actions()
+    bogus = torch.zeros((B, 15, 4), device="cuda")
+    bogus[:, 0, :] = 1                                   # four 3s: nobody holds them all in (almost) every deal
+    has_bomb3 = env.get_curr_handcards()[:, 0] == 4
+    r, done, cat = env.step_manual(bogus)
+    torch.cuda.synchronize()
+    bad = ~has_bomb3
+    assert bad.any()
+    assert (cat[bad] == -1).all() and (r[bad] == 0).all()
+    f_before = before[: 18 * B].view(torch.int64).view(9, B)
+    assert torch.equal(env._fields()[0][:, bad], f_before[:, bad])
+    assert (((env._fields()[1] >> 5) & 1).bool() == bad).all()
+    assert int(env.stats[7].item()) == int(bad.sum())
+    # the B = 1 view: a legal random move from host entropy works as in the reference (envi.py:79-85)
+    one = D.Env(debug=True)
+    one.reset(); one.prepare()
+    n = one.valid_actions().shape[0]
+    r1, d1, c1 = one.step_random(12345)
+    assert (r1, d1) == (0, False) and 1 <= c1 <= 14 and n > 0 and one.get_role_ID() == 3
