@@ -16,17 +16,19 @@ class BatchedGreedyPolicy:
         self.net, self.epsilon, self.seed, self.chunk = net, float(epsilon), int(seed), int(chunk_actions)
 
     @torch.no_grad()
-    def q_values(self, env):
-        """float32 [sumN]: Q(face[env of move i], move i) for every legal move of every env."""
+    def q_values(self, env, env_mask=None):
+        """float32 [sumN]: Q(face[env of move i], move i) for every legal move of every env.  env_mask (bool [B]): score
+        only the moves of those envs (e.g. the ones where it is the learning role's turn); the others get 0."""
         face = env.face
         actions, offsets = env.valid_actions()
         n = actions.shape[0]
         counts = (offsets[1:] - offsets[:-1]).to(torch.int64)
         owner = torch.repeat_interleave(torch.arange(env.B, device=face.device), counts, output_size=n)
-        q = torch.empty(n, dtype=torch.float32, device=face.device)
-        for lo in range(0, n, self.chunk):
-            hi = min(n, lo + self.chunk)
-            q[lo:hi] = self.net(face[owner[lo:hi]], actions[lo:hi]).reshape(-1).to(torch.float32)
+        q = torch.zeros(n, dtype=torch.float32, device=face.device)
+        rows = torch.arange(n, device=face.device) if env_mask is None else env_mask[owner].nonzero(as_tuple=True)[0]
+        for lo in range(0, rows.numel(), self.chunk):
+            sel = rows[lo:lo + self.chunk]
+            q[sel] = self.net(face[owner[sel]], actions[sel]).reshape(-1).to(torch.float32)
         return q
 
     def select(self, env, q, stepno=None):
@@ -39,5 +41,5 @@ class BatchedGreedyPolicy:
                                              torch.cuda.current_stream(q.device).cuda_stream), "ddz_select_actions")
         return choice
 
-    def act(self, env):
-        return self.select(env, self.q_values(env))
+    def act(self, env, env_mask=None):
+        return self.select(env, self.q_values(env, env_mask))

@@ -2,8 +2,8 @@
 
 The lord's decision = argmax_a Q(face, a) over its legal moves with a network of the reference's NetCooperation contract
 (10 x 15 x 4 input, 256-wide (1,k)-stride-(1,4) convolutions, net.py:125-139; random-init weights, no checkpoint ships).
-Here every env is scored every step (the shim scores all legal moves of all envs in one batched forward) and the farmers'
-turns then override the choice with a random legal move -- a lord-only scorer would cost a third of the network time.
+Only the envs where it is the lord's turn are scored (about a third of them per step); the farmers' envs take a random
+legal move.
 Reports env-steps/s and how the step time splits between the env kernel and the network.
 """
 import json
@@ -36,12 +36,13 @@ def main():
     def step():
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        q = policy.q_values(env)
+        is_lord = env.get_role_ID() == 2
+        q = policy.q_values(env, is_lord)
         greedy = policy.select(env, q)
         off = env.offsets
         cnt = (off[1:] - off[:-1])
         ent = torch.randint(0, 1 << 30, (B,), device="cuda", dtype=torch.int32, generator=gen)
-        choice = torch.where(env.get_role_ID() == 2, greedy, ent % cnt.clamp(min=1)).to(torch.int32)
+        choice = torch.where(is_lord, greedy, ent % cnt.clamp(min=1)).to(torch.int32)
         t1.record()
         env.rollout_step(choice, mode=D.native.CHOICE_INDEX, perm=pd, lord_pile=ld, pool_games=P)
         t2.record()
