@@ -394,8 +394,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ensure_built():
+    """a fresh checkout has no built artefacts (*.so are git-ignored): build them in-tree before importing the package"""
+    if not os.path.exists(os.path.join(ROOT, "doudizhu-rl_b200", "libddz_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def main():
     args = parse_args()
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ensure_built()
+    else:                                   # the other ranks wait for rank 0's build instead of racing it
+        lib = os.path.join(ROOT, "doudizhu-rl_b200", "libddz_b200.so")
+        for _ in range(600):
+            if os.path.exists(lib) and time.time() - os.path.getmtime(lib) > 2.0:
+                break
+            time.sleep(0.5)
     if args.impl == "reference":
         run_reference(args)
     else:
