@@ -253,3 +253,13 @@ def max_lead_moves_exhaustive(nthreads=8):
     vis = C.c_longlong(0)
     m = lib().ddz_ref_max_lead_moves_exhaustive(int(nthreads), _ptr(best, C.c_int8), C.byref(vis))
     return int(m), best, int(vis.value)
+
+
+def count_moves_batch(hands, lasts):
+    """number of legal moves for each (hand, last) pair (constructive generator, counting only) -> int32 [n]"""
+    h, l = _i8(hands).reshape(-1, 15), _i8(lasts).reshape(-1, 15)
+    out = np.zeros(len(h), np.int32)
+    f = lib().ddz_ref_count_moves_fast
+    for i in range(len(h)):
+        out[i] = f(_ptr(h[i], C.c_int8), _ptr(l[i], C.c_int8))
+    return out

@@ -855,3 +855,49 @@ def test_step_manual_rejects_a_move_that_is_not_legal(D):
     n = one.valid_actions().shape[0]
     r1, d1, c1 = one.step_random(12345)
     assert (r1, d1) == (0, False) and 1 <= c1 <= 14 and n > 0 and one.get_role_ID() == 3
+
+
+def test_legal_move_counts_at_scale(D, oracle):
+    """400 000 random (hand, last) pairs through ddz_legal_moves: the list lengths equal the oracle's, the kernel's own
+    closed-form-count == enumerated-count self-check never fires, every list is duplicate-free, sorted into the canonical
+    category order, and fits in the hand."""
+    rng = np.random.default_rng(2024)
+    n = 400_000
+    deck = np.array([i // 4 for i in range(52)] + [13, 14])
+    sizes = rng.integers(1, 21, n)
+    order = np.argsort(rng.random((n, 54)), axis=1)                      # a random deal per row
+    hands = np.zeros((n, 15), np.int8)
+    ranks = deck[order]
+    for k in range(20):
+        take = sizes > k
+        np.add.at(hands, (np.flatnonzero(take), ranks[take, k]), 1)
+    # previous moves: legal lead moves of other random hands (computed on the GPU), half of the pairs lead
+    other = np.zeros((n, 15), np.int8)
+    for k in range(17):
+        np.add.at(other, (np.arange(n), ranks[:, 30 + k]), 1)
+    lead_lists, lead_off = D.get_moves(other, np.zeros_like(other))
+    lo = lead_off.cpu().numpy().astype(np.int64)
+    pick = lo[:-1] + (rng.integers(0, 1 << 30, n) % np.diff(lo))
+    lasts_packed = lead_lists[torch.as_tensor(pick).cuda()].clone()
+    lasts_packed[torch.as_tensor(rng.random(n) < 0.5).cuda()] = 0
+    gen = D.MoveGenerator(n)
+    hp = D.pack_counts(torch.as_tensor(hands).cuda()).contiguous()
+    acts, offs = gen.generate(hp, lasts_packed)
+    torch.cuda.synchronize()
+    assert int(gen.stats[7].item()) == 0                                  # count_legal == what the walks emitted
+    off = offs.to(torch.int64)
+    cnt = (off[1:] - off[:-1]).cpu().numpy()
+    lasts = D.unpack_counts(lasts_packed).cpu().numpy().astype(np.int8)
+    sample = rng.choice(n, 60_000, replace=False)
+    assert np.array_equal(cnt[sample], oracle.count_moves_batch(hands[sample], lasts[sample]))
+    total = int(off[n])
+    mv = acts[:total]
+    owner = torch.repeat_interleave(torch.arange(n, device="cuda"), off[1:] - off[:-1])
+    counts = D.unpack_counts(mv)
+    assert (counts <= torch.as_tensor(hands).cuda().to(torch.int64)[owner]).all()                 # containment
+    same_owner = owner[1:] == owner[:-1]
+    assert (mv[1:][same_owner] != mv[:-1][same_owner]).all()                                     # no immediate repeats
+    key = owner * (1 << 20) + torch.arange(total, device="cuda")                                 # (sanity of CSR order)
+    assert (key[1:] > key[:-1]).all()
+    uniq = torch.unique(torch.stack([owner, mv], 1), dim=0).shape[0]
+    assert uniq == total                                                                         # duplicate-free lists
