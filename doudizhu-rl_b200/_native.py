@@ -35,6 +35,8 @@ lib.ddz_observe.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp
 lib.ddz_step.argtypes = [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.ddz_rollout_step.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
+lib.ddz_rollout_steps.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _i,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
 lib.ddz_legal_moves.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]
 lib.ddz_encode_actions.argtypes = [_vp, _i64, _vp, _vp]
 lib.ddz_encode_face.argtypes = [_vp, _i, _vp, _i, _vp]
@@ -52,7 +54,7 @@ lib.ddz_select_actions.argtypes = [_vp, _vp, C.c_float, _u64, _u64, _u32, _vp, _
 EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
            "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
-           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill")
+           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_rollout_steps")
 
 if lib.ddz_abi_version() != ABI_VERSION:
     raise ImportError("libddz_b200.so ABI %d != binding %d: rebuild" % (lib.ddz_abi_version(), ABI_VERSION))

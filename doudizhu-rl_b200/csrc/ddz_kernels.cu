@@ -228,6 +228,7 @@ struct StepArgs {
     uint64_t seed, env0; uint32_t stepno; int32_t rewards[3];
     const int8_t* perm; const int8_t* lord_pile; int pool_games;
     int8_t* r; uint8_t* done; int8_t* cat; float* reward;
+    long long prev_cap;   // capacity of `actions` (0 = unknown): a list cut off by an overflow is never read past it
 };
 struct OutArgs {
     int32_t* offsets; uint64_t* actions_u64; float4* actions_f32; long long cap; float4* face;
@@ -335,8 +336,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, stepno) % (uint32_t)cnt) : -1;
                 else {
                     const uint64_t want = choice_raw;
-                    for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
+                    const int have = a.prev_cap > 0 ? (int)max(0ll, min((long long)cnt, a.prev_cap - base)) : cnt;
+                    for (int i = 0; i < have; i++) if (a.actions[base + i] == want) { idx = i; break; }
                 }
+                if (a.prev_cap > 0 && idx >= 0 && (long long)base + idx >= a.prev_cap) idx = -1;   // dropped by an overflow
                 if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; sf += 32u; }
                 else {
                     StepOut so = apply_move(e, a.actions[base + idx], a.rewards);
@@ -737,8 +740,37 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
     int rc = fill_step_args(a, prev_offsets, prev_actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
     a.perm = perm; a.lord_pile = lord_pile; a.pool_games = perm ? pool_games : 1;
+    a.prev_cap = cap;   // the ping-pong lists have the same capacity
     OutArgs o{out_offsets, out_actions_u64, (float4*)out_actions_f32, cap, (float4*)face, 0};
     return launch_env_v<kStepObserve>(variant, face != nullptr, state, a, o, workspace, stats, B, (cudaStream_t)stream);
+}
+
+int ddz_rollout_steps(void* state, void* workspace, int variant, int nsteps,
+                      const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                      const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
+                      const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                      int8_t* r, uint8_t* done, int8_t* cat, float* reward,
+                      int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                      float* face, int64_t* stats, int B, void* stream) {
+    if (nsteps < 1 || B <= 0 || cap < 0 || !out_offsets || !out_actions_u64) return DDZ_E_ARG;
+    if (choice_mode != DDZ_CHOICE_PHILOX && choice_mode != DDZ_CHOICE_MOD) return DDZ_E_ARG;   // nobody sees the lists in between
+    const int C = face ? ddz_face_channels(variant) : 0;
+    if (C < 0) return DDZ_E_ARG;
+    const size_t nB = (size_t)B;
+    for (int s = 0; s < nsteps; s++) {
+        const size_t k = (size_t)s;
+        const int rc = ddz_rollout_step(
+            state, workspace, variant, s ? out_offsets + (k - 1) * (nB + 1) : prev_offsets,
+            s ? out_actions_u64 + (k - 1) * (size_t)cap : prev_actions_u64,
+            choice ? (const char*)choice + k * nB * 4 : nullptr, choice_mode, seed, env0,
+            stepno == DDZ_STEPNO_AUTO ? stepno : stepno + (uint32_t)s, rewards, perm, lord_pile, pool_games,
+            r ? r + k * nB : nullptr, done ? done + k * nB : nullptr, cat ? cat + k * nB : nullptr,
+            reward ? reward + k * nB * 3 : nullptr, out_offsets + k * (nB + 1), out_actions_u64 + k * (size_t)cap,
+            out_actions_f32 ? out_actions_f32 + k * (size_t)cap * 60 : nullptr, cap,
+            face ? face + k * nB * (size_t)C * 60 : nullptr, stats, B, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // ---- host-buffer pipeline -------------------------------------------------------------------------

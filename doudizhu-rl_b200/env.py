@@ -74,6 +74,32 @@ class StepResults:
             self.r_np, self.done_np, self.cat_np, self.reward_np = (t.numpy() for t in (self.r, self.done, self.cat, self.reward))
 
 
+class Trajectory:
+    """Output buffers of a multi-step call (BatchedEnv.rollout_steps): slice s of every tensor is the observation
+    and the step results after step s -- offsets int32 [K,B+1], actions_u64 int64 [K,cap], actions_f32 [K,cap,15,4],
+    face [K,B,C,15,4], r / done / cat [K,B], reward [K,B,3]."""
+
+    def __init__(self, env, nsteps, want_reward=True):
+        K, B, dev = int(nsteps), env.B, env.device
+        if K < 1:
+            raise ValueError("nsteps must be positive")
+        self.K, self.B, self.C = K, B, env.C
+        self.cap = env.cap
+        self.offsets = torch.zeros((K, B + 1), dtype=torch.int32, device=dev)
+        self.actions_u64 = torch.zeros((K, self.cap), dtype=torch.int64, device=dev)
+        self.actions_f32 = torch.empty((K, self.cap, 15, 4), dtype=torch.float32, device=dev)
+        self.face = torch.empty((K, B, env.C, 15, 4), dtype=torch.float32, device=dev)
+        self.r = torch.zeros((K, B), dtype=torch.int8, device=dev)
+        self.done = torch.zeros((K, B), dtype=torch.uint8, device=dev)
+        self.cat = torch.zeros((K, B), dtype=torch.int8, device=dev)
+        self.reward = torch.zeros((K, B, 3), dtype=torch.float32, device=dev) if want_reward else None
+
+    def valid_actions(self, s):
+        """(float32 [N_s,15,4], int32 [B+1]) of slice s (synchronises to read the total)"""
+        n = int(self.offsets[s, self.B].item())
+        return self.actions_f32[s, :min(n, self.cap)], self.offsets[s]
+
+
 class BatchedEnv:
     """B independent Doudizhu games on one GPU.  Reference: envi.py:16-157 (class Env, C=4 face)."""
 
@@ -292,6 +318,34 @@ class BatchedEnv:
         self._cur, self._fresh, self._n_total = nxt, True, None
         self._stepno += 1
         return self.r, self.done, self.cat
+
+    def rollout_steps(self, traj, entropy=None, perm=None, lord_pile=None, pool_games=1, auto_step=False):
+        """traj.K fused env-steps enqueued by ONE native call (ddz_rollout_steps), every step's observation and results
+        kept in `traj`: the random rollout (envi.py:79-85 for all three seats, game.py:259-275) needs no host decision
+        between steps.  Moves: Philox stream of the env (entropy None) or host-made entropy int32 [K,B]
+        (index = entropy % N).  Equal to traj.K calls of rollout_step; the env's own lists are stale afterwards
+        (the next .face / .valid_actions() re-observes)."""
+        self._ensure()
+        K = traj.K
+        if traj.cap != self.cap:
+            raise ValueError("the trajectory must have the env's list capacity (max_actions_per_env)")
+        mode = N.CHOICE_PHILOX if entropy is None else N.CHOICE_MOD
+        if entropy is not None:
+            entropy = self._to_dev(entropy, torch.int32)
+            if entropy.numel() != K * self.B:
+                raise ValueError("entropy must be [K,B]")
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_rollout_steps(
+                self._p(self._state), self._p(self._ws), self.VARIANT, K,
+                self._p(self._offsets[self._cur]), self._p(self._actions_u64[self._cur]), self._p(entropy), mode,
+                self.seed, self.env0, N.STEPNO_AUTO if auto_step else self._stepno, self._rewards.data_ptr(),
+                self._p(perm), self._p(lord_pile), int(pool_games), self._p(traj.r), self._p(traj.done),
+                self._p(traj.cat), self._p(traj.reward), self._p(traj.offsets), self._p(traj.actions_u64),
+                self._p(traj.actions_f32), traj.cap, self._p(traj.face), self._p(self.stats), self.B, self._stream()),
+                "ddz_rollout_steps")
+        self._fresh, self._n_total = False, None
+        self._stepno += K
+        return traj
 
     def playout(self, max_steps=256):
         """Random playout of every env (MCTS default policy, server/mcts/default_policy.py:4-10): up to max_steps random

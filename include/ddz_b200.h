@@ -88,7 +88,7 @@ int ddz_observe(const void* state, void* workspace, int variant, int32_t* offset
 
 /* env.step_manual / step_random for all envs  (envi.py:63-70, 79-85, _update :38-43; terminal + sign
  * rule_based/rule_play.py:14-28; rewards game.py:109-118 with magnitudes rewards[role]).
- * offsets/actions_u64 must be the lists ddz_observe produced for the CURRENT state.
+ * offsets/actions_u64 must be the COMPLETE lists ddz_observe produced for the CURRENT state (no overflow: stats[7]).
  * Outputs (any may be NULL): r int8[B] (-1 lord won, +1 farmers won, 0), done uint8[B], cat int8[B]
  * (card.py:13-28 category of the move, -1 if nothing was applied), reward float32[B][3].
  * Finished envs and illegal choices are no-ops (illegal: sticky error bit + stats[7]). */
@@ -98,7 +98,8 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
 
 /* One fused env-step = ddz_step, then ddz_reset(only_done=1) when perm != NULL, then ddz_observe of the
  * new state, in ONE launch.  prev_* are the lists of the state being stepped, out_* receive the new
- * lists (ping-pong; they must not alias). */
+ * lists (ping-pong; they must not alias and both hold cap moves: a choice that falls into the part of a list an
+ * overflow dropped is an illegal choice, never an out-of-bounds read). */
 int ddz_rollout_step(void* state, void* workspace, int variant,
                      const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
                      const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
@@ -106,6 +107,23 @@ int ddz_rollout_step(void* state, void* workspace, int variant,
                      int8_t* r, uint8_t* done, int8_t* cat, float* reward,
                      int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
                      float* face, int64_t* stats, int B, void* stream);
+
+/* nsteps consecutive ddz_rollout_step's of a policy that needs no host decision in between -- the random rollout of
+ * envi.py:79-85 / game.py:259-275 -- enqueued by ONE call, every step's observation kept (a trajectory):
+ *   prev_* are the lists of the state the first step starts from;
+ *   choice_mode DDZ_CHOICE_PHILOX (choice == NULL) or DDZ_CHOICE_MOD (choice = uint32 [nsteps][B] entropy);
+ *   r / done / cat are [nsteps][B], reward [nsteps][B][3] (any may be NULL);
+ *   out_offsets int32 [nsteps][B+1], out_actions_u64 [nsteps][cap], out_actions_f32 [nsteps][cap][15][4],
+ *   face float32 [nsteps][B][C][15][4]: slice s is the observation after step s (Philox step number stepno + s).
+ * nsteps launches of the fused kernel on `stream`, slice s-1 feeding step s.  (A single launch that pipelines the steps
+ * as a wavefront was built and measured slower: DESIGN.md 4, profiles/experiments/.) */
+int ddz_rollout_steps(void* state, void* workspace, int variant, int nsteps,
+                      const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
+                      const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
+                      const int32_t rewards[3], const int8_t* perm, const int8_t* lord_pile, int pool_games,
+                      int8_t* r, uint8_t* done, int8_t* cat, float* reward,
+                      int32_t* out_offsets, uint64_t* out_actions_u64, float* out_actions_f32, int64_t cap,
+                      float* face, int64_t* stats, int B, void* stream);
 
 /* r.get_moves(hand15, last15) for n independent (hand, last) pairs  (envi.py:111, server/core.py:65):
  * hands/lasts packed uint64[n]; last == 0 means lead.  Same CSR outputs as ddz_observe. */

@@ -85,6 +85,37 @@ __global__ void __launch_bounds__(128, 8) k_tma(float4* out, int nwarps) {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// variant 7: rows30_cs repeated K times by the same warps into K different buffers inside ONE launch (a K-step launch)
+__global__ void __launch_bounds__(128, 7) k_rows30_steps(float4* out, int nwarps, int K) {
+    int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= nwarps || lane >= 30) return;
+    float4 v = make_float4(1.f, 0.f, 1.f, (float)w);
+    for (int s = 0; s < K; s++) {
+        float4* dst = out + ((size_t)s * nwarps + w) * kVecPerWarp + lane;
+#pragma unroll 4
+        for (int i = 0; i < kRowsPerWarp / 2; i++, dst += 30) st_cs(dst, v);
+    }
+}
+
+// variant 8: 256-bit stores (st.global.v8.f32, sm_100+): lanes 0..29 x 32 B = four 240-byte rows per warp instruction
+__device__ __forceinline__ void st_v8(float* p, float4 a, float4 b) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
+                 "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+__global__ void __launch_bounds__(128, 8) k_rows30_v8(float4* out, int nwarps) {
+    int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= nwarps || lane >= 30) return;
+    float* dst = (float*)(out + (size_t)w * kVecPerWarp) + lane * 8;
+    float4 v = make_float4(1.f, 0.f, 1.f, (float)w);
+#pragma unroll 4
+    for (int i = 0; i < kRowsPerWarp / 4; i++, dst += 240) st_v8(dst, v, v);
+}
+__global__ void __launch_bounds__(128, 8) k_gridstride_v8(float4* out, size_t nvec8) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    float4 v = make_float4(1.f, 0.f, 1.f, 2.f);
+    for (; i < nvec8; i += stride) st_v8((float*)out + i * 8, v, v);
+}
+
 template <class F>
 static float best_ms(F launch) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -113,6 +144,24 @@ int main(int argc, char** argv) {
     REPORT("gridstride", (k_gridstride<<<grid, 128>>>(out, nvec)));
     REPORT("gridstride_148x8", (k_gridstride<<<148 * 8, 128>>>(out, nvec)));
     REPORT("tma_tile", (k_tma<<<grid, 128, 4 * 7680>>>(out, nwarps)));
+    REPORT("rows30_v8_cs", (k_rows30_v8<<<grid, 128>>>(out, nwarps)));
+    REPORT("gridstride_v8", (k_gridstride_v8<<<grid, 128>>>(out, nvec / 2)));
+    REPORT("memset", CK(cudaMemsetAsync(out, 1, bytes)));
+    {   // K steps: K launches back to back vs one launch that loops (both write K x bytes into K buffers)
+        const int K = 8;
+        float4* big; CK(cudaMalloc(&big, bytes * K + 4096));
+        float ms = best_ms([&] { for (int s = 0; s < K; s++) k_rows30<true><<<grid, 128>>>(big + (size_t)s * nvec, nwarps); });
+        printf(", \"rows30_cs_8_launches_GBs\": %.0f", bytes * K / ms / 1e6);
+        ms = best_ms([&] { k_rows30_steps<<<grid, 128>>>(big, nwarps, K); });
+        printf(", \"rows30_cs_one_launch_8_steps_GBs\": %.0f", bytes * K / ms / 1e6);
+        ms = best_ms([&] { k_gridstride<<<grid, 128>>>(big, nvec * K); });
+        printf(", \"gridstride_8x_bytes_GBs\": %.0f", bytes * K / ms / 1e6);
+        ms = best_ms([&] { k_gridstride_v8<<<grid, 128>>>(big, nvec * K / 2); });
+        printf(", \"gridstride_v8_8x_bytes_GBs\": %.0f", bytes * K / ms / 1e6);
+        ms = best_ms([&] { CK(cudaMemsetAsync(big, 1, bytes * K)); });
+        printf(", \"memset_8x_bytes_GBs\": %.0f", bytes * K / ms / 1e6);
+        CK(cudaFree(big));
+    }
     printf("}\n");
     return 0;
 }

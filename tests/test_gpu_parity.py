@@ -901,3 +901,95 @@ def test_legal_move_counts_at_scale(D, oracle):
     assert (key[1:] > key[:-1]).all()
     uniq = torch.unique(torch.stack([owner, mv], 1), dim=0).shape[0]
     assert uniq == total                                                                         # duplicate-free lists
+
+
+@pytest.mark.parametrize("cls,variant,use_entropy", [("BatchedEnvCooperation", 2, False), ("BatchedEnv", 0, True),
+                                                     ("BatchedEnvComplicated", 1, False),
+                                                     ("BatchedEnvCooperationSimplify", 3, True)])
+def test_multi_step_launch_bit_exact(D, oracle, cls, variant, use_entropy):
+    """ddz_rollout_steps: K env-steps per native call == K single steps of the oracle, every slice of the trajectory
+    (lists, one-hots, face, results) and the final state, over several calls with re-deals."""
+    B, G, K, seed, launches = 2048 + 37, 4, 12, 77, 9
+    rng = np.random.default_rng(5)
+    perm, lord = D.random_deals(B, seed=15, pool_games=G)
+    perm_d, lord_d = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = getattr(D, cls)(B, seed=seed, env0=300, max_actions_per_env=128)
+    env.prepare(perm_d, lord_d, pool_games=G)
+    ref = oracle.RefBatch(B, variant)
+    ref.deal(perm, lord, pool_games=G)
+    traj = D.Trajectory(env, K)
+    t = 0
+    for it in range(launches):
+        ent = rng.integers(0, 1 << 31, (K, B)).astype(np.int32) if use_entropy else None
+        env.rollout_steps(traj, entropy=ent, perm=perm_d, lord_pile=lord_d, pool_games=G)
+        torch.cuda.synchronize()
+        offs = traj.offsets.cpu().numpy()
+        for s in range(K):
+            ref.observe(want_f32=False)                     # the oracle steps from its current lists
+            if use_entropy:
+                rr, rd, rc, rrew = ref.step(mode=1, choice=ent[s])
+            else:
+                rr, rd, rc, rrew = ref.step(mode=2, seed=seed, env0=300, step=t)
+            ref.deal(perm, lord, only_done=True, pool_games=G)
+            t += 1
+            off, au, af, face = ref.observe(want_f32=(s % 5 == 0))
+            n = int(off[B])
+            assert np.array_equal(offs[s], off), (it, s)
+            assert np.array_equal(traj.actions_u64[s, :n].cpu().numpy().view(np.uint64), au), (it, s)
+            assert np.array_equal(traj.face[s].cpu().numpy(), face), (it, s)
+            if s % 5 == 0:
+                assert np.array_equal(traj.actions_f32[s, :n].cpu().numpy(), af), (it, s)
+            assert np.array_equal(traj.r[s].cpu().numpy(), rr) and np.array_equal(traj.done[s].cpu().numpy(), rd), (it, s)
+            assert np.array_equal(traj.cat[s].cpu().numpy(), rc) and np.array_equal(traj.reward[s].cpu().numpy(), rrew), (it, s)
+        _compare_state(env, ref, t)
+    stats = env.stats.cpu().numpy()
+    assert stats[7] == 0 and np.array_equal(stats[[0, 1, 2, 3, 4, 5, 6, 9]], ref.stats[[0, 1, 2, 3, 4, 5, 6, 9]])
+    # the env carries on with the single-step API from where the launch left it
+    n = _compare_observation(env, ref, t)
+    assert n > 0
+    env.rollout_step(mode=D.native.CHOICE_PHILOX, perm=perm_d, lord_pile=lord_d, pool_games=G)
+    ref.step(mode=2, seed=seed, env0=300, step=t)
+    ref.deal(perm, lord, only_done=True, pool_games=G)
+    _compare_observation(env, ref, t + 1)
+
+
+def test_multi_step_launch_equals_playout(D, oracle):
+    """40 steps per call without re-deal (finished envs stay finished): final state + counters equal a playout of the
+    same Philox stream."""
+    B, K = 4800, 40
+    perm, lord = D.random_deals(B, seed=3)
+    a = D.BatchedEnv(B, seed=9, max_actions_per_env=128)
+    b = D.BatchedEnv(B, seed=9)
+    for e in (a, b):
+        e.prepare(perm, lord)
+    traj = D.Trajectory(a, K)
+    a.rollout_steps(traj)
+    b.playout(K)
+    torch.cuda.synchronize()
+    fa, ma = a._fields(); fb, mb = b._fields()
+    assert torch.equal(fa, fb) and torch.equal(ma, mb)
+    sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
+    assert sa[7] == 0 and np.array_equal(sa[[0, 1, 2, 3, 4, 5, 6, 9]], sb[[0, 1, 2, 3, 4, 5, 6, 9]])
+    # the last slice is the observation of the final state
+    a.observe()
+    assert torch.equal(traj.offsets[K - 1], a.offsets)
+    n = int(a.offsets[B].item())
+    assert torch.equal(traj.actions_u64[K - 1, :n], a.actions_packed) and torch.equal(traj.face[K - 1], a.face)
+
+
+def test_overflowing_lists_are_safe(D):
+    """cap smaller than the total: the tail is dropped, stats[7] says so, and a fused step whose choice falls into the
+    dropped part is an illegal choice (sticky error bit) -- never an out-of-bounds read."""
+    B = 8192
+    perm, lord = D.random_deals(B, seed=21)
+    env = D.BatchedEnvCooperation(B, seed=2, max_actions_per_env=8)        # 20-card leads have far more than 8 moves
+    env.prepare(perm, lord)
+    env.observe()
+    torch.cuda.synchronize()
+    assert int(env.stats[7].item()) >= 1 and int(env.offsets[B].item()) > env.cap
+    for _ in range(6):
+        env.rollout_step()
+    torch.cuda.synchronize()
+    meta = env._fields()[1].cpu().numpy().view(np.uint32)
+    assert ((meta >> 5) & 1).sum() > 0                                      # envs whose move was in the dropped tail
+    assert int(env.stats[4].item()) > 0                                     # the others played on
