@@ -56,6 +56,10 @@ constexpr int kMinCtasPerSm = 28 / kWarpsPerCta;  // 28 warps per SM (one wave a
 #ifndef DDZ_LOOKBACK
 #define DDZ_LOOKBACK 4
 #endif
+#ifndef DDZ_TILE_ENVS
+#define DDZ_TILE_ENVS 32
+#endif
+constexpr int kTile = DDZ_TILE_ENVS;                     // envs per warp tile (lane <-> env for lanes < kTile)
 constexpr int kRowUnroll = DDZ_ROW_UNROLL;               // row-writer iterations in flight per lane
 constexpr int kHeavy = DDZ_HEAVY;                       // envs with more legal moves than this are expanded by the whole warp
 constexpr int kLookBack = DDZ_LOOKBACK;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
@@ -65,7 +69,7 @@ enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
 // workspace: header (ticket, finished, epoch) + one look-back word per warp tile.  Must be zero when first used.
 struct WsHeader { unsigned int ticket, finished, epoch, auto_step; };
 struct Workspace { WsHeader* h; unsigned long long* tile; };
-static inline int ntiles(int B) { return (B + 31) / 32; }
+static inline int ntiles(int B) { return (B + kTile - 1) / kTile; }
 static inline int nblocks(int B) { return (B + kEnvs - 1) / kEnvs; }
 static inline Workspace ws_of(void* p) {
     Workspace w; w.h = (WsHeader*)p; w.tile = (unsigned long long*)((char*)p + 256);
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[wib];
     const RowLane rl = RowLane::make(lane);
-    const int nt = (B + 31) / 32;
+    const int nt = (B + kTile - 1) / kTile;
     const unsigned int nwarps = gridDim.x * kWarpsPerCta;
 
     // ---- 1. tile ticket: tiles are handed out in start order, so every lower tile is already running
@@ -283,9 +287,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         __syncwarp();
     }
     if (t < nt) {
-    const int b0 = t * 32, b = b0 + lane;
-    const bool valid = b < B;
-    const int nenv = min(32, B - b0);
+    const int b0 = t * kTile, b = b0 + lane;
+    const bool valid = lane < kTile && b < B;
+    const int nenv = min(kTile, B - b0);
     trace(t, 0);
 
     // ---- 2. state transition

@@ -993,3 +993,36 @@ def test_overflowing_lists_are_safe(D):
     meta = env._fields()[1].cpu().numpy().view(np.uint32)
     assert ((meta >> 5) & 1).sum() > 0                                      # envs whose move was in the dropped tail
     assert int(env.stats[4].item()) > 0                                     # the others played on
+
+
+def test_batched_game_trains_and_competes(D):
+    """BatchedGame / BatchedDQN (game.py:10-275, dqn.py:10-80 over a batched env): counters agree with the env's own,
+    transitions reach the replay buffer, TD steps run, schedules tick; compete() plays the trained net greedily."""
+    from qnet_like import QNetLike
+    net = lambda: QNetLike(9, width=16)
+    roles = {"lord": net, "down": net, "up": None}
+    dqns = {"lord": D.BatchedDQN, "down": D.BatchedDQN, "up": None}
+    torch.manual_seed(0)
+    game = D.BatchedGame(D.BatchedEnvCooperation, roles, dqns, reward_dict={"lord": 100, "down": 50, "up": 50},
+                         train_dict={"lord": True, "down": True, "up": False}, seed=3, num_envs=512)
+    hist = game.train(1200, log_every=400)
+    st = game.env.stats.cpu().numpy()
+    assert game.episodes >= 1200 and game.episodes == st[0] and st[7] == 0
+    assert (game.lord_total_wins, game.down_total_wins, game.up_total_wins) == (st[1], st[2], st[3])
+    assert len(hist) >= 2 and abs(sum(hist[-1][r]["total_win"] for r in ("up", "lord", "down")) - 1.0) < 1e-9
+    for role in ("lord", "down"):
+        agent = getattr(game, role)
+        assert len(agent.replay_buffer) > agent.batch_size and agent.epsilon < 0.5
+        rb = agent.replay_buffer
+        n = len(rb)
+        term = rb.done[:n, 0] == 1
+        assert term.any() and (~term).any()
+        want = 100.0 if role == "lord" else 50.0
+        assert (rb.r[:n, 0][term].abs() == want).all() and (rb.r[:n, 0][~term] == 0).all()
+        assert (rb.a1[:n][term] == 0).all()                                   # game.py:123-124: a1 = zeros at the end
+        assert (rb.a0[:n].flatten(1).sum(1) >= 0).all() and rb.s0[:n].isfinite().all()
+    assert any(h["lord"]["mean_loss"] > 0 for h in hist)
+    wins = D.BatchedGame.compete(D.BatchedEnvCooperation, {"lord": net, "down": None, "up": None},
+                                 {"lord": D.BatchedDQN, "down": None, "up": None}, None, total=500, debug=False,
+                                 num_envs=256, seed=5, nets={"lord": game.lord.policy_net})
+    assert sum(wins.values()) >= 500 and wins["lord"] > 0
