@@ -801,8 +801,31 @@ class _RoleDict:
 class Env(BatchedEnv):
     """Single-env drop-in for reference envi.Env: same attribute names, shapes and return types."""
 
+    CARD_NAMES = dict(zip(range(3, 18), [str(i) for i in range(3, 11)] + ["J", "Q", "K", "A", "2", "小", "大"]))   # config.py:16-18
+
     def __init__(self, debug=False, seed=None, device=None):
+        self.old_cards = dict()                      # role -> hand before its latest move (envi.py:27, 65)
+        self.verbose = bool(debug)                   # envi.py:44-61 narrates every move when debug=True
         super().__init__(1, debug=debug, seed=seed, device=device)
+
+    def reset(self):
+        self.old_cards = dict()
+        return super().reset()
+
+    @classmethod
+    def cards2str(cls, cards):
+        """envi.py:159-161"""
+        return [cls.CARD_NAMES[int(i)] for i in cards]
+
+    def _note_move(self, role, before):
+        """the bookkeeping of envi.py:38-61 that is visible from outside: old_cards, and the narration of debug mode
+        (without the reference's blocking input() prompts)"""
+        self.old_cards[role] = before
+        if self.verbose:
+            name, char = (("上家", "$"), ("地主", "#"), ("下家", "$"))[role]
+            played = self.arr2cards(self._recent_t()[0, role].cpu().numpy())
+            print("\n%s %s手牌: %s" % (char, name, self.cards2str(before)))
+            print("%s %s出牌： %s，分别剩余： %s" % (char, name, self.cards2str(played), self.left))
 
     @property
     def face(self):
@@ -814,13 +837,17 @@ class Env(BatchedEnv):
         return super().valid_actions(False)[0]
 
     def step_manual(self, onehot_cards):
+        role, before = self.get_role_ID() - 1, self.get_curr_handcards()
         r, done, cat = super().step_manual(torch.as_tensor(onehot_cards, device=self.device).reshape(1, 15, 4))
+        self._note_move(role, before)
         return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
 
     def step_random(self, entropy=None):
+        role, before = self.get_role_ID() - 1, self.get_curr_handcards()
         if entropy is not None:
             entropy = np.asarray([entropy], dtype=np.uint32)
         r, done, cat = super().step_random(entropy)
+        self._note_move(role, before)
         return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
 
     def get_role_ID(self):

@@ -1026,3 +1026,23 @@ def test_batched_game_trains_and_competes(D):
                                  {"lord": D.BatchedDQN, "down": None, "up": None}, None, total=500, debug=False,
                                  num_envs=256, seed=5, nets={"lord": game.lord.policy_net})
     assert sum(wins.values()) >= 500 and wins["lord"] > 0
+
+
+def test_single_env_view_bookkeeping(D, capsys):
+    """envi.py:27,38-61,159-161: old_cards, cards2str and the debug narration of the B = 1 view."""
+    env = D.EnvCooperation(debug=True)
+    env.reset()
+    env.prepare()
+    assert env.cards2str([3, 10, 11, 15, 16, 17]) == ["3", "10", "J", "2", "小", "大"]
+    hand = list(env.get_curr_handcards())
+    acts = env.valid_actions()
+    r, done, cat = env.step_manual(acts[0])
+    assert list(env.old_cards[1]) == hand and len(hand) == 20          # the landlord moved first
+    played = env.onehot2arr(acts[0])
+    assert env.left[1] == 20 - int(np.sum(played))
+    out = capsys.readouterr().out
+    assert "地主出牌" in out and "分别剩余" in out
+    env.step_random()
+    assert 2 in env.old_cards and len(env.old_cards[2]) == 17
+    env.reset()
+    assert env.old_cards == {}
