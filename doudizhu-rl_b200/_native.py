@@ -20,7 +20,16 @@ if not os.path.exists(LIB_PATH):
         "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(nvcc, sm_100a). The batched env has no CPU fallback." % LIB_PATH)
 
+EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
+           "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
+           "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
+           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_rollout_steps", "ddz_encode_state_actions")
+
 lib = C.CDLL(LIB_PATH)
+_missing = [name for name in EXPORTS if not hasattr(lib, name)]
+if _missing:
+    raise ImportError("%s is older than include/ddz_b200.h (no %s): rebuild it with "
+                      "`python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, ", ".join(_missing)))
 _vp, _i, _i64, _u64, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32
 
 lib.ddz_abi_version.restype = _i
@@ -49,12 +58,8 @@ lib.ddz_pipe_step.argtypes = [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _u64, _u64,
                               _vp, _vp, C.c_size_t, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]
 lib.ddz_pipe_wait.argtypes = [_vp, _i]
 lib.ddz_pipe_refill.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.ddz_encode_state_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.ddz_select_actions.argtypes = [_vp, _vp, C.c_float, _u64, _u64, _u32, _vp, _i, _vp]
-
-EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
-           "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
-           "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
-           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_rollout_steps")
 
 if lib.ddz_abi_version() != ABI_VERSION:
     raise ImportError("libddz_b200.so ABI %d != binding %d: rebuild" % (lib.ddz_abi_version(), ABI_VERSION))

@@ -4,7 +4,9 @@ Reference: DQNFirst.greedy_action / e_greedy_action (dqn.py:50-71) score the leg
 `net(face, actions)` (net.py:81-102, which accepts a pre-batched face [N,C,15,4]) and take the argmax (or, with
 probability epsilon, a uniform random move).  Here the same is done for all B envs at once: the network runs over the
 CSR action list in chunks, and a hand-written kernel (ddz_select_actions) does the segmented argmax / epsilon draw.
-The network itself is the caller's torch module -- the consumer contract, not part of this library.
+The network itself is the caller's torch module -- the consumer contract, not part of this library.  A network that
+exposes `forward_state_action(x)` for the already concatenated input x [n, C+1, 15, 4] (what net.py:90 builds with
+`face.repeat` + `torch.cat`) gets that tensor written directly by ddz_encode_state_actions.
 """
 import torch
 
@@ -19,6 +21,17 @@ class BatchedGreedyPolicy:
     def q_values(self, env, env_mask=None):
         """float32 [sumN]: Q(face[env of move i], move i) for every legal move of every env.  env_mask (bool [B]): score
         only the moves of those envs (e.g. the ones where it is the learning role's turn); the others get 0."""
+        if hasattr(self.net, "forward_state_action") and hasattr(env, "state_actions"):
+            # the network takes the concatenated [n, C+1, 15, 4] input: one kernel writes it in place (no gather, no cat)
+            x, rows = env.state_actions(env_mask)
+            q = torch.zeros(env.num_actions, dtype=torch.float32, device=x.device)
+            for lo in range(0, x.shape[0], self.chunk):
+                out = self.net.forward_state_action(x[lo:lo + self.chunk]).reshape(-1).to(torch.float32)
+                if rows is None:
+                    q[lo:lo + out.numel()] = out
+                else:
+                    q[rows[lo:lo + out.numel()]] = out
+            return q
         face = env.face
         actions, offsets = env.valid_actions()
         n = actions.shape[0]

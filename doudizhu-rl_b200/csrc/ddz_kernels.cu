@@ -533,6 +533,50 @@ __global__ void __launch_bounds__(kEnvs) k_face(const void* state, float4* __res
     }
 }
 
+// The Q-network's input built in place (net.py:81-90: face repeated per action, torch.cat with the action plane): for every
+// legal move i of env b, out[dst + i] = [C face rows of env b | the move's one-hot row], 240 x (C+1) bytes.  One warp per
+// env: the face planes are computed once and every row goes out through the same two-rows-per-instruction writer.
+template <int V>
+__global__ void __launch_bounds__(128) k_state_actions(const void* state, const int32_t* __restrict__ offsets,
+                                                       const uint64_t* __restrict__ actions,
+                                                       const uint8_t* __restrict__ env_mask,
+                                                       const int32_t* __restrict__ dst_offsets,
+                                                       float4* __restrict__ out, int B) {
+    constexpr int C = FaceCfg<V>::C;
+    __shared__ FaceRow s_face[4][C];
+    __shared__ float4 s_lut[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int b = blockIdx.x * 4 + wib;
+    if (threadIdx.x < 5) s_lut[threadIdx.x] = make_float4(threadIdx.x > 0 ? 1.f : 0.f, threadIdx.x > 1 ? 1.f : 0.f,
+                                                          threadIdx.x > 2 ? 1.f : 0.f, threadIdx.x > 3 ? 1.f : 0.f);
+    const bool live = b < B && (!env_mask || env_mask[b]);
+    int src = 0, n = 0;
+    if (live) { src = offsets[b]; n = offsets[b + 1] - src; }
+    if (live && n > 0 && lane == 0) {
+        const Env e = load_env(view_of(const_cast<void*>(state), B), b);
+        uint64_t pl[C]; float p[2];
+        face_planes<V>(e, pl, p);
+#pragma unroll
+        for (int c = 0; c < C; c++) { s_face[wib][c].packed = pl[c]; s_face[wib][c].s = (c >= C - 2) ? p[c - (C - 2)] : 1.f; s_face[wib][c].pad = 0.f; }
+    }
+    __syncthreads();
+    if (!live || n <= 0) return;
+    const RowLane rl = RowLane::make(lane);
+    const long long dst = dst_offsets ? dst_offsets[b] : src;
+    float4* o = out + (size_t)dst * (C + 1) * 15 + (rl.first & 1) * 15 + rl.k;
+    const int nrows = n * (C + 1);
+#pragma unroll 2
+    for (int r = rl.first; r < nrows; r += 2, o += 30) {
+        const int m = r / (C + 1), c = r - m * (C + 1);
+        uint64_t packed; float sc = 1.f;
+        if (c < C) { packed = s_face[wib][c].packed; sc = s_face[wib][c].s; }
+        else packed = __ldg(&actions[src + m]);
+        float4 q = rl.thermo(packed, s_lut);
+        q.x *= sc; q.y *= sc; q.z *= sc; q.w *= sc;
+        DDZ_STORE(o, q);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restrict__ actions, long long n,
                                                         float4* __restrict__ out) {
     long long nvec = n * 15;
@@ -881,6 +925,22 @@ int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void*
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_encode_actions<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(actions_u64, n, (float4*)out);
     DDZ_LAUNCH_CHECK("k_encode_actions");
+    return 0;
+}
+
+int ddz_encode_state_actions(const void* state, int variant, const int32_t* offsets, const uint64_t* actions_u64,
+                             const uint8_t* env_mask, const int32_t* dst_offsets, float* out, int B, void* stream) {
+    if (!state || !offsets || !actions_u64 || !out || B <= 0) return DDZ_E_ARG;
+    const int grid = (B + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+        case 0: k_state_actions<0><<<grid, 128, 0, st>>>(state, offsets, actions_u64, env_mask, dst_offsets, (float4*)out, B); break;
+        case 1: k_state_actions<1><<<grid, 128, 0, st>>>(state, offsets, actions_u64, env_mask, dst_offsets, (float4*)out, B); break;
+        case 2: k_state_actions<2><<<grid, 128, 0, st>>>(state, offsets, actions_u64, env_mask, dst_offsets, (float4*)out, B); break;
+        case 3: k_state_actions<3><<<grid, 128, 0, st>>>(state, offsets, actions_u64, env_mask, dst_offsets, (float4*)out, B); break;
+        default: return DDZ_E_ARG;
+    }
+    DDZ_LAUNCH_CHECK("k_state_actions");
     return 0;
 }
 

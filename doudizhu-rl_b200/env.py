@@ -262,6 +262,32 @@ class BatchedEnv:
         off = self._offsets[self._cur].cpu().numpy()
         return [[[int(x) for x in row] for row in counts[off[b]:off[b + 1]]] for b in range(self.B)]
 
+    def state_actions(self, env_mask=None):
+        """The Q-network's input for every legal move, written in place (net.py:81-90 without `face.repeat` and
+        `torch.cat`): float32 [n, C+1, 15, 4], row i = [face of the move's env | the move's one-hot].  env_mask bool [B]:
+        only the moves of those envs, packed in env order.  Returns (x, rows) with rows = indices of the encoded moves in
+        the CSR action list (None when every move is encoded)."""
+        self._ensure()
+        off = self._offsets[self._cur]
+        if env_mask is None:
+            n, dst, rows, mask8 = self.num_actions, None, None, None
+        else:
+            mask = env_mask.to(self.device, torch.bool)
+            cnt = (off[1:] - off[:-1]) * mask
+            dst = torch.zeros(self.B + 1, dtype=torch.int32, device=self.device)
+            dst[1:] = torch.cumsum(cnt, 0)
+            n = int(dst[-1].item())
+            owner_mask = torch.repeat_interleave(mask, (off[1:] - off[:-1]).to(torch.int64), output_size=self.num_actions)
+            rows = owner_mask.nonzero(as_tuple=True)[0]
+            mask8 = mask.to(torch.uint8)
+        x = torch.empty((n, self.C + 1, 15, 4), dtype=torch.float32, device=self.device)
+        if n:
+            with torch.cuda.device(self.device):
+                N.check(N.lib.ddz_encode_state_actions(self._p(self._state), self.VARIANT, self._p(off),
+                                                       self._p(self._actions_u64[self._cur]), self._p(mask8), self._p(dst),
+                                                       x.data_ptr(), self.B, self._stream()), "ddz_encode_state_actions")
+        return x, rows
+
     def _step(self, choice, mode):
         self._ensure()
         with torch.cuda.device(self.device):

@@ -145,6 +145,14 @@ int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32
 /* Env.batch_arr2onehot over packed moves (envi.py:113,140-146): out float32[n][15][4] */
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream);
 
+/* The Q-network's input for every legal move, built in place (net.py:81-90 repeats the face per action and torch.cat's the
+ * action plane on): out float32 [n][C+1][15][4], row dst + i = [face of env b (C planes) | one-hot of move i of env b].
+ * offsets / actions_u64: the lists of the CURRENT state (ddz_observe / ddz_rollout_step).  env_mask uint8[B] (or NULL):
+ * only envs with a non-zero entry are written (e.g. the envs where the learning seat is to move); dst_offsets int32[B+1]
+ * (or NULL = offsets): first output row of each env, e.g. the exclusive prefix sum of the selected envs' move counts. */
+int ddz_encode_state_actions(const void* state, int variant, const int32_t* offsets, const uint64_t* actions_u64,
+                             const uint8_t* env_mask, const int32_t* dst_offsets, float* out, int B, void* stream);
+
 /* Batched DQNFirst.greedy_action / e_greedy_action (dqn.py:50-71): q float32[offsets[B]] are the Q-values the caller's
  * network gave to the legal moves (CSR order).  choice[b] = index of the first maximum of env b's segment (torch.argmax
  * semantics), or, with probability epsilon, a uniformly random index (Philox keyed by seed, env0+b, stepno); -1 for an

@@ -20,10 +20,25 @@ import ddz_b200 as D
 from qnet_like import QNetLike
 
 
-def main():
+class Autocast(torch.nn.Module):
+    """the same network under torch.autocast (bf16 tensor cores) -- a consumer-side choice, reported separately"""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward_state_action(self, x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return self.inner.forward_state_action(x).float()
+
+
+def main(precision="fp32"):
     B, P, steps, warm = 65536, 8, 20, 60
     torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = (precision == "tf32")
     net = QNetLike(9, width=256).cuda().eval()
+    if precision == "bf16":
+        net = Autocast(net)
     policy = D.BatchedGreedyPolicy(net, chunk_actions=1 << 16)
     perm, lord = D.random_deals(B, seed=11, pool_games=P)
     pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
@@ -56,7 +71,7 @@ def main():
     net_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / steps
     env_ms = sum(b.elapsed_time(c) for _, b, c in evs) / steps
     st = env.stats.cpu().numpy()
-    print(json.dumps({"workload": "config 3: %d envs, lord = argmax Q (NetCooperation-shaped random-init net, fp32), farmers random" % B,
+    print(json.dumps({"workload": "config 3: %d envs, lord = argmax Q (NetCooperation-shaped random-init net, %s), farmers random" % (B, precision),
                       "env_steps_per_s": B / ((net_ms + env_ms) * 1e-3), "ms_per_step": net_ms + env_ms,
                       "network_and_selection_ms": net_ms, "env_kernel_ms": env_ms,
                       "actions_scored_per_step": int(env.num_actions), "lord_win_rate": float(st[1]) / max(1, st[0]),
@@ -64,4 +79,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "fp32")

@@ -19,7 +19,10 @@ class QNetLike(nn.Module):
     def forward(self, face, actions):
         if face.dim() == 3:
             face = face.unsqueeze(0).repeat((actions.shape[0], 1, 1, 1))
-        x = torch.cat((face, actions.unsqueeze(1)), dim=1)
+        return self.forward_state_action(torch.cat((face, actions.unsqueeze(1)), dim=1))
+
+    def forward_state_action(self, x):
+        """x [N, C+1, 15, 4]: the concatenated state-action input (net.py:90)"""
         r = torch.cat([c(x) for c in self.rank_convs], -1).max(-1).values.flatten(1)      # [N, width*15]
         l = self.line_conv(x).flatten(1)                                                  # [N, width*4]
         return self.fc2(F.relu(self.fc1(torch.cat([r, l], -1))))

@@ -1046,3 +1046,42 @@ def test_single_env_view_bookkeeping(D, capsys):
     assert 2 in env.old_cards and len(env.old_cards[2]) == 17
     env.reset()
     assert env.old_cards == {}
+
+
+@pytest.mark.parametrize("cls", ["BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify"])
+def test_state_action_encoder(D, cls):
+    """ddz_encode_state_actions == torch.cat((face.repeat per action, action), 1) of net.py:81-90, bit for bit, for all
+    moves and for the moves of a subset of envs; the Q-scoring shim gives the same values through either input form."""
+    from qnet_like import QNetLike
+    B = 3000
+    perm, lord = D.random_deals(B, seed=31)
+    env = getattr(D, cls)(B, seed=4)
+    env.prepare(perm, lord)
+    for _ in range(25):
+        env.rollout_step()
+    face = env.face
+    acts, offs = env.valid_actions()
+    cnt = (offs[1:] - offs[:-1]).to(torch.int64)
+    owner = torch.repeat_interleave(torch.arange(B, device="cuda"), cnt)
+    want = torch.cat((face[owner], acts.unsqueeze(1)), dim=1)
+    x, rows = env.state_actions()
+    assert rows is None and torch.equal(x, want)
+    mask = (env.get_role_ID() == 2) | (torch.arange(B, device="cuda") % 7 == 0)
+    xs, rows = env.state_actions(mask)
+    assert torch.equal(rows, mask[owner].nonzero(as_tuple=True)[0]) and torch.equal(xs, want[rows])
+    none = torch.zeros(B, dtype=torch.bool, device="cuda")
+    assert env.state_actions(none)[0].shape[0] == 0
+    torch.manual_seed(1)
+    net = QNetLike(env.C, width=8).cuda().eval()
+
+    class TwoInput(torch.nn.Module):                      # the same network without the concatenated entry point
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, face, actions):
+            return self.inner(face, actions)
+
+    qa = D.BatchedGreedyPolicy(net, chunk_actions=4096).q_values(env, mask)
+    qb = D.BatchedGreedyPolicy(TwoInput(net), chunk_actions=4096).q_values(env, mask)
+    assert torch.equal(qa, qb)
