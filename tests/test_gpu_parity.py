@@ -1085,3 +1085,16 @@ def test_state_action_encoder(D, cls):
     qa = D.BatchedGreedyPolicy(net, chunk_actions=4096).q_values(env, mask)
     qb = D.BatchedGreedyPolicy(TwoInput(net), chunk_actions=4096).q_values(env, mask)
     assert torch.equal(qa, qb)
+
+
+def test_mcts_entry_point(D):
+    """mcts(payload) (server/mcts/interface.py:15-45): the search bot's wire format in, a move as card values out."""
+    payload = {"role_id": 1,
+               "hand_card": {0: [13, 14, 14, 15], 1: [3, 4, 5, 6, 7], 2: [8, 8, 9, 9]},
+               "last_taken": {0: [], 1: [], 2: []}}
+    assert D.mcts(payload, computation_budget=600) == [3, 4, 5, 6, 7]       # the straight wins on the spot
+    # following a pair of 9s with 10 10 J in hand against opponents that are one move from going out: play the 10s
+    payload = {"role_id": "2", "hand_card": {"0": [3], "1": [4], "2": [10, 10, 11]},
+               "last_taken": {"0": [], "1": [9, 9], "2": []}}
+    payload["role_id"] = 2
+    assert D.mcts(payload, computation_budget=2000, seed=3) == [10, 10]
