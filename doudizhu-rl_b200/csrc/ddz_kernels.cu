@@ -432,7 +432,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 sr.lead = rpack & 1; sr.cat = (rpack >> 1) & 127; sr.len = (rpack >> 8) & 255; sr.val = (rpack >> 16) & 255;
                 const int loc = __shfl_sync(FULL, local, src), nn = __shfl_sync(FULL, n, src);
                 WindowEmitter em{wbuf, loc - w0, win};
-                disagree |= (enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em) != nn);
+                const int got = (MODE == kRaw) ? enumerate_legal_warp_long(sm_, sr, (rpack >> 24) & 1, lane, em)   // long lists
+                                               : enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em);
+                disagree |= (got != nn);
             }
             __syncwarp();
             if (w0 == 0) trace(t, 7);
