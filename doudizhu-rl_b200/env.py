@@ -821,21 +821,24 @@ class _RoleDict:
         self._fn = fn
 
     def __getitem__(self, role):
-        return self._fn()[0, int(role)].cpu().numpy().astype(np.float64)
+        return np.asarray(self._fn()[int(role)], dtype=np.float64)
 
 
 class Env(BatchedEnv):
     """Single-env drop-in for reference envi.Env: same attribute names, shapes and return types."""
 
+    _NIBBLE_SHIFTS = (4 * np.arange(15, dtype=np.uint64))[None, :]
     CARD_NAMES = dict(zip(range(3, 18), [str(i) for i in range(3, 11)] + ["J", "Q", "K", "A", "2", "小", "大"]))   # config.py:16-18
 
     def __init__(self, debug=False, seed=None, device=None):
         self.old_cards = dict()                      # role -> hand before its latest move (envi.py:27, 65)
+        self._snap_key, self._snap_val = None, None
         self.verbose = bool(debug)                   # envi.py:44-61 narrates every move when debug=True
         super().__init__(1, debug=debug, seed=seed, device=device)
 
     def reset(self):
         self.old_cards = dict()
+        self._snap_val = None
         return super().reset()
 
     @classmethod
@@ -849,7 +852,7 @@ class Env(BatchedEnv):
         self.old_cards[role] = before
         if self.verbose:
             name, char = (("上家", "$"), ("地主", "#"), ("下家", "$"))[role]
-            played = self.arr2cards(self._recent_t()[0, role].cpu().numpy())
+            played = self.arr2cards(self._snap()["recent"][role])
             print("\n%s %s手牌: %s" % (char, name, self.cards2str(before)))
             print("%s %s出牌： %s，分别剩余： %s" % (char, name, self.cards2str(played), self.left))
 
@@ -862,45 +865,75 @@ class Env(BatchedEnv):
             return super().valid_actions(True)[0]
         return super().valid_actions(False)[0]
 
+    # One 80-byte D2H per state serves every getter of the reference API (role, hands, hand-outs, history, left): the
+    # single-env loop of game.py asks for several of them per decision, and each would otherwise be its own sync.
+    def _snap(self):
+        key = (self._stepno, self._games_dealt, self._cur, self._fresh)
+        if self._snap_key != key or self._snap_val is None:
+            host = self._state.cpu().numpy()                 # B = 1: nine uint64 fields + the meta word = 76 bytes
+            cnt = ((host[:18].view(np.uint64)[:, None] >> self._NIBBLE_SHIFTS) & 15).astype(np.int64)
+            m = int(host[18]) & 0xFFFFFFFF
+            self._snap_val = {"hand": cnt[0:3], "hist": cnt[3:6], "recent": cnt[6:9], "role": m & 3,
+                              "done": bool((m >> 2) & 1), "winner": (m >> 3) & 3}
+            self._snap_key = key
+        return self._snap_val
+
+    def _results_host(self):
+        """(r, done, cat) of the latest step with one D2H (the three lie next to each other in the results buffer)"""
+        b = self._results[self._res].buf[:3].cpu().numpy()
+        return int(b[0:1].view(np.int8)[0]), bool(b[1]), int(b[2:3].view(np.int8)[0])
+
     def step_manual(self, onehot_cards):
         role, before = self.get_role_ID() - 1, self.get_curr_handcards()
-        r, done, cat = super().step_manual(torch.as_tensor(onehot_cards, device=self.device).reshape(1, 15, 4))
+        super().step_manual(torch.as_tensor(onehot_cards, device=self.device).reshape(1, 15, 4))
+        self._snap_val = None
         self._note_move(role, before)
-        return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
+        return self._results_host()
 
     def step_random(self, entropy=None):
         role, before = self.get_role_ID() - 1, self.get_curr_handcards()
         if entropy is not None:
             entropy = np.asarray([entropy], dtype=np.uint32)
-        r, done, cat = super().step_random(entropy)
+        super().step_random(entropy)
+        self._snap_val = None
         self._note_move(role, before)
-        return int(r[0].item()), bool(done[0].item()), int(cat[0].item())
+        return self._results_host()
+
+    def prepare(self, *args, **kw):
+        self._snap_val = None
+        return super().prepare(*args, **kw)
+
+    def load_state_dict(self, sd):
+        self._snap_val = None
+        return super().load_state_dict(sd)
 
     def get_role_ID(self):
-        return int(super().get_role_ID()[0].item())
+        return self._snap()["role"] + 1
 
     def get_curr_handcards(self):
-        return self.arr2cards(super().get_curr_handcards()[0].cpu().numpy())
+        sn = self._snap()
+        return self.arr2cards(sn["hand"][sn["role"]])
 
     def get_last_two_cards(self):
-        two = super().get_last_two_cards()[0].cpu().numpy()
-        return [list(self.arr2cards(two[0])), list(self.arr2cards(two[1]))]
+        sn = self._snap()
+        s = sn["role"]
+        return [list(self.arr2cards(sn["recent"][(s + 2) % 3])), list(self.arr2cards(sn["recent"][(s + 1) % 3]))]
 
     @property
     def left(self):
-        return BatchedEnv.left.fget(self)[0].cpu().numpy()
+        return self._snap()["hand"].sum(-1)
 
     @property
     def taken(self):
-        return BatchedEnv.taken.fget(self)[0].cpu().numpy().astype(np.float64)
+        return self._snap()["hist"].sum(0).astype(np.float64)
 
     @property
     def history(self):
-        return _RoleDict(self._history_t)
+        return _RoleDict(lambda: self._snap()["hist"])
 
     @property
     def recent_handout(self):
-        return _RoleDict(self._recent_t)
+        return _RoleDict(lambda: self._snap()["recent"])
 
 
 class EnvComplicated(Env):
