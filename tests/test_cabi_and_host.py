@@ -110,3 +110,51 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 1e5
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_replay_buffer_and_td_step_on_cpu():
+    """trainer.ReplayBuffer = bounded deque semantics (dqn.py:14); td_step = the reference's target and loss
+    (dqn.py:39-47); BatchedDQN schedules (dqn.py:73-80).  Pure torch host logic: runs without a GPU."""
+    import torch
+    import ddz_b200 as D
+    rb = D.ReplayBuffer(5, 2, "cpu")
+    mk = lambda n, v: (torch.full((n, 2, 15, 4), float(v)), torch.full((n, 15, 4), float(v)), torch.full((n,), float(v)),
+                       torch.full((n, 2, 15, 4), float(v) + 0.5), torch.full((n, 15, 4), float(v) + 0.5), torch.zeros(n))
+    rb.append(*mk(3, 1))
+    assert len(rb) == 3
+    rb.append(*mk(4, 2))                                   # wraps: the two oldest entries are overwritten
+    assert len(rb) == 5 and sorted(rb.r[:, 0].tolist()) == [1.0, 2.0, 2.0, 2.0, 2.0]
+    rb.append(*mk(9, 3))                                   # more than the capacity at once: the last five survive
+    assert len(rb) == 5 and rb.r[:, 0].tolist() == [3.0] * 5
+    s0, a0, r, s1, a1, done = rb.sample(64, torch.Generator().manual_seed(0))
+    assert s0.shape == (64, 2, 15, 4) and r.shape == (64, 1) and done.shape == (64, 1)
+
+    class Q(torch.nn.Module):                              # Q(s, a) = w * (mean(s) + mean(a))
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(2.0))
+
+        def forward(self, face, actions):
+            return (self.w * (face.flatten(1).mean(1) + actions.flatten(1).mean(1))).unsqueeze(1)
+
+    pol, tgt = Q(), Q()
+    with torch.no_grad():
+        tgt.w.fill_(3.0)
+    opt = torch.optim.SGD(pol.parameters(), lr=0.0)
+    batch = (torch.ones(4, 2, 15, 4), torch.ones(4, 15, 4), torch.tensor([[0.], [0.], [100.], [-100.]]),
+             torch.ones(4, 2, 15, 4) * 2, torch.ones(4, 15, 4) * 2, torch.tensor([[0.], [0.], [1.], [1.]]))
+    loss = D.td_step(pol, tgt, opt, batch, gamma=0.95)
+    y = torch.tensor([0.95 * 12, 0.95 * 12, 100.0, -100.0])          # r + (1 - done) * gamma * Q_target(s1, a1)
+    assert torch.allclose(loss, ((torch.full((4,), 4.0) - y) ** 2).mean())
+
+    dqn = D.BatchedDQN(Q, 2, "cpu", replay_size=64, batch_size=8)
+    assert dqn.epsilon == 0.5 and dqn.perceive(*mk(4, 1)) is None     # fewer than a minibatch: no update yet
+    assert dqn.perceive(*mk(6, 2)) is not None and len(dqn.replay_buffer) == 10
+    dqn.update_epsilon(1066)
+    assert abs(dqn.epsilon - (0.01 + 0.49 * np.exp(-1.0))) < 1e-9      # config.py:9-10,13 + dqn.py:73-76
+    with torch.no_grad():
+        dqn.policy_net.w.fill_(7.0)
+    dqn.update_target(19)
+    assert float(dqn.target_net.w.detach()) != 7.0
+    dqn.update_target(20)
+    assert float(dqn.target_net.w.detach()) == 7.0
