@@ -299,18 +299,19 @@ def run_ours(args):
             pg, lg, _ = ge._pool[g]
             hosts.append(D.HostRollout(env, pg, lg, P))
     sink = [0]
-    pending = [[None, None] for _ in range(NG)]
+    DEPTH = D.native.PIPE_DEPTH                                   # the host reads step i's results while step i+3 is issued
+    pending = [[None] * DEPTH for _ in range(NG)]
 
     def e2e_step(i):
         for g in range(NG):                                       # each HostRollout issues on its group's stream
             if i % REFILL == 0:
                 pp, ll = pool_h[(i // REFILL) % 2]
                 hosts[g].refill((i // REFILL) % P, pp, ll)
-            old = pending[g][i & 1]
-            if old is not None:                                   # the host reads the results of step i-2
+            old = pending[g][i % DEPTH]
+            if old is not None:                                   # the host reads the results of step i-DEPTH
                 D.HostRollout.wait(old)
                 sink[0] += int(old.done_np[0]) + int(old.r_np[-1])
-            pending[g][i & 1] = hosts[g].step(ent_h[g][i % R])
+            pending[g][i % DEPTH] = hosts[g].step(ent_h[g][i % R])
 
     for i in range(max(W, 4)):
         e2e_step(i)
@@ -381,7 +382,7 @@ def run_ours(args):
             "e2e": {"value": B * e2e_K * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_K, "steps": e2e_K,
                     "api": "HostRollout.step(entropy_host) per env group (native ddz_pipe_step: H2D entropy -> k_env -> D2H "
-                           "r/done/cat -- the reference step's return tuple -- on copy streams), results of step t-2 read by the host every step, "
+                           "r/done/cat -- the reference step's return tuple -- on copy streams), results of step t-4 read by the host every step (ring of 4 pinned result buffers), "
                            "refill(slot, perm_host, lord_host) uploads host-made deals every %d steps" % REFILL},
             "gpu_launches": K * NG,
             "clocks": clocks,

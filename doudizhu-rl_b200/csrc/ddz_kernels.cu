@@ -825,10 +825,13 @@ int ddz_rollout_steps(void* state, void* workspace, int variant, int nsteps,
 
 // ---- host-buffer pipeline -------------------------------------------------------------------------
 struct ddz_pipe {
-    cudaStream_t h2d, d2h;
-    cudaEvent_t in_ready[2], in_free[2], kernel_done[2], out_done[2], stage_free, stage_full;
+    cudaStream_t h2d, d2h, refill;
+    cudaEvent_t in_ready[2], in_free[2], kernel_done[2], out_done[DDZ_PIPE_DEPTH], stage_free, stage_full;
     unsigned long long step;
     bool stage_used;
+    // a deal-pool upload that is on its way into the staging buffers: committed (device-to-device, between two steps) by
+    // the first ddz_pipe_step that finds it complete, so that no step ever waits for a large host copy
+    struct { int8_t *dst_perm, *dst_lord, *stage_perm, *stage_lord; size_t rows; bool active; } pending;
 };
 #define DDZ_CUDA(call, what)                                   \
     do {                                                       \
@@ -838,23 +841,38 @@ struct ddz_pipe {
 
 ddz_pipe* ddz_pipe_create(void) {
     ddz_pipe* p = new ddz_pipe();
-    p->step = 0; p->stage_used = false;
+    p->step = 0; p->stage_used = false; p->pending.active = false;
     bool ok = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->refill, cudaStreamNonBlocking) == cudaSuccess;
     cudaEvent_t* evs[] = {&p->in_ready[0], &p->in_ready[1], &p->in_free[0], &p->in_free[1], &p->kernel_done[0],
-                          &p->kernel_done[1], &p->out_done[0], &p->out_done[1], &p->stage_free, &p->stage_full};
+                          &p->kernel_done[1], &p->stage_free, &p->stage_full};
     for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    for (cudaEvent_t& e : p->out_done) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cuda_fail(cudaGetLastError(), "ddz_pipe_create"); delete p; return nullptr; }
     return p;
 }
 void ddz_pipe_destroy(ddz_pipe* p) {
     if (!p) return;
-    cudaStreamDestroy(p->h2d); cudaStreamDestroy(p->d2h);
+    cudaStreamDestroy(p->h2d); cudaStreamDestroy(p->d2h); cudaStreamDestroy(p->refill);
     cudaEvent_t evs[] = {p->in_ready[0], p->in_ready[1], p->in_free[0], p->in_free[1], p->kernel_done[0],
-                         p->kernel_done[1], p->out_done[0], p->out_done[1], p->stage_free, p->stage_full};
+                         p->kernel_done[1], p->stage_free, p->stage_full};
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->out_done) cudaEventDestroy(e);
     delete p;
 }
+// replace the pool slot by the staged upload (device-to-device on the main stream, i.e. between two steps)
+static int pipe_commit_refill(ddz_pipe* p, cudaStream_t main_s, bool wait) {
+    if (!p->pending.active) return 0;
+    if (!wait && cudaEventQuery(p->stage_full) != cudaSuccess) { cudaGetLastError(); return 0; }   // still uploading
+    DDZ_CUDA(cudaStreamWaitEvent(main_s, p->stage_full, 0), "wait stage_full");
+    DDZ_CUDA(cudaMemcpyAsync(p->pending.dst_perm, p->pending.stage_perm, p->pending.rows * 54, cudaMemcpyDeviceToDevice, main_s), "D2D perm");
+    DDZ_CUDA(cudaMemcpyAsync(p->pending.dst_lord, p->pending.stage_lord, p->pending.rows, cudaMemcpyDeviceToDevice, main_s), "D2D lord");
+    DDZ_CUDA(cudaEventRecord(p->stage_free, main_s), "record stage_free");
+    p->pending.active = false;
+    return 0;
+}
+
 int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
                   const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
                   const void* host_choice, void* dev_choice, uint64_t seed, uint64_t env0, uint32_t stepno,
@@ -865,6 +883,7 @@ int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
     if (!p || !host_choice || !dev_choice || !results_dev || !results_host || B <= 0) return DDZ_E_ARG;
     if (results_bytes < (size_t)B * 3) return DDZ_E_ARG;       // at least r | done | cat; the reward block is optional
     cudaStream_t main_s = (cudaStream_t)stream;
+    if (int rc = pipe_commit_refill(p, main_s, false)) return rc;
     const int k = (int)(p->step & 1);
     const bool primed = p->step >= 2;                          // events of this parity were recorded two steps ago
     // H2D of this step's entropy, once the kernel that last read dev_choice (two steps ago) is done
@@ -873,7 +892,7 @@ int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
     DDZ_CUDA(cudaEventRecord(p->in_ready[k], p->h2d), "record in_ready");
     DDZ_CUDA(cudaStreamWaitEvent(main_s, p->in_ready[k], 0), "wait in_ready");
     // results_dev alternates between two sets: the D2H that last read this set was issued two steps ago
-    if (primed) DDZ_CUDA(cudaStreamWaitEvent(main_s, p->out_done[k], 0), "wait out_done");
+    if (primed) DDZ_CUDA(cudaStreamWaitEvent(main_s, p->out_done[(p->step - 2) % DDZ_PIPE_DEPTH], 0), "wait out_done");
     char* rd = (char*)results_dev;
     const size_t off_reward = ((size_t)3 * B + 15) / 16 * 16;
     int rc = ddz_rollout_step(state, workspace, variant, prev_offsets, prev_actions_u64, dev_choice, DDZ_CHOICE_MOD, seed,
@@ -885,12 +904,12 @@ int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
     DDZ_CUDA(cudaEventRecord(p->in_free[k], main_s), "record in_free");
     DDZ_CUDA(cudaStreamWaitEvent(p->d2h, p->kernel_done[k], 0), "wait kernel_done");
     DDZ_CUDA(cudaMemcpyAsync(results_host, results_dev, results_bytes, cudaMemcpyDeviceToHost, p->d2h), "D2H results");
-    DDZ_CUDA(cudaEventRecord(p->out_done[k], p->d2h), "record out_done");
+    DDZ_CUDA(cudaEventRecord(p->out_done[p->step % DDZ_PIPE_DEPTH], p->d2h), "record out_done");
     p->step++;
     return 0;
 }
 int ddz_pipe_wait(ddz_pipe* p, int slot) {
-    if (!p || slot < 0 || slot > 1) return DDZ_E_ARG;
+    if (!p || slot < 0 || slot >= DDZ_PIPE_DEPTH) return DDZ_E_ARG;
     DDZ_CUDA(cudaEventSynchronize(p->out_done[slot]), "ddz_pipe_wait");
     return 0;
 }
@@ -899,16 +918,20 @@ int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot,
     if (!p || !pool_perm_slot || !pool_lord_slot || !host_perm || !host_lord || !stage_perm || !stage_lord || B <= 0)
         return DDZ_E_ARG;
     cudaStream_t main_s = (cudaStream_t)stream;
-    if (p->stage_used) DDZ_CUDA(cudaStreamWaitEvent(p->h2d, p->stage_free, 0), "wait stage_free");
-    DDZ_CUDA(cudaMemcpyAsync(stage_perm, host_perm, (size_t)B * 54, cudaMemcpyHostToDevice, p->h2d), "H2D perm");
-    DDZ_CUDA(cudaMemcpyAsync(stage_lord, host_lord, (size_t)B, cudaMemcpyHostToDevice, p->h2d), "H2D lord");
-    DDZ_CUDA(cudaEventRecord(p->stage_full, p->h2d), "record stage_full");
-    DDZ_CUDA(cudaStreamWaitEvent(main_s, p->stage_full, 0), "wait stage_full");
-    DDZ_CUDA(cudaMemcpyAsync(pool_perm_slot, stage_perm, (size_t)B * 54, cudaMemcpyDeviceToDevice, main_s), "D2D perm");
-    DDZ_CUDA(cudaMemcpyAsync(pool_lord_slot, stage_lord, (size_t)B, cudaMemcpyDeviceToDevice, main_s), "D2D lord");
-    DDZ_CUDA(cudaEventRecord(p->stage_free, main_s), "record stage_free");
+    if (int rc = pipe_commit_refill(p, main_s, true)) return rc;          // an earlier upload still staged: commit it first
+    if (p->stage_used) DDZ_CUDA(cudaStreamWaitEvent(p->refill, p->stage_free, 0), "wait stage_free");
+    DDZ_CUDA(cudaMemcpyAsync(stage_perm, host_perm, (size_t)B * 54, cudaMemcpyHostToDevice, p->refill), "H2D perm");
+    DDZ_CUDA(cudaMemcpyAsync(stage_lord, host_lord, (size_t)B, cudaMemcpyHostToDevice, p->refill), "H2D lord");
+    DDZ_CUDA(cudaEventRecord(p->stage_full, p->refill), "record stage_full");
+    p->pending.dst_perm = pool_perm_slot; p->pending.dst_lord = pool_lord_slot;
+    p->pending.stage_perm = stage_perm; p->pending.stage_lord = stage_lord;
+    p->pending.rows = (size_t)B; p->pending.active = true;
     p->stage_used = true;
     return 0;
+}
+int ddz_pipe_flush(ddz_pipe* p, void* stream) {
+    if (!p) return DDZ_E_ARG;
+    return pipe_commit_refill(p, (cudaStream_t)stream, true);
 }
 
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,

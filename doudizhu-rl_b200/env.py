@@ -658,7 +658,7 @@ class HostRollout:
         self.perm_d = env._to_dev(perm, torch.int8).reshape(self.G, B, 54).contiguous()
         self.lord_d = env._to_dev(lord_pile, torch.int8).reshape(self.G, B).contiguous()
         self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.results_h = [StepResults(B, "cpu", pin=True) for _ in range(2)]
+        self.results_h = [StepResults(B, "cpu", pin=True) for _ in range(N.PIPE_DEPTH)]   # ring: read up to 3 steps late
         self.d2h_bytes = self.results_h[0].nbytes if fetch_reward else _align(3 * B, 16)
         self._stage = None
         with torch.cuda.device(dev):
@@ -675,10 +675,12 @@ class HostRollout:
         if pipe and N is not None and getattr(N, "lib", None) is not None:   # module globals may be gone at interpreter exit
             N.lib.ddz_pipe_destroy(pipe)
 
-    def refill(self, slot, perm, lord_pile):
+    def refill(self, slot, perm, lord_pile, now=False):
         """upload one slot of the deal pool: perm int8 [B,54], lord_pile int8 [B], pinned host memory.  The upload
-        lands in a staging buffer on the copy stream (overlapping the kernels); the slot itself is replaced by a
-        device-to-device copy ordered between two steps, so no kernel ever reads a half-written permutation."""
+        lands in a staging buffer on its own copy stream (overlapping the kernels); the slot itself is replaced by a
+        device-to-device copy ordered between two steps -- no kernel ever reads a half-written permutation -- issued by
+        the first step() that finds the upload complete, so no step waits for it.  now=True (or flush()) makes the
+        replacement take effect before the next step, at the price of that step waiting for the upload."""
         env, B = self.env, self.env.B
         if self._stage is None:
             self._stage = (torch.empty((B, 54), dtype=torch.int8, device=env.device),
@@ -689,20 +691,27 @@ class HostRollout:
             N.check(N.lib.ddz_pipe_refill(self._pipe, self.perm_d[slot].data_ptr(), self.lord_d[slot].data_ptr(),
                                           perm.data_ptr(), lord_pile.data_ptr(), self._stage[0].data_ptr(),
                                           self._stage[1].data_ptr(), B, self._main.cuda_stream), "ddz_pipe_refill")
+        if now:
+            self.flush()
+
+    def flush(self):
+        """commit a staged refill now: the next step sees the new deals (the stream waits for the upload)"""
+        with torch.cuda.device(self.env.device):
+            N.check(N.lib.ddz_pipe_flush(self._pipe, self._main.cuda_stream), "ddz_pipe_flush")
 
     def _build_args(self):
-        """Everything ddz_pipe_step needs is constant per (list parity, step parity): marshal it once."""
+        """Everything ddz_pipe_step needs is constant per (list parity, step index % PIPE_DEPTH): marshal it once."""
         import ctypes as C
         env = self.env
         vp = lambda t: C.c_void_p(None if t is None else t.data_ptr())
         self._argv = {}
         for cur in (0, 1):
             nxt = 1 - cur
-            for k in (0, 1):
+            for k in range(N.PIPE_DEPTH):
                 self._argv[(cur, k)] = [
                     C.c_void_p(self._pipe), vp(env._state), vp(env._ws), C.c_int(env.VARIANT),
                     vp(env._offsets[cur]), vp(env._actions_u64[cur]),
-                    None, vp(self.entropy_d[k]), C.c_uint64(env.seed), C.c_uint64(env.env0), None,
+                    None, vp(self.entropy_d[k & 1]), C.c_uint64(env.seed), C.c_uint64(env.env0), None,
                     vp(env._rewards), vp(self.perm_d), vp(self.lord_d), C.c_int(self.G),
                     vp(env._results[nxt].buf), vp(self.results_h[k].buf), C.c_size_t(self.d2h_bytes),
                     vp(env._offsets[nxt]), vp(env._actions_u64[nxt]), vp(env._actions_f32), C.c_int64(env.cap),
@@ -711,8 +720,8 @@ class HostRollout:
 
     def step(self, entropy_h):
         """entropy_h: pinned int32 [B].  Returns the StepResults (pinned host views) this step will fill; they are
-        valid after `wait(results)` (or any later synchronisation)."""
-        env, k = self.env, self.i & 1
+        valid after `wait(results)` (or any later synchronisation) and are reused PIPE_DEPTH steps later."""
+        env, k = self.env, self.i % N.PIPE_DEPTH
         if self._argv is None:
             self._build_args()
         cur = env._cur

@@ -167,9 +167,13 @@ int ddz_select_actions(const float* q, const int32_t* offsets, float epsilon, ui
  *                       >= 3B, i.e. the reward floats are optional)  ->  results_host (pinned)
  * so the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t.  The pipe object only owns two CUDA
  * streams and a few events; every buffer stays caller-owned.  results_dev must alternate between two buffers (the
- * caller's ping-pong sets); ddz_pipe_wait(slot) blocks the host until the D2H issued by the step with that parity
- * (slot = step index & 1) has landed.  ddz_pipe_refill uploads one slot of the deal pool through a caller-provided
- * staging buffer and replaces the slot with a device-to-device copy ordered between two steps. */
+ * caller's ping-pong sets); results_host may rotate through up to DDZ_PIPE_DEPTH pinned buffers, so the host can read
+ * the results of step t as late as while step t + DDZ_PIPE_DEPTH - 1 is being issued; ddz_pipe_wait(slot) blocks the
+ * host until the D2H issued by the latest step with slot == step index % DDZ_PIPE_DEPTH has landed.  ddz_pipe_refill starts the upload of one slot of the deal pool into a
+ * caller-provided staging buffer on a third copy stream and returns; the slot itself is replaced by a device-to-device
+ * copy ordered between two steps, issued by the first ddz_pipe_step that finds the upload complete (so no step waits
+ * for it), or by ddz_pipe_flush / the next ddz_pipe_refill, which do wait.  One upload can be in flight per pipe. */
+#define DDZ_PIPE_DEPTH 4
 typedef struct ddz_pipe ddz_pipe;
 ddz_pipe* ddz_pipe_create(void);
 void ddz_pipe_destroy(ddz_pipe* p);
@@ -183,6 +187,7 @@ int ddz_pipe_step(ddz_pipe* p, void* state, void* workspace, int variant,
 int ddz_pipe_wait(ddz_pipe* p, int slot);
 int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot, const int8_t* host_perm,
                     const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord, int B, void* stream);
+int ddz_pipe_flush(ddz_pipe* p, void* stream);   /* commit a staged deal-pool upload now (stream waits for it) */
 
 /* env.face only (envi.py:87-217) */
 int ddz_encode_face(const void* state, int variant, float* face, int B, void* stream);

@@ -35,3 +35,21 @@ for mode in ("submit_only", "with_wait_and_read"):
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
     print(mode, "host issue %.1f us/step, wall %.1f us/step" % (t_issue / N * 1e6, t_all / N * 1e6))
+
+# the same two groups without any copies: direct launches of the fused step from Python (no graph), device entropy
+dev_ent = [torch.as_tensor(np.random.default_rng(9 + g).integers(0, 1 << 31, Bg).astype(np.int32)).cuda() for g in range(NG)]
+for label in ("direct_launch_mod_entropy", "direct_launch_philox"):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(N):
+        for g, env in enumerate(ge.envs):
+            with torch.cuda.stream(ge.streams[g]):
+                pg, lg, _ = ge._pool[g]
+                if label.endswith("philox"):
+                    env.rollout_step(perm=pg, lord_pile=lg, pool_games=P)
+                else:
+                    env.rollout_step(dev_ent[g], mode=D.native.CHOICE_MOD, perm=pg, lord_pile=lg, pool_games=P)
+    t_issue = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    print(label, "host issue %.1f us/step, wall %.1f us/step" % (t_issue / N * 1e6, t_all / N * 1e6))

@@ -324,7 +324,7 @@ def test_host_rollout_pipeline_matches_oracle(D, oracle):
         if t % 40 == 20:                              # refresh slot (t // 40) % G with new host-made deals
             slot = (t // 40) % G
             p2, l2 = D.random_deals(B, seed=100 + t)
-            host.refill(slot, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory())
+            host.refill(slot, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory(), now=True)
             pool[0][slot], pool[1][slot] = p2, l2
         res = host.step(ents[t % 6])
         ref.observe(want_f32=False, want_face=False)
@@ -1098,3 +1098,34 @@ def test_mcts_entry_point(D):
                "last_taken": {"0": [], "1": [9, 9], "2": []}}
     payload["role_id"] = 2
     assert D.mcts(payload, computation_budget=2000, seed=3) == [10, 10]
+
+
+def test_deferred_pool_refill(D):
+    """HostRollout.refill uploads in the background; the slot is replaced (whole, between two steps) by the first step
+    that finds the upload complete, or at once by flush()."""
+    B, G = 4096, 4
+    perm, lord = D.random_deals(B, seed=1, pool_games=G)
+    env = D.BatchedEnvCooperation(B, seed=3)
+    env.prepare(perm, lord, pool_games=G)
+    host = D.HostRollout(env, perm, lord, G)
+    ent = torch.as_tensor(np.random.default_rng(0).integers(0, 1 << 31, B).astype(np.int32)).pin_memory()
+    p2, l2 = D.random_deals(B, seed=77)
+    p2t, l2t = torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory()
+    old = host.perm_d[2].clone()
+    host.refill(2, p2t, l2t)
+    for _ in range(200):                                  # the upload (220 KB) lands within a few steps
+        res = host.step(ent)
+        slot = host.perm_d[2].cpu()
+        assert torch.equal(slot, old.cpu()) or torch.equal(slot, p2t)      # never a mixture
+        if torch.equal(slot, p2t):
+            break
+    D.HostRollout.wait(res)
+    torch.cuda.synchronize()
+    assert torch.equal(host.perm_d[2].cpu(), p2t) and torch.equal(host.lord_d[2].cpu(), l2t)
+    p3, l3 = D.random_deals(B, seed=78)
+    p3t, l3t = torch.as_tensor(p3).pin_memory(), torch.as_tensor(l3).pin_memory()
+    host.refill(1, p3t, l3t)
+    host.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(host.perm_d[1].cpu(), p3t) and torch.equal(host.lord_d[1].cpu(), l3t)
+    assert int(env.stats[7].item()) == 0
