@@ -62,6 +62,12 @@ constexpr int kMinCtasPerSm = 28 / kWarpsPerCta;  // 28 warps per SM (one wave a
 constexpr int kTile = DDZ_TILE_ENVS;                     // envs per warp tile (lane <-> env for lanes < kTile)
 constexpr int kRowUnroll = DDZ_ROW_UNROLL;               // row-writer iterations in flight per lane
 constexpr int kHeavy = DDZ_HEAVY;                       // envs with more legal moves than this are expanded by the whole warp
+#ifndef DDZ_PHASE_ORDER
+#define DDZ_PHASE_ORDER 0
+#endif
+// which of the two output phases a tile runs first: 0 = odd tiles rule work first, even tiles face rows first (default),
+// 1 = every tile face rows first, 2 = every tile rule work first
+DDZ_DEV bool kFaceSecond(int t) { return DDZ_PHASE_ORDER == 0 ? (t & 1) != 0 : DDZ_PHASE_ORDER == 2; }
 constexpr int kLookBack = DDZ_LOOKBACK;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
 
 enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
     int disagree = 0;
 #pragma unroll 1
     for (int ph = 0; ph < 2; ph++) {
-    if ((ph == 0) != ((t & 1) != 0)) {
+    if ((ph == 0) != kFaceSecond(t)) {
         // ---- 5. face rows: [nenv][C] rows of 240 B, contiguous for the warp
         trace(t, 2);
         if (V >= 0 && o.face) write_rows<FaceRow>(o.face + (size_t)b0 * C * 15, nenv * C, rl, sm.lut, sm.face);
