@@ -53,4 +53,17 @@ for nme, sel in (("even", ~odd), ("odd", odd)):
     out[nme + "_tiles"] = {k: float(np.nanmean(v[sel])) for k, v in dur.items()}
 out["even_tiles_end_p50"] = float(np.nanmedian(np.maximum(tr[even, 3], tr[even, 6])))
 out["odd_tiles_end_p50"] = float(np.nanmedian(np.maximum(tr[~even, 3], tr[~even, 6])))
+# what makes phase A slow, and who waits for whom: deals per tile, legal moves per tile
+done_after = env.done.cpu().numpy().astype(np.int64)            # envs that finished with this step (and were re-dealt)
+pad = (-B) % 32
+deals = np.pad(done_after, (0, pad)).reshape(nt, 32).sum(1)
+off = env.offsets.cpu().numpy().astype(np.int64)
+moves = np.add.reduceat(np.diff(off), np.arange(0, B, 32))
+out["phaseA_by_deals_in_tile"] = {str(k): {"tiles": int((deals == k).sum()), "mean_us": float(np.nanmean(dur["phaseA"][deals == k]))}
+                                  for k in range(0, 6) if (deals == k).any()}
+a_end = tr[:, 1]
+running_max = np.fmax.accumulate(np.nan_to_num(a_end, nan=0.0))
+out["phaseA_end_running_max_percentiles_us"] = {str(q): float(np.percentile(running_max, q)) for q in (10, 50, 90, 100)}
+out["lookback_end_minus_running_max_p50_us"] = float(np.nanmedian(tr[:, 5] - running_max))
+out["corr_moves_vs_lifetime"] = float(np.corrcoef(moves, np.nan_to_num(dur["warp_lifetime"]))[0, 1])
 print(json.dumps(out, indent=1))
