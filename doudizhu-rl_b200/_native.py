@@ -24,7 +24,7 @@ if not os.path.exists(LIB_PATH):
 EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
            "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
-           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions")
+           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit")
 
 lib = C.CDLL(LIB_PATH)
 _missing = [name for name in EXPORTS if not hasattr(lib, name)]
@@ -61,6 +61,8 @@ lib.ddz_pipe_wait.argtypes = [_vp, _i]
 lib.ddz_pipe_refill.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.ddz_pipe_flush.argtypes = [_vp, _vp]
 lib.ddz_encode_state_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.ddz_legal_count.argtypes = [_vp, _vp, _i, _vp]
+lib.ddz_legal_emit.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]
 lib.ddz_select_actions.argtypes = [_vp, _vp, C.c_float, _u64, _u64, _u32, _vp, _i, _vp]
 
 if lib.ddz_abi_version() != ABI_VERSION:

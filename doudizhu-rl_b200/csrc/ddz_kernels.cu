@@ -595,6 +595,19 @@ __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restri
     }
 }
 
+// number of legal moves of the player to move in every env, closed form (no list): one thread per env
+__global__ void __launch_bounds__(256) k_legal_count(const void* state, int32_t* __restrict__ counts, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Env e = load_env(view_of(const_cast<void*>(state), B), b);
+    int n = 0;
+    if (!e.done()) {
+        const uint64_t hand = hand_to_move(e), last = trick_of(e);
+        n = count_legal(masks_of(hand), rule_of(last), last != 0);
+    }
+    counts[b] = n;
+}
+
 // idx-th legal move of n independent (hand, last) pairs in closed form (no list): the building block of the playout
 __global__ void __launch_bounds__(256) k_kth_moves(const uint64_t* __restrict__ hands, const uint64_t* __restrict__ lasts,
                                                    const int32_t* __restrict__ idx, uint64_t* __restrict__ moves,
@@ -753,6 +766,18 @@ int ddz_observe(const void* state, void* workspace, int variant, int32_t* offset
     OutArgs o{offsets, actions_u64, (float4*)actions_f32, cap, (float4*)face, 0};
     return launch_env_v<kObserve>(variant, face != nullptr, const_cast<void*>(state), a, o, workspace, stats, B,
                                   (cudaStream_t)stream);
+}
+
+int ddz_legal_count(const void* state, int32_t* counts, int B, void* stream) {
+    if (!state || !counts || B <= 0) return DDZ_E_ARG;
+    k_legal_count<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, counts, B);
+    DDZ_LAUNCH_CHECK("k_legal_count");
+    return 0;
+}
+
+int ddz_legal_emit(const void* state, void* workspace, int32_t* offsets, uint64_t* actions_u64, int64_t cap,
+                   int64_t* stats, int B, void* stream) {
+    return ddz_observe(state, workspace, 0, offsets, actions_u64, nullptr, cap, nullptr, stats, B, stream);
 }
 
 static int fill_step_args(StepArgs& a, const int32_t* offsets, const uint64_t* actions, const void* choice, int mode,

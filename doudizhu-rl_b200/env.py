@@ -262,6 +262,14 @@ class BatchedEnv:
         off = self._offsets[self._cur].cpu().numpy()
         return [[[int(x) for x in row] for row in counts[off[b]:off[b + 1]]] for b in range(self.B)]
 
+    def legal_counts(self):
+        """int32 [B]: number of legal moves of the player to move in every env, in closed form (ddz_legal_count) -- no
+        lists are built or needed (e.g. to size buffers, or to draw a uniformly random move index for ddz_kth_moves)."""
+        counts = torch.empty(self.B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ddz_legal_count(self._p(self._state), counts.data_ptr(), self.B, self._stream()), "ddz_legal_count")
+        return counts
+
     def state_actions(self, env_mask=None):
         """The Q-network's input for every legal move, written in place (net.py:81-90 without `face.repeat` and
         `torch.cat`): float32 [n, C+1, 15, 4], row i = [face of the move's env | the move's one-hot].  env_mask bool [B]:

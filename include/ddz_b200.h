@@ -86,6 +86,13 @@ int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool
 int ddz_observe(const void* state, void* workspace, int variant, int32_t* offsets, uint64_t* actions_u64,
                 float* actions_f32, int64_t cap, float* face, int64_t* stats, int B, void* stream);
 
+/* The two halves of env.valid_actions() on their own (r.get_moves, envi.py:111): the number of legal moves of the player
+ * to move in every env in closed form (no list, no workspace; finished envs: 0), and the packed CSR lists without any
+ * float tensor (= ddz_observe with actions_f32 = face = NULL).  counts[b] == offsets[b+1] - offsets[b]. */
+int ddz_legal_count(const void* state, int32_t* counts, int B, void* stream);
+int ddz_legal_emit(const void* state, void* workspace, int32_t* offsets, uint64_t* actions_u64, int64_t cap,
+                   int64_t* stats, int B, void* stream);
+
 /* env.step_manual / step_random for all envs  (envi.py:63-70, 79-85, _update :38-43; terminal + sign
  * rule_based/rule_play.py:14-28; rewards game.py:109-118 with magnitudes rewards[role]).
  * offsets/actions_u64 must be the COMPLETE lists ddz_observe produced for the CURRENT state (no overflow: stats[7]).

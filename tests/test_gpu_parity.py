@@ -1129,3 +1129,28 @@ def test_deferred_pool_refill(D):
     torch.cuda.synchronize()
     assert torch.equal(host.perm_d[1].cpu(), p3t) and torch.equal(host.lord_d[1].cpu(), l3t)
     assert int(env.stats[7].item()) == 0
+
+
+def test_legal_count_and_emit_entry_points(D, oracle):
+    """ddz_legal_count (closed form, no lists) == the list lengths; ddz_legal_emit == ddz_observe's packed lists."""
+    B = 5000
+    perm, lord = D.random_deals(B, seed=8)
+    env = D.BatchedEnvComplicated(B, seed=6)
+    env.prepare(perm, lord)
+    for t in range(70):
+        if t % 10 == 0:
+            cnt = env.legal_counts()
+            off = env.offsets.to(torch.int64)
+            assert torch.equal(cnt.to(torch.int64), off[1:] - off[:-1])
+        env.rollout_step()                                   # no re-deal: finished envs accumulate and count 0
+    assert int((env.legal_counts() == 0).sum().item()) == int(env.is_done.sum().item()) > 0
+    offs = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+    acts = torch.zeros(env.cap, dtype=torch.int64, device="cuda")
+    ws = torch.zeros(D.native.lib.ddz_workspace_bytes(B), dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(16, dtype=torch.int64, device="cuda")
+    rc = D.native.lib.ddz_legal_emit(env._state.data_ptr(), ws.data_ptr(), offs.data_ptr(), acts.data_ptr(), env.cap,
+                                     stats.data_ptr(), B, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    n = env.num_actions
+    assert torch.equal(offs, env.offsets) and torch.equal(acts[:n], env.actions_packed) and int(stats[7].item()) == 0
