@@ -209,9 +209,13 @@ DDZ_DEV void each_kicker_set(uint32_t main, uint32_t mult, uint32_t S, int k, ui
     uint64_t base = pack_move(main, mult, 0, 0);
     for (uint32_t c = first_combo(S, k); c; c = next_combo(c, S)) f(base + pack_move(c, kmult, 0, 0));
 }
+// MULT cards of one rank: the nibble goes straight to its place (no mask spreading)
+DDZ_DEV uint64_t pack_rank(int rank, uint32_t mult) { return (uint64_t)mult << (4 * rank); }
+// MULT cards of each of the L consecutive ranks s .. s+L-1 (1 <= L <= 12)
+DDZ_DEV uint64_t pack_run(int s, int L, uint32_t mult) { return ((0x1111111111111111ull >> (64 - 4 * L)) * mult) << (4 * s); }
 template <int MULT, class F>
 DDZ_DEV void each_rank(uint32_t mask, F& f) {
-    while (mask) { uint32_t b = mask & (0u - mask); mask ^= b; f(pack_move(b, MULT, 0, 0)); }
+    while (mask) { const int r = __ffs(mask) - 1; mask &= mask - 1; f(pack_rank(r, MULT)); }
 }
 template <int MULT, int LMIN, int LMAX, class F>
 DDZ_DEV void each_line(uint32_t src, const Rule& ru, int cat, F& f) {
@@ -226,7 +230,7 @@ DDZ_DEV void each_line(uint32_t src, const Rule& ru, int cat, F& f) {
         uint32_t run = ((1u << LMIN) - 1u) << s;
         for (int L = LMIN; L <= LMAX; L++) {
             if ((R & run) != run) break;
-            if (ru.len_ok(cat, L)) f(pack_move(run, MULT, 0, 0));
+            if (ru.len_ok(cat, L)) f(pack_run(s, L, MULT));
             run |= run << 1;
         }
     }
@@ -257,11 +261,21 @@ DDZ_DEV void enumerate_legal(const Masks& m, const Rule& ru, bool has_last, F& f
     if (ru.allowed(4)) each_rank<4>(m.g4 & ru.from(4), f);
     if (ru.allowed(5)) {
         uint32_t mains = m.g3 & ru.from(5);
-        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 3, m.g1 & ~b, 1, 1, f); }
+        while (mains) {
+            const int r = __ffs(mains) - 1; mains &= mains - 1;
+            const uint64_t base = pack_rank(r, 3);
+            uint32_t ks = m.g1 & ~(1u << r);
+            while (ks) { const int q = __ffs(ks) - 1; ks &= ks - 1; f(base + pack_rank(q, 1)); }
+        }
     }
     if (ru.allowed(6)) {
         uint32_t mains = m.g3 & ru.from(6);
-        while (mains) { uint32_t b = mains & (0u - mains); mains ^= b; each_kicker_set(b, 3, m.g2 & ~b, 1, 2, f); }
+        while (mains) {
+            const int r = __ffs(mains) - 1; mains &= mains - 1;
+            const uint64_t base = pack_rank(r, 3);
+            uint32_t ks = m.g2 & ~(1u << r);
+            while (ks) { const int q = __ffs(ks) - 1; ks &= ks - 1; f(base + pack_rank(q, 2)); }
+        }
     }
     if (ru.allowed(7)) each_line<1, 5, 12>(m.g1, ru, 7, f);
     if (ru.allowed(8)) each_line<2, 3, 10>(m.g2, ru, 8, f);
@@ -302,7 +316,7 @@ DDZ_DEV void coop_kicker_sets(uint32_t main, uint32_t mult, uint32_t S, int k, u
 template <int MULT, class F>
 DDZ_DEV int coop_ranks(uint32_t mask, int off, int lane, F& f) {
     const int c = __popc(mask);
-    if (lane < c) f(off + lane, pack_move(nth_bit(mask, lane), MULT, 0, 0));
+    if (lane < c) f(off + lane, pack_rank(__fns(mask, 0, lane + 1), MULT));
     return c;
 }
 template <class F>
@@ -311,8 +325,8 @@ DDZ_DEV int coop_main_plus_one(uint32_t mains, uint32_t kicksrc, uint32_t kmult,
     const int c = nm * nk;
     for (int i = lane; i < c; i += 32) {
         const int mi = i / nk, ki = i - mi * nk;
-        const uint32_t main = nth_bit(mains, mi);
-        f(off + i, pack_move(main, 3, nth_bit(kicksrc & ~main, ki), kmult));
+        const int mr = __fns(mains, 0, mi + 1);
+        f(off + i, pack_rank(mr, 3) + pack_rank(__fns(kicksrc & ~(1u << mr), 0, ki + 1), kmult));
     }
     return c;
 }
@@ -332,7 +346,7 @@ DDZ_DEV int coop_lines(uint32_t src, const Rule& ru, int cat, int off, int lane,
         const int c = same ? ((ru.len >= LMIN && ru.len <= maxL) ? 1 : 0) : (maxL - LMIN + 1);
         if (lane < c) {
             const int L = same ? ru.len : LMIN + lane;
-            f(off + n + lane, pack_move(((1u << L) - 1u) << s, MULT, 0, 0));
+            f(off + n + lane, pack_run(s, L, MULT));
         }
         n += c;
     }
@@ -446,7 +460,7 @@ DDZ_DEV int flat_groups(const KickGroups& G, uint32_t mult, uint32_t kmult, int 
 template <class F>
 DDZ_DEV int flat_ranks(uint32_t mask, uint32_t mult, int off, int lane, F& f) {
     const int c = __popc(mask);
-    if (lane < c) f(off + lane, pack_move(nth_bit(mask, lane), mult, 0, 0));
+    if (lane < c) f(off + lane, pack_rank(__fns(mask, 0, lane + 1), mult));
     return c;
 }
 template <class F>
@@ -464,7 +478,7 @@ DDZ_DEV int flat_lines(uint32_t src, uint32_t mult, int lmin, int lmax, const Ru
         const int c = same ? ((ru.len >= lmin && ru.len <= maxL) ? 1 : 0) : (maxL - lmin + 1);
         if (lane < c) {
             const int L = same ? ru.len : lmin + lane;
-            f(off + n + lane, pack_move(((1u << L) - 1u) << s, mult, 0, 0));
+            f(off + n + lane, pack_run(s, L, mult));
         }
         n += c;
     }
