@@ -315,20 +315,21 @@ DDZ_DEV void coop_kicker_sets(uint32_t main, uint32_t mult, uint32_t S, int k, u
 }
 template <int MULT, class F>
 DDZ_DEV int coop_ranks(uint32_t mask, int off, int lane, F& f) {
-    const int c = __popc(mask);
-    if (lane < c) f(off + lane, pack_rank(__fns(mask, 0, lane + 1), MULT));
-    return c;
+    // lane l owns rank l: its place in the list is the number of set bits below it (no search for the j-th bit)
+    if ((mask >> lane) & 1u) f(off + __popc(mask & ((1u << lane) - 1u)), pack_rank(lane, MULT));
+    return __popc(mask);
 }
 template <class F>
 DDZ_DEV int coop_main_plus_one(uint32_t mains, uint32_t kicksrc, uint32_t kmult, int off, int lane, F& f) {
-    const int nm = __popc(mains), nk = __popc(kicksrc) - 1;   // every main rank is itself in kicksrc
-    const int c = nm * nk;
-    for (int i = lane; i < c; i += 32) {
-        const int mi = i / nk, ki = i - mi * nk;
-        const int mr = __fns(mains, 0, mi + 1);
-        f(off + i, pack_rank(mr, 3) + pack_rank(__fns(kicksrc & ~(1u << mr), 0, ki + 1), kmult));
+    // uniform loop over the trios; lane l owns kicker rank l (its list index = set bits below it)
+    int n = 0;
+    while (mains) {
+        const int mr = __ffs(mains) - 1; mains &= mains - 1;
+        const uint32_t ks = kicksrc & ~(1u << mr);
+        if ((ks >> lane) & 1u) f(off + n + __popc(ks & ((1u << lane) - 1u)), pack_rank(mr, 3) + pack_rank(lane, kmult));
+        n += __popc(ks);
     }
-    return c;
+    return n;
 }
 template <int MULT, int LMIN, int LMAX, class F>
 DDZ_DEV int coop_lines(uint32_t src, const Rule& ru, int cat, int off, int lane, F& f) {
@@ -443,25 +444,25 @@ DDZ_DEV int flat_groups(const KickGroups& G, uint32_t mult, uint32_t kmult, int 
     const int idx = i0 - __shfl_sync(FULL, pre, g);
     uint32_t combo = 0;
     if (i0 < i1) combo = idx ? unrank_combo(S, k, idx) : first_combo(S, k);
+    uint64_t base = pack_move(mainm, mult, 0, 0);          // the main ranks' nibbles: constant inside a group
     for (int it = 0; it < chunk; it++) {
         const bool act = i0 + it < i1;
         if (act) {
-            f(off + i0 + it, pack_move(mainm, mult, combo, kmult));
+            f(off + i0 + it, base + pack_move(combo, kmult, 0, 0));
             combo = next_combo(combo, S);
         }
         const bool adv = act && combo == 0 && i0 + it + 1 < i1;                    // group exhausted, chunk goes on
         const int gn = adv ? g + 1 : g;
         const uint32_t m2 = __shfl_sync(FULL, G.main, gn), S2 = __shfl_sync(FULL, G.S, gn);
         const int k2 = __shfl_sync(FULL, G.k, gn);
-        if (adv) { g = gn; mainm = m2; S = S2; k = k2; combo = first_combo(S, k); }
+        if (adv) { g = gn; mainm = m2; S = S2; k = k2; combo = first_combo(S, k); base = pack_move(mainm, mult, 0, 0); }
     }
     return total;
 }
 template <class F>
 DDZ_DEV int flat_ranks(uint32_t mask, uint32_t mult, int off, int lane, F& f) {
-    const int c = __popc(mask);
-    if (lane < c) f(off + lane, pack_rank(__fns(mask, 0, lane + 1), mult));
-    return c;
+    if ((mask >> lane) & 1u) f(off + __popc(mask & ((1u << lane) - 1u)), pack_rank(lane, mult));
+    return __popc(mask);
 }
 template <class F>
 DDZ_DEV int flat_lines(uint32_t src, uint32_t mult, int lmin, int lmax, const Rule& ru, int cat, int off, int lane, F& f) {
