@@ -116,6 +116,40 @@ __global__ void __launch_bounds__(128, 8) k_gridstride_v8(float4* out, size_t nv
     for (; i < nvec8; i += stride) st_v8((float*)out + i * 8, v, v);
 }
 
+// variant 9: the warps of a CTA write ONE region at a time together (row pairs interleaved between the warps), region
+// after region: the same bytes per CTA as rows30, but 1/WARPS as many concurrently open output streams
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_rows30_cta(float4* out, int nwarps) {
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane >= 30) return;
+    float4 v = make_float4(1.f, 0.f, 1.f, (float)wib);
+    for (int j = 0; j < WARPS; j++) {
+        const int w = blockIdx.x * WARPS + j;
+        if (w >= nwarps) return;
+        float4* dst = out + (size_t)w * kVecPerWarp + wib * 30 + lane;
+#pragma unroll 4
+        for (int i = wib; i < kRowsPerWarp / 2; i += WARPS, dst += 30 * WARPS) st_cs(dst, v);
+    }
+}
+
+// variant 10: "expand" as short-lived CTAs in address order: every thread writes 4 float4 of thermometer rows computed
+// from 16-byte row descriptors (packed counts + scale) read through L1/L2 -- the output stage of an env-step as its own
+// kernel.  CTA = 256 threads = 16 KB of output, then exit.
+__global__ void __launch_bounds__(256) k_expand_oneshot(const float4* __restrict__ desc, float4* __restrict__ out, size_t nvec) {
+    const size_t j0 = (size_t)blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t j = j0 + 256 * k;
+        if (j >= nvec) return;
+        const unsigned row = (unsigned)(j / 15), rank = (unsigned)(j - (size_t)row * 15);
+        const float4 d = __ldg(&desc[row]);
+        const unsigned w = rank >= 8 ? __float_as_uint(d.y) : __float_as_uint(d.x);
+        const unsigned c = (w >> (4 * (rank & 7))) & 15u;
+        const float s = d.z;
+        out[j] = make_float4(c > 0 ? s : 0.f, c > 1 ? s : 0.f, c > 2 ? s : 0.f, c > 3 ? s : 0.f);
+    }
+}
+
 template <class F>
 static float best_ms(F launch) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -144,6 +178,16 @@ int main(int argc, char** argv) {
     REPORT("gridstride", (k_gridstride<<<grid, 128>>>(out, nvec)));
     REPORT("gridstride_148x8", (k_gridstride<<<148 * 8, 128>>>(out, nvec)));
     REPORT("tma_tile", (k_tma<<<grid, 128, 4 * 7680>>>(out, nwarps)));
+    {
+        const size_t nrows = nvec / 15;
+        float4* desc; CK(cudaMalloc(&desc, nrows * 16));
+        CK(cudaMemset(desc, 0x3f, nrows * 16));
+        REPORT("expand_oneshot_16KB_ctas", (k_expand_oneshot<<<(unsigned)((nvec + 1023) / 1024), 256>>>(desc, out, nvec)));
+        CK(cudaFree(desc));
+    }
+    REPORT("rows30_cta4_1024_streams", (k_rows30_cta<4><<<nwarps / 4, 128>>>(out, nwarps)));
+    REPORT("rows30_cta8_512_streams", (k_rows30_cta<8><<<nwarps / 8, 256>>>(out, nwarps)));
+    REPORT("rows30_cta16_256_streams", (k_rows30_cta<16><<<nwarps / 16, 512>>>(out, nwarps)));
     REPORT("rows30_v8_cs", (k_rows30_v8<<<grid, 128>>>(out, nwarps)));
     REPORT("gridstride_v8", (k_gridstride_v8<<<grid, 128>>>(out, nvec / 2)));
     REPORT("memset", CK(cudaMemsetAsync(out, 1, bytes)));
