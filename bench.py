@@ -59,14 +59,15 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(envs, groups):
+def ncu_traffic(envs, groups, compressed):
     """DRAM bytes per step (all launches of the step) from the committed ncu --set full captures of the same workload,
     or None when there is no capture for this shape."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if envs != 131072:
             return None
-        return {1: d["single_group"], 2: d["two_groups"]}[groups]["traffic_bytes_per_step"]
+        key = {(1, False): "single_group", (2, True): "two_groups", (2, False): "two_groups_plain_memory"}[(groups, compressed)]
+        return d[key]["traffic_bytes_per_step"]
     except Exception:
         return None
 
@@ -205,6 +206,7 @@ def run_ours(args):
     # ---------------- the rank's envs as NG stream-parallel groups (one group's load-only prologue and tail
     # overlap the other group's store phase); device-resident deal pool, Philox moves on the device
     ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=NG, seed=SEED, device=dev, env0=env0, max_actions_per_env=160)
+    compressed = hasattr(ge.envs[0]._face, "_ddz_rows")          # row buffers in compressible memory (the default where supported)
     ge.prepare(perm, lord, pool_games=P)
     for _ in range(args.prefill):
         ge.rollout_step()
@@ -365,15 +367,19 @@ def run_ours(args):
                                             "stats all-reduce (int64[16], NCCL) every %d steps on a side stream, inside the timed region"
                                             % STATS_EVERY),
                             "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
+                            "row_buffers": ("compressible device memory (CU_MEM_ALLOCATION_COMP_GENERIC: the L2 compresses "
+                                            "the 0/1 thermometer rows on their way to HBM)" if compressed else "plain device memory"),
                             "games_finished": int(gstats[0].item()),
                             "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))}, **info),
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B, NG),
+                         "unit": "GB/s", "frac": kern_gbs / peak, "traffic": ncu_traffic(B, NG, compressed),
                          "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
                          "algorithmic_bytes_per_step": B * eb, "ms_per_step": step_ms, "launches_in_flight": NG,
                          "note": "achieved = algorithmic bytes of one step of all envs / wall time per step; the step is "
                                  "%d concurrent launches of the same kernel (one per env group); traffic = ncu DRAM bytes "
-                                 "of those launches (profiles/r1_traffic.json)" % NG,
+                                 "of those launches (profiles/r1_traffic.json)%s" % (
+                                     NG, "; it is far below the algorithmic bytes because the row buffers are compressible memory"
+                                     if compressed else ""),
                          "single_launch": ({"ms_per_launch": info["single_group_graph_ms_per_step"],
                                             "achieved": B * eb / (info["single_group_graph_ms_per_step"] * 1e-3) / 1e9,
                                             "frac": B * eb / (info["single_group_graph_ms_per_step"] * 1e-3) / 1e9 / peak,

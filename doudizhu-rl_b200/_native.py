@@ -24,7 +24,7 @@ if not os.path.exists(LIB_PATH):
 EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
            "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
-           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit")
+           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit", "ddz_rows_alloc", "ddz_rows_free")
 
 lib = C.CDLL(LIB_PATH)
 _missing = [name for name in EXPORTS if not hasattr(lib, name)]
@@ -63,6 +63,8 @@ lib.ddz_pipe_flush.argtypes = [_vp, _vp]
 lib.ddz_encode_state_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.ddz_legal_count.argtypes = [_vp, _vp, _i, _vp]
 lib.ddz_legal_emit.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]
+lib.ddz_rows_alloc.argtypes = [C.c_size_t, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+lib.ddz_rows_free.argtypes = [_vp, C.c_size_t]
 lib.ddz_select_actions.argtypes = [_vp, _vp, C.c_float, _u64, _u64, _u32, _vp, _i, _vp]
 
 if lib.ddz_abi_version() != ABI_VERSION:
@@ -79,3 +81,41 @@ def check(rc, what):
     if rc == E_CUDA:
         raise DdzError("%s: CUDA failure: %s" % (what, lib.ddz_last_error().decode()))
     raise DdzError("%s: bad argument (code %d)" % (what, rc))
+
+
+class _RowMemory:
+    """one compressible device allocation (ddz_rows_alloc), exposed through __cuda_array_interface__"""
+
+    def __init__(self, nbytes, device_index):
+        ptr, mapped = C.c_void_p(), C.c_size_t()
+        check(lib.ddz_rows_alloc(nbytes, device_index, C.byref(ptr), C.byref(mapped)), "ddz_rows_alloc")
+        self.ptr, self.mapped, self.nbytes = ptr.value, mapped.value, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (self.ptr, False), "version": 2}
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr and lib is not None:
+            lib.ddz_rows_free(ptr, self.mapped)
+
+
+def row_tensor(shape, device):
+    """float32 tensor for thermometer rows (face / action one-hots) in COMPRESSIBLE device memory when the GPU has it
+    (the L2 compresses the 0/1 rows on their way to HBM: +15 % store bandwidth for this data), else plain torch memory.
+    DDZ_NO_COMPRESSION=1 forces plain memory."""
+    import torch
+    n = 1
+    for d in shape:
+        n *= int(d)
+    dev = torch.device(device)
+    if n == 0 or os.environ.get("DDZ_NO_COMPRESSION"):
+        return torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    try:
+        with torch.cuda.device(index):
+            torch.cuda.current_stream()                  # the primary context exists
+            mem = _RowMemory(4 * n, index)
+    except DdzError:
+        return torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+    t = torch.as_tensor(mem, device=dev).view(tuple(shape))
+    t._ddz_rows = mem                                    # keep the allocation alive with the tensor object
+    return t

@@ -23,6 +23,7 @@
 // traffic (profiles/).  Two earlier variants that staged rows in shared memory and pushed them with TMA bulk stores
 // (cp.async.bulk) measured slower (profiles/r1b*, r1c*): the path is nowhere near issue-bound, what it
 // needs is many independent warps with stores in flight and no synchronisation.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -734,6 +735,43 @@ static int launch_env_v(int variant, bool want_face, void* state, const StepArgs
     return DDZ_E_ARG;
 }
 
+// driver entry points for the compressible row buffers (ddz_rows_alloc), fetched through the runtime
+namespace {
+struct DriverApi {
+    CUresult (*getGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+    CUresult (*release)(CUmemGenericAllocationHandle);
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+    CUresult (*addressFree)(CUdeviceptr, size_t);
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    CUresult (*unmap)(CUdeviceptr, size_t);
+    CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+    bool ok;
+};
+template <class Fn>
+bool driver_fn(const char* name, Fn& fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !p) {
+        cudaGetLastError();
+        return false;
+    }
+    fn = reinterpret_cast<Fn>(p);
+    return true;
+}
+const DriverApi& driver_api() {
+    static DriverApi d = [] {
+        DriverApi a{};
+        a.ok = driver_fn("cuMemGetAllocationGranularity", a.getGranularity) && driver_fn("cuMemCreate", a.create) &&
+               driver_fn("cuMemRelease", a.release) && driver_fn("cuMemAddressReserve", a.reserve) &&
+               driver_fn("cuMemAddressFree", a.addressFree) && driver_fn("cuMemMap", a.map) &&
+               driver_fn("cuMemUnmap", a.unmap) && driver_fn("cuMemSetAccess", a.setAccess);
+        return a;
+    }();
+    return d;
+}
+}  // namespace
+
 extern "C" {
 
 #ifdef DDZ_TRACE
@@ -963,6 +1001,58 @@ int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot,
 int ddz_pipe_flush(ddz_pipe* p, void* stream) {
     if (!p) return DDZ_E_ARG;
     return pipe_commit_refill(p, (cudaStream_t)stream, true);
+}
+
+// ---- compressible row buffers ------------------------------------------------------------------------
+// The one-hot / face rows are floats that are 0 or 1 (or 0 or a scale): lines of them compress well.  Memory created with
+// CU_MEM_ALLOCATION_COMP_GENERIC is compressed by the L2 on its way to HBM (and expanded on the way back), which raises
+// the bandwidth the row writer sees (profiles/r1u_compressible.json).  Driver entry points are fetched through the
+// runtime (cudaGetDriverEntryPoint): the library does not link libcuda and still loads on a machine without a driver.
+
+int ddz_rows_alloc(size_t bytes, int device, void** ptr, size_t* mapped_bytes) {
+    if (!ptr || !mapped_bytes || bytes == 0 || device < 0) return DDZ_E_ARG;
+    *ptr = nullptr; *mapped_bytes = 0;
+    const DriverApi& d = driver_api();
+    if (!d.ok) { snprintf(g_err, sizeof g_err, "ddz_rows_alloc: virtual memory management entry points not available"); return DDZ_E_CUDA; }
+    CUmemAllocationProp prop; memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.allocFlags.compressionType = CU_MEM_ALLOCATION_COMP_GENERIC;
+    size_t gran = 0;
+    if (d.getGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) {
+        snprintf(g_err, sizeof g_err, "ddz_rows_alloc: compressible memory is not supported on device %d", device);
+        return DDZ_E_CUDA;
+    }
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    if (d.create(&h, size, &prop, 0) != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof g_err, "ddz_rows_alloc: cuMemCreate(%zu bytes, compressible) failed", size);
+        return DDZ_E_CUDA;
+    }
+    CUdeviceptr p = 0;
+    if (d.reserve(&p, size, 0, 0, 0) != CUDA_SUCCESS) { d.release(h); snprintf(g_err, sizeof g_err, "ddz_rows_alloc: address reservation failed"); return DDZ_E_CUDA; }
+    CUmemAccessDesc acc; memset(&acc, 0, sizeof acc);
+    acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (d.map(p, size, 0, h, 0) != CUDA_SUCCESS || d.setAccess(p, size, &acc, 1) != CUDA_SUCCESS) {
+        d.unmap(p, size); d.addressFree(p, size); d.release(h);
+        snprintf(g_err, sizeof g_err, "ddz_rows_alloc: mapping failed");
+        return DDZ_E_CUDA;
+    }
+    d.release(h);                      // the mapping keeps the memory alive until ddz_rows_free unmaps it
+    *ptr = (void*)p; *mapped_bytes = size;
+    return 0;
+}
+
+int ddz_rows_free(void* ptr, size_t mapped_bytes) {
+    if (!ptr || mapped_bytes == 0) return DDZ_E_ARG;
+    const DriverApi& d = driver_api();
+    if (!d.ok) return DDZ_E_CUDA;
+    if (d.unmap((CUdeviceptr)ptr, mapped_bytes) != CUDA_SUCCESS || d.addressFree((CUdeviceptr)ptr, mapped_bytes) != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof g_err, "ddz_rows_free: unmap failed");
+        return DDZ_E_CUDA;
+    }
+    return 0;
 }
 
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,

@@ -87,8 +87,8 @@ class Trajectory:
         self.cap = env.cap
         self.offsets = torch.zeros((K, B + 1), dtype=torch.int32, device=dev)
         self.actions_u64 = torch.zeros((K, self.cap), dtype=torch.int64, device=dev)
-        self.actions_f32 = torch.empty((K, self.cap, 15, 4), dtype=torch.float32, device=dev)
-        self.face = torch.empty((K, B, env.C, 15, 4), dtype=torch.float32, device=dev)
+        self.actions_f32 = N.row_tensor((K, self.cap, 15, 4), dev)
+        self.face = N.row_tensor((K, B, env.C, 15, 4), dev)
         self.r = torch.zeros((K, B), dtype=torch.int8, device=dev)
         self.done = torch.zeros((K, B), dtype=torch.uint8, device=dev)
         self.cat = torch.zeros((K, B), dtype=torch.int8, device=dev)
@@ -125,8 +125,8 @@ class BatchedEnv:
             self._ws = torch.zeros(max(1, N.lib.ddz_workspace_bytes(B) // 4), dtype=torch.int32, device=dev)
             self._offsets = [torch.zeros(B + 1, dtype=torch.int32, device=dev) for _ in range(2)]
             self._actions_u64 = [torch.zeros(self.cap, dtype=torch.int64, device=dev) for _ in range(2)]
-            self._actions_f32 = torch.empty((self.cap, 15, 4), dtype=torch.float32, device=dev)
-            self._face = torch.empty((B, self.C, 15, 4), dtype=torch.float32, device=dev)
+            self._actions_f32 = N.row_tensor((self.cap, 15, 4), dev)      # compressible memory where the GPU has it
+            self._face = N.row_tensor((B, self.C, 15, 4), dev)
             self._results = [StepResults(B, dev) for _ in range(2)]   # two sets: a D2H read of one may overlap the next step
             self._res = 0
             self.stats = torch.zeros(16, dtype=torch.int64, device=dev)

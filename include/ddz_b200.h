@@ -196,6 +196,14 @@ int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot,
                     const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord, int B, void* stream);
 int ddz_pipe_flush(ddz_pipe* p, void* stream);   /* commit a staged deal-pool upload now (stream waits for it) */
 
+/* Optional allocator for the big float row buffers (actions_f32, face): device memory created compressible
+ * (CU_MEM_ALLOCATION_COMP_GENERIC), so the L2 compresses the 0/1 thermometer rows on their way to HBM and expands them
+ * for the reader -- transparent to every kernel, +15 % store bandwidth for this data.  The caller owns the buffer and
+ * gives it back with ddz_rows_free(ptr, mapped_bytes); plain cudaMalloc / torch memory works everywhere as well.
+ * Returns DDZ_E_CUDA (text in ddz_last_error) when the device or driver has no compressible memory. */
+int ddz_rows_alloc(size_t bytes, int device, void** ptr, size_t* mapped_bytes);
+int ddz_rows_free(void* ptr, size_t mapped_bytes);
+
 /* env.face only (envi.py:87-217) */
 int ddz_encode_face(const void* state, int variant, float* face, int B, void* stream);
 

@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path, called through the C-ABI (ddz_b200 -> ctypes -> libddz_b200.so), against the CPU oracle
 and the committed golden fixtures.  Everything is integer / exact-float work: comparisons are bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -1154,3 +1156,38 @@ def test_legal_count_and_emit_entry_points(D, oracle):
     torch.cuda.synchronize()
     n = env.num_actions
     assert torch.equal(offs, env.offsets) and torch.equal(acts[:n], env.actions_packed) and int(stats[7].item()) == 0
+
+
+def test_compressible_row_buffers(D):
+    """ddz_rows_alloc / row_tensor: the face and one-hot buffers live in compressible device memory where the GPU has it;
+    they behave like any other tensor, survive the allocator object going out of scope, and are given back on deletion."""
+    import gc
+    env = D.BatchedEnvCooperation(2048, seed=1)
+    if not hasattr(env._face, "_ddz_rows"):
+        pytest.skip("no compressible memory on this device / driver")
+    perm, lord = D.random_deals(2048, seed=2)
+    env.prepare(perm, lord)
+    a = D.native.row_tensor((1000, 15, 4), "cuda")
+    assert a.is_cuda and a.dtype == torch.float32 and a.shape == (1000, 15, 4) and a.data_ptr() % 256 == 0
+    a.fill_(3.0)
+    b = a.view(-1)[:60].clone()
+    assert float(b.sum().item()) == 180.0
+    free0 = torch.cuda.mem_get_info()[0]
+    big = D.native.row_tensor((64 << 20,), "cuda")                   # 256 MB
+    big.zero_()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] <= free0 - (200 << 20)
+    del big
+    gc.collect()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (16 << 20)         # unmapped and released
+    os.environ["DDZ_NO_COMPRESSION"] = "1"
+    try:
+        plain = D.BatchedEnvCooperation(2048, seed=1)
+        assert not hasattr(plain._face, "_ddz_rows")
+        plain.prepare(perm, lord)
+        for _ in range(30):
+            env.rollout_step(); plain.rollout_step()
+        assert torch.equal(env.face, plain.face) and torch.equal(env.valid_actions()[0], plain.valid_actions()[0])
+    finally:
+        del os.environ["DDZ_NO_COMPRESSION"]
