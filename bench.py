@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--prefill", type=int, default=150, help="untimed env-steps that bring the games to their steady-state mix")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=2, help="stream-parallel env groups per GPU (1 = one chain of launches)")
+    ap.add_argument("--groups", type=int, default=4, help="stream-parallel env groups per GPU (1 = one chain of launches)")
     ap.add_argument("--no-single", action="store_true", help="skip the single-group information run")
     return ap.parse_args()
 
@@ -66,7 +66,8 @@ def ncu_traffic(envs, groups, compressed):
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if envs != 131072:
             return None
-        key = {(1, False): "single_group", (2, True): "two_groups", (2, False): "two_groups_plain_memory"}[(groups, compressed)]
+        key = {(1, False): "single_group", (2, True): "two_groups", (2, False): "two_groups_plain_memory",
+               (4, True): "four_groups"}[(groups, compressed)]
         return d[key]["traffic_bytes_per_step"]
     except Exception:
         return None

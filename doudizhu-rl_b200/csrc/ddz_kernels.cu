@@ -36,7 +36,7 @@
 namespace ddz {
 
 #ifndef DDZ_THREADS
-#define DDZ_THREADS 128
+#define DDZ_THREADS 64
 #endif
 constexpr int kThreads = DDZ_THREADS;            // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;

@@ -558,7 +558,8 @@ class GroupedEnv:
 
     The step kernel has a load-only prologue (no stores for the first ~8 us) and a tail; a single chain of launches
     pays both every step.  With two (or more) unsynchronised chains one group's prologue and tail overlap another
-    group's store phase (+17 % env-steps/s at 131 072 envs, profiles/r1_two_stream_experiment.json) -- the classic
+    group's store phase (+17 % env-steps/s at 131 072 envs with two groups, +27 % with four once the row buffers are
+    compressible; profiles/r1_two_stream_experiment.json, r1u_group_sweep.json) -- the classic
     double-buffered actor: while group A's observations are consumed, group B steps.  Global env ids (Philox stream,
     deal rows) are those of one big batch, so every env's trajectory is independent of the grouping.
     """
