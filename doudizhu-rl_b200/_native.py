@@ -24,7 +24,8 @@ if not os.path.exists(LIB_PATH):
 EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
            "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
-           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit", "ddz_rows_alloc", "ddz_rows_free")
+           "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit", "ddz_rows_alloc", "ddz_rows_free",
+           "ddz_mpipe_create", "ddz_mpipe_destroy", "ddz_mpipe_step", "ddz_mpipe_wait", "ddz_mpipe_refill", "ddz_mpipe_flush")
 
 lib = C.CDLL(LIB_PATH)
 _missing = [name for name in EXPORTS if not hasattr(lib, name)]
@@ -65,6 +66,25 @@ lib.ddz_legal_count.argtypes = [_vp, _vp, _i, _vp]
 lib.ddz_legal_emit.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]
 lib.ddz_rows_alloc.argtypes = [C.c_size_t, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
 lib.ddz_rows_free.argtypes = [_vp, C.c_size_t]
+
+
+class GroupStep(C.Structure):
+    """ddz_group_step of include/ddz_b200.h"""
+    _fields_ = [("state", _vp), ("workspace", _vp), ("prev_offsets", _vp), ("prev_actions_u64", _vp),
+                ("out_offsets", _vp), ("out_actions_u64", _vp), ("out_actions_f32", _vp), ("face", _vp),
+                ("perm", _vp), ("lord_pile", _vp), ("reward", _vp),
+                ("cap", _i64), ("env0", _u64), ("B", _i), ("stream", _vp)]
+
+
+MPIPE_MAX_GROUPS = 16
+lib.ddz_mpipe_create.argtypes = [_i]
+lib.ddz_mpipe_create.restype = _vp
+lib.ddz_mpipe_destroy.argtypes = [_vp]
+lib.ddz_mpipe_destroy.restype = None
+lib.ddz_mpipe_step.argtypes = [_vp, C.POINTER(GroupStep), _i, _vp, _vp, _u64, _u32, _vp, _i, _vp, _vp, _vp]
+lib.ddz_mpipe_wait.argtypes = [_vp, _i]
+lib.ddz_mpipe_refill.argtypes = [_vp, C.POINTER(GroupStep), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp]
+lib.ddz_mpipe_flush.argtypes = [_vp, C.POINTER(GroupStep)]
 lib.ddz_select_actions.argtypes = [_vp, _vp, C.c_float, _u64, _u64, _u32, _vp, _i, _vp]
 
 if lib.ddz_abi_version() != ABI_VERSION:

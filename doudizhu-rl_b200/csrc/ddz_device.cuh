@@ -13,7 +13,21 @@
 #pragma once
 #include <cstdint>
 
+#ifdef DDZ_HOST_HARNESS
+// tests/host_harness compiles this rule code for the CPU with g++ (the per-hand logic has no warp intrinsics), so that
+// the enumeration can be checked against the oracle where there is no GPU.  Never defined in the product build.
+#include <algorithm>
+#define DDZ_DEV inline
+#define __constant__ static const
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+using std::max;
+using std::min;
+#else
 #define DDZ_DEV __device__ __forceinline__
+#endif
 
 namespace ddz {
 
@@ -293,6 +307,7 @@ DDZ_DEV void enumerate_legal(const Masks& m, const Rule& ru, bool has_last, F& f
     }
 }
 
+#ifndef DDZ_HOST_HARNESS
 // ------------------------------------------------------------------------------------------------
 // warp-cooperative enumeration of ONE env (same list, same order), for envs with many legal moves.
 // All 32 lanes walk the canonical group sequence with identical control flow; a group of c moves starting at
@@ -300,7 +315,6 @@ DDZ_DEV void enumerate_legal(const Masks& m, const Rule& ru, bool has_last, F& f
 // combinations, found by unranking), and f(index, packed_move) stores it.  A thread-per-env enumeration of a
 // 300-move hand is a 300-step dependent chain in one lane; this makes it ~10 steps per lane.
 // ------------------------------------------------------------------------------------------------
-DDZ_DEV uint32_t nth_bit(uint32_t mask, int j) { return 1u << __fns(mask, 0, j + 1); }   // j-th set bit (0-based)
 
 // c kicker sets of size k out of S for one main group, split into 32 contiguous chunks
 template <class F>
@@ -407,146 +421,18 @@ DDZ_DEV int enumerate_legal_warp(const Masks& m, const Rule& ru, bool has_last, 
     return off;
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same list for the long-list specialist (ddz_legal_moves, BASELINE config 5: hundreds of moves per hand).  Two things
-// differ from enumerate_legal_warp: (1) the kicker-set groups of a category are flattened into ONE index space, so a lane
-// unranks once per category instead of once per group; (2) every category walk takes its shape (multiplicity, line
-// lengths, wing size) as run-time values and is called from a short non-unrolled loop -- one copy of each walk in the
-// instruction stream.  On adversarial hands this is 1.37x faster (fewer instructions, far fewer instruction-fetch stalls);
-// inside the env-step kernel, where long lists are rare and short, the specialised walks above measure 2-7 % faster.
-// ------------------------------------------------------------------------------------------------
-struct KickGroups {   // lane g (< ng) holds group g = (main ranks, kicker source S, kicker count k, C(|S|, k) > 0 sets)
-    uint32_t main = 0, S = 0; int k = 0, c = 0, ng = 0;
-    DDZ_DEV void add(int lane, uint32_t main_, uint32_t S_, int k_, int c_) {
-        if (c_ <= 0) return;
-        if (lane == ng) { main = main_; S = S_; k = k_; c = c_; }
-        ng++;
-    }
-};
-// The `total` moves of all groups are split into 32 contiguous chunks; a lane unranks ONCE, at the start of its chunk,
-// then walks successors, stepping into the next group when one is exhausted.  Uniform control flow: every lane runs the
-// same number of iterations and takes part in every shuffle.
-template <class F>
-DDZ_DEV int flat_groups(const KickGroups& G, uint32_t mult, uint32_t kmult, int off, int lane, F& f) {
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    if (G.ng == 0) return 0;
-    const int mine = lane < G.ng ? G.c : 0;
-    int inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
-    const int pre = inc - mine, total = __shfl_sync(FULL, inc, 31);
-    const int chunk = (total + 31) >> 5;
-    const int i0 = lane * chunk, i1 = min(total, i0 + chunk);
-    int g = 0;
-    for (int j = 1; j < G.ng; j++) if (__shfl_sync(FULL, pre, j) <= i0) g = j;     // the group my chunk starts in
-    uint32_t mainm = __shfl_sync(FULL, G.main, g), S = __shfl_sync(FULL, G.S, g);
-    int k = __shfl_sync(FULL, G.k, g);
-    const int idx = i0 - __shfl_sync(FULL, pre, g);
-    uint32_t combo = 0;
-    if (i0 < i1) combo = idx ? unrank_combo(S, k, idx) : first_combo(S, k);
-    uint64_t base = pack_move(mainm, mult, 0, 0);          // the main ranks' nibbles: constant inside a group
-    for (int it = 0; it < chunk; it++) {
-        const bool act = i0 + it < i1;
-        if (act) {
-            f(off + i0 + it, base + pack_move(combo, kmult, 0, 0));
-            combo = next_combo(combo, S);
-        }
-        const bool adv = act && combo == 0 && i0 + it + 1 < i1;                    // group exhausted, chunk goes on
-        const int gn = adv ? g + 1 : g;
-        const uint32_t m2 = __shfl_sync(FULL, G.main, gn), S2 = __shfl_sync(FULL, G.S, gn);
-        const int k2 = __shfl_sync(FULL, G.k, gn);
-        if (adv) { g = gn; mainm = m2; S = S2; k = k2; combo = first_combo(S, k); base = pack_move(mainm, mult, 0, 0); }
-    }
-    return total;
-}
-template <class F>
-DDZ_DEV int flat_ranks(uint32_t mask, uint32_t mult, int off, int lane, F& f) {
-    if ((mask >> lane) & 1u) f(off + __popc(mask & ((1u << lane) - 1u)), pack_rank(lane, mult));
-    return __popc(mask);
-}
-template <class F>
-DDZ_DEV int flat_lines(uint32_t src, uint32_t mult, int lmin, int lmax, const Rule& ru, int cat, int off, int lane, F& f) {
-    const uint32_t R = src & kLineMask;
-    uint32_t t = R;
-    for (int L = 2; L <= lmin; L++) t &= R >> (L - 1);
-    t &= ru.from(cat);
-    const bool same = !ru.lead && cat == ru.cat;
-    int n = 0;
-    while (t) {                                            // uniform: every lane sees the same starts
-        const int s = __ffs(t) - 1; t &= t - 1;
-        const int run = __ffs(~(R >> s)) - 1;              // length of the run of ones starting at s
-        const int maxL = min(run, lmax);
-        const int c = same ? ((ru.len >= lmin && ru.len <= maxL) ? 1 : 0) : (maxL - lmin + 1);
-        if (lane < c) {
-            const int L = same ? ru.len : lmin + lane;
-            f(off + n + lane, pack_run(s, L, mult));
-        }
-        n += c;
-    }
-    return n;
-}
-template <class F>
-DDZ_DEV int flat_planes(uint32_t g3, uint32_t kicksrc, int lmax, uint32_t kmult, const Rule& ru, int cat, int off, int lane, F& f) {
-    const uint32_t R = g3 & kLineMask;
-    uint32_t t = R & (R >> 1) & ru.from(cat);
-    KickGroups G;
-    int n = 0;
-    while (t) {
-        const int s = __ffs(t) - 1; t &= t - 1;
-        uint32_t run = 3u << s;
-        for (int L = 2; L <= lmax; L++) {
-            if ((R & run) != run) break;
-            if (ru.len_ok(cat, L)) {
-                const uint32_t S = kicksrc & ~run;
-                if (G.ng == 32) { n += flat_groups(G, 3, kmult, off + n, lane, f); G = KickGroups(); }
-                G.add(lane, run, S, L, binom(__popc(S), L));
-            }
-            run |= run << 1;
-        }
-    }
-    return n + flat_groups(G, 3, kmult, off + n, lane, f);
-}
-template <class F>
-DDZ_DEV int flat_four_two(uint32_t mains, uint32_t kicksrc, uint32_t kmult, int off, int lane, F& f) {
-    KickGroups G;
-    while (mains) {
-        const uint32_t b = mains & (0u - mains); mains ^= b;
-        const uint32_t S = kicksrc & ~b;
-        G.add(lane, b, S, 2, binom(__popc(S), 2));
-    }
-    return flat_groups(G, 4, kmult, off, lane, f);
-}
-template <class F>
-DDZ_DEV int enumerate_legal_warp_long(const Masks& m, const Rule& ru, bool has_last, int lane, F& f) {
-    if (m.g1 == 0) { if (has_last && lane == 0) f(0, 0ull); return has_last ? 1 : 0; }
-    int off = 0;
-    if (!ru.lead) { if (lane == 0) f(0, 0ull); off = 1; }
-#pragma unroll 1
-    for (int k = 1; k <= 4; k++)                            // solo, pair, trio, bomb
-        if (ru.allowed(k)) off += flat_ranks((k == 1 ? m.g1 : k == 2 ? m.g2 : k == 3 ? m.g3 : m.g4) & ru.from(k), k, off, lane, f);
-#pragma unroll 1
-    for (int v = 0; v < 2; v++)                             // trio + solo, trio + pair
-        if (ru.allowed(5 + v)) off += coop_main_plus_one(m.g3 & ru.from(5 + v), v ? m.g2 : m.g1, 1 + v, off, lane, f);
-#pragma unroll 1
-    for (int v = 0; v < 3; v++)                             // straights of solos (5..12), pairs (3..10), trios (2..6)
-        if (ru.allowed(7 + v))
-            off += flat_lines(v == 0 ? m.g1 : v == 1 ? m.g2 : m.g3, 1 + v, v == 0 ? 5 : v == 1 ? 3 : 2,
-                              v == 0 ? 12 : v == 1 ? 10 : 6, ru, 7 + v, off, lane, f);
-#pragma unroll 1
-    for (int v = 0; v < 2; v++)                             // airplanes with solo wings (2..5 trios), pair wings (2..4)
-        if (ru.allowed(10 + v)) off += flat_planes(m.g3, v ? m.g2 : m.g1, v ? 4 : 5, 1 + v, ru, 10 + v, off, lane, f);
-    if (ru.allowed(12) && (m.g1 & kRocket) == kRocket) { if (lane == 0) f(off, pack_move(kRocket, 1, 0, 0)); off++; }
-#pragma unroll 1
-    for (int v = 0; v < 2; v++)                             // four with two solos / two pairs
-        if (ru.allowed(13 + v)) off += flat_four_two(m.g4 & ru.from(13 + v), v ? m.g2 : m.g1, 1 + v, off, lane, f);
-    return off;
-}
+#endif  // DDZ_HOST_HARNESS
 
 // ------------------------------------------------------------------------------------------------
 // idx-th legal move in canonical order WITHOUT enumerating the list: walk the categories with their closed-form
 // counts, then unrank inside the one group that holds it (O(#groups), not O(#moves)).  idx must be < count_legal.
 // Used by the playout kernel (a random rollout needs one move per decision, not the list).
 // ------------------------------------------------------------------------------------------------
+#ifdef DDZ_HOST_HARNESS
+DDZ_DEV uint32_t nth_bit(uint32_t mask, int j) { while (j-- > 0) mask &= mask - 1; return mask & (0u - mask); }
+#else
+DDZ_DEV uint32_t nth_bit(uint32_t mask, int j) { return 1u << __fns(mask, 0, j + 1); }   // j-th set bit (0-based)
+#endif
 template <int MULT, int LMIN, int LMAX>
 DDZ_DEV bool select_line(uint32_t src, const Rule& ru, int cat, int& idx, uint64_t& mv) {
     const uint32_t R = src & kLineMask;
@@ -692,6 +578,7 @@ DDZ_DEV uint64_t trick_of(const Env& e) {
     return last_move(p1, p2);
 }
 
+#ifndef DDZ_HOST_HARNESS
 // Warp-cooperative deal.  `need` = ballot of the lanes whose env must be re-dealt; for each of them the
 // whole warp reads the 54-byte permutation row (lane l < 27 loads cards 2l and 2l+1 as one 16-bit word), builds the
 // four piles with hardware warp reductions (nibble sums never carry: a rank has at most 4 cards) and checks that the
@@ -751,6 +638,8 @@ DDZ_DEV unsigned int warp_deal(unsigned int need, Env& e, const int8_t* __restri
     }
     return __reduce_or_sync(0xFFFFFFFFu, bad);
 }
+
+#endif  // DDZ_HOST_HARNESS
 
 struct StepOut { int r, done, cat; float reward[3]; bool applied, pass; int winner; };
 

@@ -32,6 +32,7 @@
 
 #include "../../include/ddz_b200.h"
 #include "ddz_device.cuh"
+#include "ddz_flat.cuh"
 
 namespace ddz {
 
@@ -131,6 +132,48 @@ DDZ_DEV void step_stats(int64_t* stats, unsigned int sf, const int32_t* rewards,
     stat_add(stats, 5, over ? (winner == 1 ? rewards[1] : -rewards[1]) : 0);
     stat_add(stats, 6, over ? (winner == 1 ? -(rewards[0] + rewards[2]) : rewards[0] + rewards[2]) : 0);
     stat_add(stats, 7, (int)((sf >> 5) & 3) + extra_err);
+}
+
+
+// Decoupled look-back over the per-tile words: sum of the totals of all tiles before `t` (kLookBack windows of 32
+// predecessors per round trip), then publish this tile's inclusive prefix.  Never hangs: after 2^22 polls the tile flags
+// an error (stats[7]) and carries on with what it has.
+DDZ_DEV long long tile_lookback(const Workspace& ws, int t, unsigned long long epoch_tag, int total, int lane, int64_t* stats) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    long long base = 0;
+    if (t <= 0) return 0;
+    int p = t - 1;
+    unsigned int spins = 0;
+    bool finished = false;
+    while (!finished) {
+        unsigned long long w[kLookBack];
+#pragma unroll
+        for (int j = 0; j < kLookBack; j++) {
+            const int idx = p - 32 * j - lane;
+            w[j] = idx >= 0 ? ld_relaxed(&ws.tile[idx]) : (epoch_tag | kInclusive);   // before tile 0: prefix 0
+        }
+#pragma unroll
+        for (int j = 0; j < kLookBack; j++) {
+            if (finished) break;
+            const bool ok = ((w[j] >> 34) == (epoch_tag >> 34)) && ((w[j] >> 32) & 3ull) != 0;
+            if (!__all_sync(FULL, ok)) {    // not published yet: poll again from this window
+                __nanosleep(64);
+                if (++spins > (1u << 22)) { // never hang the GPU: flag the error and carry on
+                    if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                    finished = true;
+                }
+                break;
+            }
+            const unsigned int incmask = __ballot_sync(FULL, ((w[j] >> 32) & 3ull) == 2ull);
+            // lanes up to and including the nearest inclusive predecessor contribute
+            const int stop = incmask ? (__ffs(incmask) - 1) : 31;
+            base += warp_sum_ll(lane <= stop ? (long long)(unsigned int)w[j] : 0ll);
+            p -= 32;
+            if (incmask) finished = true;
+        }
+    }
+    if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
+    return base;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,48 +482,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                 sr.lead = rpack & 1; sr.cat = (rpack >> 1) & 127; sr.len = (rpack >> 8) & 255; sr.val = (rpack >> 16) & 255;
                 const int loc = __shfl_sync(FULL, local, src), nn = __shfl_sync(FULL, n, src);
                 WindowEmitter em{wbuf, loc - w0, win};
-                const int got = (MODE == kRaw) ? enumerate_legal_warp_long(sm_, sr, (rpack >> 24) & 1, lane, em)   // long lists
-                                               : enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em);
+                const int got = enumerate_legal_warp(sm_, sr, (rpack >> 24) & 1, lane, em);
                 disagree |= (got != nn);
             }
             __syncwarp();
             if (w0 == 0) trace(t, 7);
 
             if (w0 == 0) {
-                // look-back: kLookBack windows of 32 predecessor tiles per round trip
-                if (t > 0) {
-                    int p = t - 1;
-                    unsigned int spins = 0;
-                    bool finished = false;
-                    while (!finished) {
-                        unsigned long long w[kLookBack];
-#pragma unroll
-                        for (int j = 0; j < kLookBack; j++) {
-                            const int idx = p - 32 * j - lane;
-                            w[j] = idx >= 0 ? ld_relaxed(&ws.tile[idx]) : (epoch_tag | kInclusive);   // before tile 0: prefix 0
-                        }
-#pragma unroll
-                        for (int j = 0; j < kLookBack; j++) {
-                            if (finished) break;
-                            const bool ok = ((w[j] >> 34) == (epoch_tag >> 34)) && ((w[j] >> 32) & 3ull) != 0;
-                            if (!__all_sync(FULL, ok)) {    // not published yet: poll again from this window
-                                __nanosleep(64);
-                                if (++spins > (1u << 22)) { // never hang the GPU: flag the error and carry on
-                                    if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
-                                    finished = true;
-                                }
-                                break;
-                            }
-                            const unsigned int incmask = __ballot_sync(FULL, ((w[j] >> 32) & 3ull) == 2ull);
-                            // lanes up to and including the nearest inclusive predecessor contribute
-                            const int stop = incmask ? (__ffs(incmask) - 1) : 31;
-                            base += warp_sum_ll(lane <= stop ? (long long)(unsigned int)w[j] : 0ll);
-                            p -= 32;
-                            if (incmask) finished = true;
-                        }
-                    }
-                    if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | kInclusive | (unsigned int)(base + total));
-                }
+                base = tile_lookback(ws, t, epoch_tag, total, lane, stats);
                 if (valid) o.offsets[b] = (int32_t)(base + local);
                 if (t == nt - 1 && lane == 0) {
                     o.offsets[B] = (int32_t)(base + total);
@@ -510,6 +519,151 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         if (fin == nwarps - 1) {                            // the last warp of the launch re-arms the workspace
             ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = epoch + 1;
             if (STEP) ws.h->auto_step = (a.stepno == DDZ_STEPNO_AUTO ? autostep : a.stepno) + 1;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// r.get_moves for n independent (hand, last) pairs, long lists welcome (ddz_legal_moves; BASELINE config 5).
+// Warp tile = 32 pairs.  Phase A, one lane per pair: count moves and groups, write the hand's rank lists and its group
+// descriptors into the warp's shared-memory arena (ddz_flat.cuh).  Phase B, one lane per two consecutive moves of the
+// tile: 64 moves per warp iteration; which descriptor a move belongs to comes from a 64-bit bitmap of the group starts
+// inside the window (one coalesced load of the next 32 descriptors + two warp OR-reductions), never from a search; the
+// pair goes out as one aligned 16-byte store.  Arena rounds: as many whole hands as fit kFlatArena descriptors.
+// The CSR offsets come from the same decoupled look-back as k_env; its wait hides behind phase A of the first round.
+// ------------------------------------------------------------------------------------------------
+#ifndef DDZ_FLAT_WARPS
+#define DDZ_FLAT_WARPS 4
+#endif
+#ifndef DDZ_FLAT_ARENA
+#define DDZ_FLAT_ARENA 512
+#endif
+constexpr int kFlatWarps = DDZ_FLAT_WARPS;
+constexpr int kFlatArena = DDZ_FLAT_ARENA;      // >= 160: the most groups any 15-rank hand can have is 155
+__device__ const flat::SubsetTable g_subsets = flat::SubsetTable();
+
+struct __align__(16) FlatWarpSmem {
+    flat::Desc arena[kFlatArena + 2];
+    uint8_t lists[32 * flat::kListsPerHand * flat::kListStride];
+};
+
+__global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* __restrict__ hands,
+                                                                  const uint64_t* __restrict__ lasts, OutArgs o,
+                                                                  Workspace ws, int64_t* stats, int B) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ __align__(16) uint16_t s_table[(flat::kTableSize + 7) / 8 * 8];
+    __shared__ FlatWarpSmem s_warp[kFlatWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    FlatWarpSmem& sm = s_warp[wib];
+    for (int i = threadIdx.x; i < flat::kTableSize; i += kFlatWarps * 32) s_table[i] = g_subsets.v[i];
+    const int nt = (B + 31) / 32;
+    const unsigned int nwarps = gridDim.x * kFlatWarps;
+    int t = blockIdx.x * kFlatWarps + wib;
+    unsigned int epoch = 0;
+    if (lane == 0) {
+        if (!o.static_tiles) t = (int)atomicAdd(&ws.h->ticket, 1u);
+        epoch = ws.h->epoch;
+    }
+    if (!o.static_tiles) t = __shfl_sync(FULL, t, 0);
+    __syncthreads();                                        // the subset table is staged
+    if (t < nt) {
+        const int b = t * 32 + lane;
+        const bool valid = b < B;
+        uint64_t hand = 0, last = 0;
+        if (valid) { hand = hands[b]; last = lasts[b]; }
+        epoch = __shfl_sync(FULL, epoch, 0);
+        const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
+        const Masks hm = masks_of(hand);
+        const Rule ru = rule_of(last);
+        flat::CountSink cs;
+        if (valid) flat::walk_groups(hm, ru, last != 0, 4 * lane, cs);
+        const int n = cs.n, ng = cs.ng;
+        int inc = n, dinc = ng;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(FULL, inc, d), v = __shfl_up_sync(FULL, dinc, d);
+            if (lane >= d) { inc += u; dinc += v; }
+        }
+        const int local = inc - n, total = __shfl_sync(FULL, inc, 31);
+        const int dloc = dinc - ng, dtotal = __shfl_sync(FULL, dinc, 31);
+        if (lane == 0) st_relaxed(&ws.tile[t], epoch_tag | (t == 0 ? kInclusive : kAggregate) | (unsigned int)total);
+        if (valid) flat::write_lists(hm, 4 * lane, sm.lists);
+
+        long long base = 0, lim = 0;
+        int disagree = 0, h0 = 0;
+        bool first = true;
+#pragma unroll 1
+        while (h0 < 32) {
+            // ---- phase A of this round: the hands [h0, h1) whose descriptors fit the arena
+            const int D0 = __shfl_sync(FULL, dloc, h0);
+            const unsigned int fits = __ballot_sync(FULL, lane >= h0 && dloc + ng - D0 <= kFlatArena);
+            const int h1 = h0 + __popc(fits);
+            const int m0 = __shfl_sync(FULL, local, h0);
+            const int m1s = __shfl_sync(FULL, local, h1 & 31), d1s = __shfl_sync(FULL, dloc, h1 & 31);
+            const int m1 = h1 < 32 ? m1s : total, nd = (h1 < 32 ? d1s : dtotal) - D0;
+            if (h1 == h0) { disagree = 1; break; }           // cannot happen (a hand has at most 155 groups)
+            if (valid && lane >= h0 && lane < h1) {
+                flat::WriteSink wsk{sm.arena, dloc - D0, kFlatArena, (uint32_t)local};
+                flat::walk_groups(hm, ru, last != 0, 4 * lane, wsk);
+                disagree |= (wsk.d != dloc - D0 + ng) | (wsk.start != (uint32_t)(local + n));
+            }
+            if (lane == 0) { flat::Desc e; e.start = (uint32_t)m1; e.prm = 0; sm.arena[nd] = e; }
+            __syncwarp();
+            if (first) {
+                first = false;
+                base = tile_lookback(ws, t, epoch_tag, total, lane, stats);
+                if (valid) o.offsets[b] = (int32_t)(base + local);
+                if (t == nt - 1 && lane == 0) {
+                    o.offsets[B] = (int32_t)(base + total);
+                    if (stats) {
+                        atomicAdd((unsigned long long*)&stats[8], (unsigned long long)(base + total));
+                        if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
+                    }
+                }
+                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // moves of this tile that fit
+            }
+            // ---- phase B: moves [m0, mEnd) of the tile, 64 per iteration, lane <-> two consecutive list slots
+            const int mEnd = (int)min((long long)m1, lim);
+            int gcur = 0;
+#pragma unroll 1
+            for (int w0 = m0 - (int)((base + m0) & 1); w0 < mEnd; w0 += 64) {
+                uint32_t blo = 0, bhi = 0;
+                for (int gq = gcur + 1;; gq += 32) {        // group starts inside the window (descriptors after gcur)
+                    const int idx = gq + lane;
+                    const uint32_t rel = idx <= nd ? sm.arena[idx].start - (uint32_t)w0 : 64u;   // past the sentinel: none
+                    blo |= rel < 32u ? 1u << rel : 0u;
+                    bhi |= (rel >= 32u && rel < 64u) ? 1u << (rel - 32u) : 0u;
+                    if (!__shfl_sync(FULL, (int)(rel < 64u), 31)) break;
+                }
+                blo = __reduce_or_sync(FULL, blo); bhi = __reduce_or_sync(FULL, bhi);
+                const int x = 2 * lane;
+                const uint32_t mlo = x < 31 ? (2u << x) - 1u : 0xFFFFFFFFu, mhi = x < 32 ? 0u : (2u << (x - 32)) - 1u;
+                const int g0 = gcur + __popc(blo & mlo) + __popc(bhi & mhi);
+                const int g1 = g0 + (int)(((x + 1 < 32) ? (blo >> (x + 1)) : (bhi >> (x - 31))) & 1u);
+                const int i0 = w0 + x;
+                const bool v0 = i0 >= m0 && i0 < mEnd, v1 = i0 + 1 < mEnd;
+                if (v0 || v1) {
+                    uint64_t mv0, mv1;
+                    const flat::Desc d0 = sm.arena[g0], d1 = sm.arena[g1];
+                    const int c0 = (int)(sm.arena[g0 + 1].start - d0.start), c1 = (int)(sm.arena[g1 + 1].start - d1.start);
+                    flat::decode2(d0.prm, i0 - (int)d0.start, c0, v0, d1.prm, i0 + 1 - (int)d1.start, c1, v1, s_table, sm.lists, mv0, mv1);
+                    uint64_t* dst = o.actions_u64 + (base + i0);          // base + i0 is even: 16-byte aligned
+                    if (v0 && v1) *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(mv0, mv1);
+                    else if (v0) dst[0] = mv0;
+                    else dst[1] = mv1;
+                }
+                gcur += __popc(blo) + __popc(bhi);
+            }
+            __syncwarp();                                   // the arena is consumed before the next round overwrites it
+            h0 = h1;
+        }
+        stat_add(stats, 7, disagree);
+    }
+    if (lane == 0) {
+        const unsigned int fin = atomicAdd(&ws.h->finished, 1u);
+        if (fin == nwarps - 1) {                            // the last warp of the launch re-arms the workspace
+            ws.h->ticket = 0; ws.h->finished = 0; ws.h->epoch = epoch + 1;
             __threadfence();
         }
     }
@@ -1003,6 +1157,120 @@ int ddz_pipe_flush(ddz_pipe* p, void* stream) {
     return pipe_commit_refill(p, (cudaStream_t)stream, true);
 }
 
+// ---- host-buffer pipeline over several env groups ---------------------------------------------------
+// One native call per env-step of ALL groups of a GPU: one H2D of the step's entropy, one launch per group on the group's
+// own stream, one D2H of every group's r | done | cat.  3 G + 6 CUDA calls per step instead of 12 G (ddz_pipe_step per
+// group), so that eight groups are not host-bound.
+struct ddz_mpipe {
+    int G;
+    cudaStream_t h2d, d2h, refill;
+    cudaEvent_t in_ready[2], out_done[DDZ_PIPE_DEPTH], stage_full;
+    cudaEvent_t kdone[2][DDZ_MPIPE_MAX_GROUPS], committed[DDZ_MPIPE_MAX_GROUPS];
+    unsigned long long step;
+    bool stage_used;
+    struct { int8_t *dst_perm[DDZ_MPIPE_MAX_GROUPS], *dst_lord[DDZ_MPIPE_MAX_GROUPS]; int8_t *stage_perm, *stage_lord; bool active; } pending;
+};
+
+ddz_mpipe* ddz_mpipe_create(int groups) {
+    if (groups < 1 || groups > DDZ_MPIPE_MAX_GROUPS) { snprintf(g_err, sizeof g_err, "ddz_mpipe_create: 1..%d groups", DDZ_MPIPE_MAX_GROUPS); return nullptr; }
+    ddz_mpipe* p = new ddz_mpipe();
+    p->G = groups; p->step = 0; p->stage_used = false; p->pending.active = false;
+    bool ok = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->refill, cudaStreamNonBlocking) == cudaSuccess;
+    auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    mk(&p->in_ready[0]); mk(&p->in_ready[1]); mk(&p->stage_full);
+    for (cudaEvent_t& e : p->out_done) mk(&e);
+    for (int g = 0; g < groups; g++) { mk(&p->kdone[0][g]); mk(&p->kdone[1][g]); mk(&p->committed[g]); }
+    if (!ok) { cuda_fail(cudaGetLastError(), "ddz_mpipe_create"); delete p; return nullptr; }   // (a failed create leaks its few events)
+    return p;
+}
+void ddz_mpipe_destroy(ddz_mpipe* p) {
+    if (!p) return;
+    cudaStreamDestroy(p->h2d); cudaStreamDestroy(p->d2h); cudaStreamDestroy(p->refill);
+    cudaEventDestroy(p->in_ready[0]); cudaEventDestroy(p->in_ready[1]); cudaEventDestroy(p->stage_full);
+    for (cudaEvent_t e : p->out_done) cudaEventDestroy(e);
+    for (int g = 0; g < p->G; g++) { cudaEventDestroy(p->kdone[0][g]); cudaEventDestroy(p->kdone[1][g]); cudaEventDestroy(p->committed[g]); }
+    delete p;
+}
+// replace every group's pool slot by its part of the staged upload, each on the group's stream (between two of its steps)
+static int mpipe_commit_refill(ddz_mpipe* p, const ddz_group_step* gs, bool wait) {
+    if (!p->pending.active) return 0;
+    if (!wait && cudaEventQuery(p->stage_full) != cudaSuccess) { cudaGetLastError(); return 0; }   // still uploading
+    size_t row0 = 0;
+    for (int g = 0; g < p->G; g++) {
+        cudaStream_t st = (cudaStream_t)gs[g].stream;
+        const size_t rows = (size_t)gs[g].B;
+        DDZ_CUDA(cudaStreamWaitEvent(st, p->stage_full, 0), "wait stage_full");
+        DDZ_CUDA(cudaMemcpyAsync(p->pending.dst_perm[g], p->pending.stage_perm + 54 * row0, rows * 54, cudaMemcpyDeviceToDevice, st), "D2D perm");
+        DDZ_CUDA(cudaMemcpyAsync(p->pending.dst_lord[g], p->pending.stage_lord + row0, rows, cudaMemcpyDeviceToDevice, st), "D2D lord");
+        DDZ_CUDA(cudaEventRecord(p->committed[g], st), "record committed");
+        row0 += rows;
+    }
+    p->pending.active = false;
+    return 0;
+}
+
+int ddz_mpipe_step(ddz_mpipe* p, const ddz_group_step* gs, int variant, const void* host_choice, void* dev_choice,
+                   uint64_t seed, uint32_t stepno, const int32_t rewards[3], int pool_games,
+                   void* results_dev, void* results_host, int64_t* stats) {
+    if (!p || !gs || !host_choice || !dev_choice || !results_dev || !results_host) return DDZ_E_ARG;
+    size_t total = 0;
+    for (int g = 0; g < p->G; g++) { if (gs[g].B <= 0 || !gs[g].state) return DDZ_E_ARG; total += (size_t)gs[g].B; }
+    if (int rc = mpipe_commit_refill(p, gs, false)) return rc;
+    const int k = (int)(p->step & 1);
+    // the H2D of step s reuses dev_choice / results_dev of step s-2: wait until that step's results have left the device
+    if (p->step >= 2) DDZ_CUDA(cudaStreamWaitEvent(p->h2d, p->out_done[(p->step - 2) % DDZ_PIPE_DEPTH], 0), "wait out_done");
+    DDZ_CUDA(cudaMemcpyAsync(dev_choice, host_choice, total * 4, cudaMemcpyHostToDevice, p->h2d), "H2D entropy");
+    DDZ_CUDA(cudaEventRecord(p->in_ready[k], p->h2d), "record in_ready");
+    size_t off = 0;
+    for (int g = 0; g < p->G; g++) {
+        const ddz_group_step& q = gs[g];
+        cudaStream_t st = (cudaStream_t)q.stream;
+        const size_t B = (size_t)q.B;
+        DDZ_CUDA(cudaStreamWaitEvent(st, p->in_ready[k], 0), "wait in_ready");
+        char* rd = (char*)results_dev + 3 * off;
+        int rc = ddz_rollout_step(q.state, q.workspace, variant, q.prev_offsets, q.prev_actions_u64,
+                                  (const char*)dev_choice + 4 * off, DDZ_CHOICE_MOD, seed, q.env0, stepno, rewards, q.perm,
+                                  q.lord_pile, pool_games, (int8_t*)rd, (uint8_t*)rd + B, (int8_t*)rd + 2 * B, q.reward,
+                                  q.out_offsets, q.out_actions_u64, q.out_actions_f32, q.cap, q.face, stats, q.B, q.stream);
+        if (rc) return rc;
+        DDZ_CUDA(cudaEventRecord(p->kdone[k][g], st), "record kdone");
+        DDZ_CUDA(cudaStreamWaitEvent(p->d2h, p->kdone[k][g], 0), "wait kdone");
+        off += B;
+    }
+    DDZ_CUDA(cudaMemcpyAsync(results_host, results_dev, 3 * total, cudaMemcpyDeviceToHost, p->d2h), "D2H results");
+    DDZ_CUDA(cudaEventRecord(p->out_done[p->step % DDZ_PIPE_DEPTH], p->d2h), "record out_done");
+    p->step++;
+    return 0;
+}
+int ddz_mpipe_wait(ddz_mpipe* p, int slot) {
+    if (!p || slot < 0 || slot >= DDZ_PIPE_DEPTH) return DDZ_E_ARG;
+    DDZ_CUDA(cudaEventSynchronize(p->out_done[slot]), "ddz_mpipe_wait");
+    return 0;
+}
+int ddz_mpipe_refill(ddz_mpipe* p, const ddz_group_step* gs, int8_t* const* pool_perm_slot, int8_t* const* pool_lord_slot,
+                     const int8_t* host_perm, const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord) {
+    if (!p || !gs || !pool_perm_slot || !pool_lord_slot || !host_perm || !host_lord || !stage_perm || !stage_lord) return DDZ_E_ARG;
+    if (int rc = mpipe_commit_refill(p, gs, true)) return rc;             // an earlier upload still staged: commit it first
+    size_t total = 0;
+    for (int g = 0; g < p->G; g++) {
+        if (p->stage_used) DDZ_CUDA(cudaStreamWaitEvent(p->refill, p->committed[g], 0), "wait committed");
+        p->pending.dst_perm[g] = pool_perm_slot[g]; p->pending.dst_lord[g] = pool_lord_slot[g];
+        total += (size_t)gs[g].B;
+    }
+    DDZ_CUDA(cudaMemcpyAsync(stage_perm, host_perm, total * 54, cudaMemcpyHostToDevice, p->refill), "H2D perm");
+    DDZ_CUDA(cudaMemcpyAsync(stage_lord, host_lord, total, cudaMemcpyHostToDevice, p->refill), "H2D lord");
+    DDZ_CUDA(cudaEventRecord(p->stage_full, p->refill), "record stage_full");
+    p->pending.stage_perm = stage_perm; p->pending.stage_lord = stage_lord; p->pending.active = true;
+    p->stage_used = true;
+    return 0;
+}
+int ddz_mpipe_flush(ddz_mpipe* p, const ddz_group_step* gs) {
+    if (!p || !gs) return DDZ_E_ARG;
+    return mpipe_commit_refill(p, gs, true);
+}
+
 // ---- compressible row buffers ------------------------------------------------------------------------
 // The one-hot / face rows are floats that are 0 or 1 (or 0 or a scale): lines of them compress well.  Memory created with
 // CU_MEM_ALLOCATION_COMP_GENERIC is compressed by the L2 on its way to HBM (and expanded on the way back), which raises
@@ -1058,9 +1326,12 @@ int ddz_rows_free(void* ptr, size_t mapped_bytes) {
 int ddz_legal_moves(const uint64_t* hands, const uint64_t* lasts, void* workspace, int32_t* offsets,
                     uint64_t* actions_u64, int64_t cap, int64_t* stats, int n, void* stream) {
     if (!hands || !lasts || !workspace || !offsets || !actions_u64 || n <= 0 || cap < 0) return DDZ_E_ARG;
-    StepArgs a; memset(&a, 0, sizeof a);
+    if ((reinterpret_cast<uintptr_t>(actions_u64) & 15u) != 0) return DDZ_E_ARG;   // pairs of moves go out as 16-byte stores
     OutArgs o{offsets, actions_u64, nullptr, cap, nullptr, 0};
-    return launch_env<-1, kRaw>(nullptr, hands, lasts, a, o, workspace, stats, n, (cudaStream_t)stream);
+    const int grid = (ntiles(n) + kFlatWarps - 1) / kFlatWarps;
+    k_legal_flat<<<grid, kFlatWarps * 32, 0, (cudaStream_t)stream>>>(hands, lasts, o, ws_of(workspace), stats, n);
+    DDZ_LAUNCH_CHECK("k_legal_flat");
+    return 0;
 }
 
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream) {

@@ -13,30 +13,15 @@ import numpy as np
 import torch
 
 from . import _native as N
+from .deals import DEAL_SEED0, default_deals, random_deals, adversarial_pairs, ADVERSARIAL_POOL  # noqa: F401  (re-exported)
 
 VARIANT_CHANNELS = (4, 7, 9, 6)
 DEFAULT_REWARDS = (50, 100, 50)          # role 0 up, 1 lord, 2 down  (reference game.py:13-14)
-DEAL_SEED0 = 20260101                    # default deal stream: PCG64(DEAL_SEED0 + game).permutation(54)
 _SHIFTS = None
 
 
 def _shifts(device):
     return (torch.arange(15, device=device, dtype=torch.int64) * 4)
-
-
-def default_deals(first_game, n):
-    """The documented default shuffle stream: game g -> PCG64(20260101+g).permutation(54), lord_pile 0."""
-    perm = np.stack([np.random.Generator(np.random.PCG64(DEAL_SEED0 + first_game + i)).permutation(54)
-                     for i in range(n)]).astype(np.int8)
-    return perm, np.zeros(n, np.int8)
-
-
-def random_deals(n, seed, pool_games=1):
-    """Vectorised synthetic deals for large batches: int8 [pool_games*n, 54] permutations, random landlord pile."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    perm = rng.permuted(np.tile(np.arange(54, dtype=np.int8), (pool_games * n, 1)), axis=1)
-    lord = rng.integers(0, 3, size=pool_games * n, dtype=np.int8)
-    return perm, lord
 
 
 def pack_counts(counts):
@@ -106,7 +91,7 @@ class BatchedEnv:
     VARIANT = N.FACE_FIRST
 
     def __init__(self, num_envs=1, debug=False, seed=None, device=None, max_actions_per_env=None,
-                 rewards=DEFAULT_REWARDS, env0=0):
+                 rewards=DEFAULT_REWARDS, env0=0, stats=None):
         if not torch.cuda.is_available():
             raise N.DdzError("BatchedEnv needs a CUDA device: the env runs as sm_100a kernels, there is no CPU path")
         self.B = int(num_envs)
@@ -129,7 +114,8 @@ class BatchedEnv:
             self._face = N.row_tensor((B, self.C, 15, 4), dev)
             self._results = [StepResults(B, dev) for _ in range(2)]   # two sets: a D2H read of one may overlap the next step
             self._res = 0
-            self.stats = torch.zeros(16, dtype=torch.int64, device=dev)
+            # int64 [16] counters the kernels add to atomically; several envs (the groups of a GroupedEnv) may share one
+            self.stats = stats if stats is not None else torch.zeros(16, dtype=torch.int64, device=dev)
             self._rewards = torch.tensor(list(rewards), dtype=torch.int32, device="cpu")
         self._cur = 0            # which ping-pong list describes the current state
         self._fresh = False      # lists/face valid for the current state?
@@ -570,10 +556,14 @@ class GroupedEnv:
         self.B, self.G, self.Bg = int(num_envs), int(groups), int(num_envs) // int(groups)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.G)]
+        # ONE statistics vector for all groups: every kernel adds to it atomically, so reading the rank's counters (and
+        # the multi-GPU all-reduce, sharding.allreduce_stats) needs no reduction over the groups
+        self._stats = torch.zeros(16, dtype=torch.int64, device=self.device)
         self.envs = []
         for g in range(self.G):
             with torch.cuda.stream(self.streams[g]):
-                self.envs.append(env_cls(self.Bg, seed=seed, device=self.device, env0=env0 + g * self.Bg, **kw))
+                self.envs.append(env_cls(self.Bg, seed=seed, device=self.device, env0=env0 + g * self.Bg,
+                                         stats=self._stats, **kw))
         self.graphs = None
         self._pool = None
 
@@ -643,8 +633,8 @@ class GroupedEnv:
 
     @property
     def stats(self):
-        """int64 [16] summed over the groups (call join() / synchronize first)"""
-        return torch.stack([e.stats for e in self.envs]).sum(0)
+        """int64 [16], shared by all groups (call join() / synchronize before reading it)"""
+        return self._stats
 
 
 class HostRollout:
@@ -756,6 +746,129 @@ class HostRollout:
     def wait(results):
         N.check(N.lib.ddz_pipe_wait(results._pipe, results._slot), "ddz_pipe_wait")
         return results
+
+
+class GroupStepResults:
+    """Host view of one step's results of all groups (pinned): r | done | cat per group, group-major."""
+
+    def __init__(self, sizes, pin=True):
+        self.sizes = list(sizes)
+        self.nbytes = 3 * sum(self.sizes)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8)
+        if pin:
+            self.buf = self.buf.pin_memory()
+        self.r, self.done, self.cat = [], [], []
+        off = 0
+        for B in self.sizes:
+            self.r.append(self.buf[off:off + B].view(torch.int8).numpy())
+            self.done.append(self.buf[off + B:off + 2 * B].numpy())
+            self.cat.append(self.buf[off + 2 * B:off + 3 * B].view(torch.int8).numpy())
+            off += 3 * B
+
+
+class HostRolloutGroups:
+    """HostRollout for a GroupedEnv: ONE native call per env-step of all groups (ddz_mpipe_step) -- one H2D of the step's
+    entropy (pinned int32 [B], group-major = global env order), one launch per group on its stream, one D2H of every
+    group's r | done | cat into a ring of PIPE_DEPTH pinned buffers.  3 G + 6 CUDA calls per step instead of 12 G, so the
+    host keeps up with eight groups.  refill(slot, perm [B,54], lord [B]) uploads one slot of every group's deal pool."""
+
+    def __init__(self, ge):
+        import ctypes as C
+        self.ge, self.G, dev = ge, ge.G, ge.device
+        if ge._pool is None:
+            raise ValueError("prepare() the GroupedEnv first (it owns the device-resident deal pools)")
+        self.P = ge._pool[0][2]
+        self.sizes = [e.B for e in ge.envs]
+        B = sum(self.sizes)
+        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.results_d = [torch.zeros(3 * B, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.results_h = [GroupStepResults(self.sizes) for _ in range(N.PIPE_DEPTH)]
+        self.h2d_bytes, self.d2h_bytes = 4 * B, 3 * B
+        self._stage = None
+        with torch.cuda.device(dev):
+            self._pipe = N.lib.ddz_mpipe_create(self.G)
+        if not self._pipe:
+            raise N.DdzError("ddz_mpipe_create failed: %s" % N.lib.ddz_last_error().decode())
+        self.i = 0
+        for e in ge.envs:
+            e._ensure()
+        # the group descriptors are constant per list parity: marshal them once
+        self._gs = {}
+        for cur in (0, 1):
+            arr = (N.GroupStep * self.G)()
+            for g, e in enumerate(ge.envs):
+                nxt = 1 - cur
+                pg, lg, _ = ge._pool[g]
+                q = arr[g]
+                q.state, q.workspace = e._state.data_ptr(), e._ws.data_ptr()
+                q.prev_offsets, q.prev_actions_u64 = e._offsets[cur].data_ptr(), e._actions_u64[cur].data_ptr()
+                q.out_offsets, q.out_actions_u64 = e._offsets[nxt].data_ptr(), e._actions_u64[nxt].data_ptr()
+                q.out_actions_f32, q.face = e._actions_f32.data_ptr(), e._face.data_ptr()
+                q.perm, q.lord_pile = pg.data_ptr(), lg.data_ptr()
+                q.reward = e._results[nxt].reward.data_ptr()
+                q.cap, q.env0, q.B, q.stream = e.cap, e.env0, e.B, ge.streams[g].cuda_stream
+            self._gs[cur] = arr
+        e0 = ge.envs[0]
+        self._const = (C.c_int(e0.VARIANT), C.c_uint64(e0.seed), C.c_void_p(e0._rewards.data_ptr()), C.c_int(self.P),
+                       C.c_void_p(ge.stats.data_ptr()))
+        self._same_device = torch.cuda.current_device() == (dev.index or 0)
+
+    def __del__(self):
+        pipe, self._pipe = getattr(self, "_pipe", None), None
+        if pipe and N is not None and getattr(N, "lib", None) is not None:
+            N.lib.ddz_mpipe_destroy(pipe)
+
+    def step(self, entropy_h):
+        """entropy_h: pinned int32 [B] (global env order).  Returns the GroupStepResults this step fills; valid after
+        wait(results), reused PIPE_DEPTH steps later."""
+        ge, k = self.ge, self.i % N.PIPE_DEPTH
+        cur = ge.envs[0]._cur
+        variant, seed, rewards, P, stats = self._const
+        args = (self._pipe, self._gs[cur], variant, entropy_h.data_ptr(), self.entropy_d[self.i & 1].data_ptr(), seed,
+                ge.envs[0]._stepno, rewards, P, self.results_d[self.i & 1].data_ptr(), self.results_h[k].buf.data_ptr(), stats)
+        if self._same_device:
+            rc = N.lib.ddz_mpipe_step(*args)
+        else:
+            with torch.cuda.device(ge.device):
+                rc = N.lib.ddz_mpipe_step(*args)
+        if rc:
+            N.check(rc, "ddz_mpipe_step")
+        nxt = 1 - cur
+        for e in ge.envs:
+            e._cur, e._res, e._fresh, e._n_total = nxt, nxt, True, None
+            e._stepno += 1
+        res = self.results_h[k]
+        res._slot, res._pipe = k, self._pipe
+        self.i += 1
+        return res
+
+    @staticmethod
+    def wait(results):
+        N.check(N.lib.ddz_mpipe_wait(results._pipe, results._slot), "ddz_mpipe_wait")
+        return results
+
+    def refill(self, slot, perm, lord_pile, now=False):
+        """upload one slot of every group's deal pool from pinned host arrays perm int8 [B,54], lord_pile int8 [B]
+        (global env order); committed between two steps by the first step() that finds the upload complete"""
+        import ctypes as C
+        ge = self.ge
+        B = sum(self.sizes)
+        if self._stage is None:
+            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=ge.device),
+                           torch.empty(B, dtype=torch.int8, device=ge.device))
+        perm, lord_pile = torch.as_tensor(perm), torch.as_tensor(lord_pile)
+        self._keep = (perm, lord_pile)
+        pp = (C.c_void_p * self.G)(*[ge._pool[g][0][slot].data_ptr() for g in range(self.G)])
+        ll = (C.c_void_p * self.G)(*[ge._pool[g][1][slot].data_ptr() for g in range(self.G)])
+        with torch.cuda.device(ge.device):
+            N.check(N.lib.ddz_mpipe_refill(self._pipe, self._gs[0], pp, ll, perm.data_ptr(), lord_pile.data_ptr(),
+                                           self._stage[0].data_ptr(), self._stage[1].data_ptr()), "ddz_mpipe_refill")
+        if now:
+            self.flush()
+
+    def flush(self):
+        with torch.cuda.device(self.ge.device):
+            N.check(N.lib.ddz_mpipe_flush(self._pipe, self._gs[0]), "ddz_mpipe_flush")
 
 
 class BatchedEnvComplicated(BatchedEnv):

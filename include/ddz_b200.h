@@ -10,8 +10,10 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
- *   - the caller (PyTorch) owns every buffer; the library never allocates device memory and keeps no
- *     pointer after the call returns;
+ *   - the caller (PyTorch) owns every buffer the launchers touch, and no launcher keeps a pointer after it returns.
+ *     Two opt-in helpers do own resources: ddz_pipe_* / ddz_mpipe_* objects hold CUDA streams and events (and remember
+ *     the destination of a staged deal-pool upload until it is committed), and ddz_rows_alloc maps compressible device
+ *     memory that the caller frees with ddz_rows_free;
  *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default);
  *   - return value: 0 ok, <0 error (DDZ_E_*); no exceptions, nothing printed;
  *   - there is NO CPU fallback: without a CUDA device every launcher returns DDZ_E_CUDA.
@@ -195,6 +197,40 @@ int ddz_pipe_wait(ddz_pipe* p, int slot);
 int ddz_pipe_refill(ddz_pipe* p, int8_t* pool_perm_slot, int8_t* pool_lord_slot, const int8_t* host_perm,
                     const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord, int B, void* stream);
 int ddz_pipe_flush(ddz_pipe* p, void* stream);   /* commit a staged deal-pool upload now (stream waits for it) */
+
+/* ---- the same pipeline over several env groups of one GPU: ONE native call per env-step of all groups.
+ * The envs of a GPU run as G independent groups (own state, workspace, ping-pong lists, stream) so that one group's
+ * load-only prologue overlaps another group's store phase.  ddz_mpipe_step issues, for step s:
+ *   copy stream : H2D host_choice (pinned, sum(B_g) x 4 bytes, group-major) -> dev_choice (alternate two buffers by parity)
+ *   stream g    : wait; ddz_rollout_step of group g with its slice of dev_choice; r | done | cat of group g go to
+ *                 results_dev + 3 * (sum of B of the groups before g)   (r[B_g] | done[B_g] | cat[B_g])
+ *   copy stream : wait for all groups; D2H results_dev (3 x sum(B_g) bytes; alternate two buffers by parity) ->
+ *                 results_host (pinned; rotate up to DDZ_PIPE_DEPTH buffers, ddz_mpipe_wait(slot) blocks on the D2H of the
+ *                 latest step with step index % DDZ_PIPE_DEPTH == slot)
+ * i.e. 3 G + 6 CUDA calls per step.  `gs` describes the groups FOR THIS STEP (prev_* = lists of the current state, out_* =
+ * the other ping-pong set); reward (float32 [B_g][3], device) is optional and stays on the device.  stats may be one
+ * vector shared by all groups (the kernels add atomically).  ddz_mpipe_refill uploads one slot of every group's deal pool
+ * from ONE pinned host array (rows group-major) into a staging buffer; each group's slot is replaced on the group's
+ * stream by the first step that finds the upload complete, or by ddz_mpipe_flush / the next refill, which wait for it. */
+#define DDZ_MPIPE_MAX_GROUPS 16
+typedef struct {
+    void* state; void* workspace;
+    const int32_t* prev_offsets; const uint64_t* prev_actions_u64;
+    int32_t* out_offsets; uint64_t* out_actions_u64; float* out_actions_f32; float* face;
+    const int8_t* perm; const int8_t* lord_pile;   /* the group's deal pool [pool_games][B][54] / [pool_games][B] */
+    float* reward;                                 /* device, optional */
+    int64_t cap; uint64_t env0; int B; void* stream;
+} ddz_group_step;
+typedef struct ddz_mpipe ddz_mpipe;
+ddz_mpipe* ddz_mpipe_create(int groups);
+void ddz_mpipe_destroy(ddz_mpipe* p);
+int ddz_mpipe_step(ddz_mpipe* p, const ddz_group_step* gs, int variant, const void* host_choice, void* dev_choice,
+                   uint64_t seed, uint32_t stepno, const int32_t rewards[3], int pool_games,
+                   void* results_dev, void* results_host, int64_t* stats);
+int ddz_mpipe_wait(ddz_mpipe* p, int slot);
+int ddz_mpipe_refill(ddz_mpipe* p, const ddz_group_step* gs, int8_t* const* pool_perm_slot, int8_t* const* pool_lord_slot,
+                     const int8_t* host_perm, const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord);
+int ddz_mpipe_flush(ddz_mpipe* p, const ddz_group_step* gs);
 
 /* Optional allocator for the big float row buffers (actions_f32, face): device memory created compressible
  * (CU_MEM_ALLOCATION_COMP_GENERIC), so the L2 compresses the 0/1 thermometer rows on their way to HBM and expands them

@@ -612,6 +612,61 @@ int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t 
 }
 
 /* ------------------------------------------------------------------ */
+/* CPU baseline of the legal-move microbench (BASELINE config 5)        */
+/* ------------------------------------------------------------------ */
+/* r.get_moves (envi.py:111) for n independent packed (hand, last) pairs, `reps` passes, split over nthreads; every list is
+ * packed back to the product's uint64 format (that is the output a caller of the batched generator gets).  counts[n]
+ * (optional) receives the list lengths, *checksum an order-independent digest of every emitted move. */
+typedef struct { const uint64_t* hands; const uint64_t* lasts; int i0, i1, reps; int32_t* counts; int64_t moves;
+                 uint64_t checksum; double seconds; pthread_barrier_t* bar; } gm_job;
+static void* gm_worker(void* arg) {
+    gm_job* j = (gm_job*)arg;
+    int8_t* out = (int8_t*)malloc(DDZ_REF_MAX_LEGAL * 15);
+    uint64_t cs = 0; int64_t moves = 0;
+    pthread_barrier_wait(j->bar);
+    double t0 = now_s();
+    for (int rep = 0; rep < j->reps; rep++)
+        for (int i = j->i0; i < j->i1; i++) {
+            int8_t h[15], l[15];
+            ddz_ref_unpack(j->hands[i], h); ddz_ref_unpack(j->lasts[i], l);
+            int N = ddz_ref_get_moves_fast(h, l, out, DDZ_REF_MAX_LEGAL);
+            if (N > DDZ_REF_MAX_LEGAL) N = DDZ_REF_MAX_LEGAL;
+            for (int k = 0; k < N; k++) cs += ddz_ref_pack(out + 15 * k) * 0x9E3779B97F4A7C15ULL;
+            if (j->counts && rep == 0) j->counts[i] = N;
+            moves += N;
+        }
+    j->seconds = now_s() - t0; j->checksum = cs; j->moves = moves;
+    free(out);
+    return 0;
+}
+int64_t ddz_ref_get_moves_batch(const uint64_t* hands, const uint64_t* lasts, int n, int reps, int nthreads, int32_t* counts,
+                                uint64_t* checksum, double* seconds) {
+    ensure();
+    if (n <= 0 || reps < 1) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > n) nthreads = n;
+    gm_job* jobs = (gm_job*)calloc((size_t)nthreads, sizeof(gm_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    pthread_barrier_t bar; pthread_barrier_init(&bar, 0, (unsigned)nthreads);
+    for (int i = 0; i < nthreads; i++) {
+        jobs[i].hands = hands; jobs[i].lasts = lasts; jobs[i].reps = reps; jobs[i].counts = counts; jobs[i].bar = &bar;
+        jobs[i].i0 = (int)((int64_t)n * i / nthreads); jobs[i].i1 = (int)((int64_t)n * (i + 1) / nthreads);
+        pthread_create(&th[i], 0, gm_worker, &jobs[i]);
+    }
+    int64_t total = 0; uint64_t cs = 0; double sec = 0;
+    for (int i = 0; i < nthreads; i++) {
+        pthread_join(th[i], 0);
+        total += jobs[i].moves; cs += jobs[i].checksum;
+        if (jobs[i].seconds > sec) sec = jobs[i].seconds;
+    }
+    if (checksum) *checksum = cs;
+    if (seconds) *seconds = sec;
+    pthread_barrier_destroy(&bar);
+    free(jobs); free(th);
+    return total;
+}
+
+/* ------------------------------------------------------------------ */
 /* exhaustive bound on the length of a legal-move list                  */
 /* ------------------------------------------------------------------ */
 /* Lead-move count of a hand in closed form (popcount x binomial), the same arithmetic the device uses; checked

@@ -91,6 +91,8 @@ def lib():
         L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
                                       C.POINTER(C.c_double)]
         L.ddz_ref_rollout.restype = C.c_int64
+        L.ddz_ref_get_moves_batch.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, i32p, u64p, C.POINTER(C.c_double)]
+        L.ddz_ref_get_moves_batch.restype = C.c_int64
         L.ddz_ref_count_lead_closed.argtypes = [i8p]
         L.ddz_ref_max_lead_moves_exhaustive.argtypes = [C.c_int, i8p, C.POINTER(C.c_longlong)]
         _lib = L
@@ -240,6 +242,19 @@ def rollout(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_game
                               _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64),
                               C.byref(cs), C.byref(sec))
     return int(n), float(sec.value), stats, int(cs.value)
+
+
+def get_moves_batch(hands_packed, lasts_packed, reps=1, nthreads=1):
+    """CPU baseline of config 5: (moves emitted, seconds, counts int32[n], checksum) for packed uint64 pairs"""
+    h = np.ascontiguousarray(hands_packed, dtype=np.uint64)
+    l = np.ascontiguousarray(lasts_packed, dtype=np.uint64)
+    counts = np.zeros(len(h), np.int32)
+    cs, sec = C.c_uint64(0), C.c_double(0)
+    n = lib().ddz_ref_get_moves_batch(_ptr(h, C.c_uint64), _ptr(l, C.c_uint64), len(h), int(reps), int(nthreads),
+                                      _ptr(counts, C.c_int32), C.byref(cs), C.byref(sec))
+    if n < 0:
+        raise ValueError("get_moves_batch failed")
+    return int(n), float(sec.value), counts, int(cs.value)
 
 
 def count_lead_closed(hand):

@@ -1,20 +1,21 @@
 """A Q-network with the reference's input/output contract (net.py:81-102: face [N,C,15,4] or [C,15,4], actions [N,15,4]
 -> [N,1]) for tests of the batched Q-scoring shim.  Architecture as described in SURVEY.md section 2 (#4): the C face
 channels + 1 action channel go through (1,k) convolutions with stride (1,4), k = 1..4, and a (15,1) "shunzi"
-convolution, then two linear layers.  Written from that description for test purposes; weights are random."""
+convolution, then two linear layers (width = hidden = 256 gives NetCooperation's sizes, net.py:125-139: ~3.6 MFLOP per
+scored action).  Written from that description for test purposes; weights are random."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 
 class QNetLike(nn.Module):
-    def __init__(self, face_channels, width=32):
+    def __init__(self, face_channels, width=32, hidden=64):
         super().__init__()
         cin = face_channels + 1
         self.rank_convs = nn.ModuleList([nn.Conv2d(cin, width, (1, k), (1, 4)) for k in (1, 2, 3, 4)])
         self.line_conv = nn.Conv2d(cin, width, (15, 1), 1)
-        self.fc1 = nn.Linear(width * (15 + 4), 64)
-        self.fc2 = nn.Linear(64, 1)
+        self.fc1 = nn.Linear(width * (15 + 4), hidden)
+        self.fc2 = nn.Linear(hidden, 1)
 
     def forward(self, face, actions):
         if face.dim() == 3:
