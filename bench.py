@@ -505,7 +505,7 @@ def run_config4(args):
                     "api": "HostRolloutGroups.step(entropy_host): ONE native call per env-step of all groups (ddz_mpipe_step: one "
                            "H2D of the pinned entropy, one k_env launch per group on its stream, one D2H of r/done/cat -- the "
                            "reference step's return tuple -- on copy streams), results of step t-4 read by the host every step "
-                           "(ring of 4 pinned result buffers), refill(slot, perm_host, lord_host) uploads host-made deals "
+                           "(rings of 4 buffers on both sides), refill(slot, perm_host, lord_host) uploads host-made deals "
                            "every %d steps" % REFILL},
             "gpu_launches": K * NG,
             "verify": verdict,

@@ -21,7 +21,7 @@ if not os.path.exists(LIB_PATH):
         "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(nvcc, sm_100a). The batched env has no CPU fallback." % LIB_PATH)
 
-EXPORTS = ("ddz_abi_version", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
+EXPORTS = ("ddz_abi_version", "ddz_prob_form", "ddz_set_tile_order", "ddz_face_channels", "ddz_state_bytes", "ddz_workspace_bytes", "ddz_last_error",
            "ddz_reset", "ddz_observe", "ddz_step", "ddz_rollout_step", "ddz_legal_moves", "ddz_encode_actions",
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
            "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit", "ddz_rows_alloc", "ddz_rows_free",
@@ -35,6 +35,20 @@ if _missing:
 _vp, _i, _i64, _u64, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32
 
 lib.ddz_abi_version.restype = _i
+lib.ddz_prob_form.restype = _i
+lib.ddz_set_tile_order.argtypes = [_i]
+TILES_AUTO, TILES_TICKET = 0, 1
+
+
+def set_tile_order(mode):
+    """"auto" (default) or "ticket": ask for ticket-ordered tiles when other kernels (a Q-network, a collective) share the
+    GPU with the env launches (include/ddz_b200.h, ddz_set_tile_order).  Returns the previous mode."""
+    m = {"auto": TILES_AUTO, "ticket": TILES_TICKET}[mode] if isinstance(mode, str) else int(mode)
+    prev = lib.ddz_set_tile_order(m)
+    if prev < 0:
+        raise ValueError("unknown tile order %r" % (mode,))
+    return "ticket" if prev == TILES_TICKET else "auto"
+
 lib.ddz_face_channels.argtypes = [_i]
 lib.ddz_state_bytes.argtypes = [_i]
 lib.ddz_state_bytes.restype = C.c_size_t

@@ -5,9 +5,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("ddz_kernels.cu", "ddz_device.cuh")] + \
+SRC = [os.path.join(HERE, "csrc", f) for f in ("ddz_kernels.cu", "ddz_device.cuh", "ddz_flat.cuh")] + \
       [os.path.join(ROOT, "include", "ddz_b200.h")]
 LIB = os.path.join(HERE, "libddz_b200.so")
+LIB_FORM_B = os.path.join(HERE, "libddz_b200_formB.so")   # the other layout of the probability planes (-DDDZ_PROB_FORM_B)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -20,12 +21,14 @@ def nvcc_path():
     return p
 
 
-def build_native(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in SRC):
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC[0]]
+def build_native(force=False, verbose=False, form_b=False):
+    lib = LIB_FORM_B if form_b else LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in SRC):
+        return lib
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-DDDZ_PROB_FORM_B"] if form_b else []) + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", lib, SRC[0]]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -29,6 +29,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 
 #include "../../include/ddz_b200.h"
 #include "ddz_device.cuh"
@@ -73,6 +75,26 @@ DDZ_DEV bool kFaceSecond(int t) { return DDZ_PHASE_ORDER == 0 ? (t & 1) != 0 : D
 constexpr int kLookBack = DDZ_LOOKBACK;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
 
 enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
+
+// The two probability planes of a face (native get_state_prob, envi.py:94; get_state_prob_manual, server/core.py:26-33) are
+// "cards nobody has shown yet", scaled by the share of each opponent's hand.  Their layout inside a rank's four slots is
+// not pinned by anything in the reference (oracle/SEMANTICS.md):
+//   form A (default)        thermometer(unknown count), left-aligned like every other plane;
+//   form B (-DDDZ_PROB_FORM_B)  deck60 - known60 element-wise: the ones are RIGHT-aligned (jokers have one slot: unchanged).
+// Form B rows carry bit 3 in the nibbles of ranks 0..12 and read the reversed half of a 16-entry thermometer LUT.
+#ifdef DDZ_PROB_FORM_B
+constexpr int kProbForm = 1, kLutEntries = 16;
+constexpr uint64_t kProbMark = 0x0008888888888888ull;
+#else
+constexpr int kProbForm = 0, kLutEntries = 8;
+constexpr uint64_t kProbMark = 0ull;
+#endif
+// entry i of the thermometer LUT: i = count 0..4 -> {c>0, c>1, c>2, c>3}; i = 8 + count -> the same ones right-aligned
+DDZ_DEV float4 lut_entry(int i) {
+    const int c = i & 7;
+    return (i & 8) ? make_float4(c > 3 ? 1.f : 0.f, c > 2 ? 1.f : 0.f, c > 1 ? 1.f : 0.f, c > 0 ? 1.f : 0.f)
+                   : make_float4(c > 0 ? 1.f : 0.f, c > 1 ? 1.f : 0.f, c > 2 ? 1.f : 0.f, c > 3 ? 1.f : 0.f);
+}
 
 // workspace: header (ticket, finished, epoch) + one look-back word per warp tile.  Must be zero when first used.
 struct WsHeader { unsigned int ticket, finished, epoch, auto_step; };
@@ -137,10 +159,12 @@ DDZ_DEV void step_stats(int64_t* stats, unsigned int sf, const int32_t* rewards,
 
 // Decoupled look-back over the per-tile words: sum of the totals of all tiles before `t` (kLookBack windows of 32
 // predecessors per round trip), then publish this tile's inclusive prefix.  Never hangs: after 2^22 polls the tile flags
-// an error (stats[7]) and carries on with what it has.
-DDZ_DEV long long tile_lookback(const Workspace& ws, int t, unsigned long long epoch_tag, int total, int lane, int64_t* stats) {
+// an error (stats[7]), sets `timed_out` -- the caller then writes none of its rows, its base being unknown -- and carries on.
+DDZ_DEV long long tile_lookback(const Workspace& ws, int t, unsigned long long epoch_tag, int total, int lane, int64_t* stats,
+                                bool& timed_out) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     long long base = 0;
+    timed_out = false;
     if (t <= 0) return 0;
     int p = t - 1;
     unsigned int spins = 0;
@@ -160,7 +184,7 @@ DDZ_DEV long long tile_lookback(const Workspace& ws, int t, unsigned long long e
                 __nanosleep(64);
                 if (++spins > (1u << 22)) { // never hang the GPU: flag the error and carry on
                     if (lane == 0 && stats) atomicAdd((unsigned long long*)&stats[7], 1ull);
-                    finished = true;
+                    finished = true; timed_out = true;
                 }
                 break;
             }
@@ -267,7 +291,7 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
         planes[n++] = pick3(prev, e.recent[0], e.recent[1], e.recent[2]);
         planes[n++] = pick3(next, e.recent[0], e.recent[1], e.recent[2]);   // (role-2)%3 == next
     }
-    uint64_t unknown = kDeckPacked - taken - hand;
+    uint64_t unknown = (kDeckPacked - taken - hand) | kProbMark;
     planes[n++] = unknown;
     planes[n++] = unknown;
     int size1 = card_count(pick3(next, e.hand[0], e.hand[1], e.hand[2]));
@@ -275,6 +299,18 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
     int tot = size1 + size2;
     p[0] = tot > 0 ? __fdiv_rn((float)size1, (float)tot) : 0.f;
     p[1] = tot > 0 ? __fdiv_rn((float)size2, (float)tot) : 0.f;
+}
+
+// Cold path of the step phase: the chosen entry lies in the part of a list that an overflow of the action buffer dropped.
+// Not inlined: it must not cost the hot path registers or instruction-cache space.
+__device__ __noinline__ uint64_t cut_list_move(uint64_t hand, uint64_t last, int idx) {
+    return select_legal(masks_of(hand), rule_of(last), last != 0, idx);      // ~0 if idx is out of range
+}
+__device__ __noinline__ long long cut_list_find(uint64_t hand, uint64_t last, uint64_t want, int from, int cnt) {
+    const Masks m = masks_of(hand);
+    const Rule ru = rule_of(last);
+    for (int i = from; i < cnt; i++) if (select_legal(m, ru, last != 0, i) == want) return i;
+    return -1;
 }
 
 struct StepArgs {
@@ -302,7 +338,7 @@ struct WindowEmitter {   // enumerate_legal_warp functor: move number idx of the
 struct __align__(128) WarpSmem {
     FaceRow face[32 * 9];                                   // 4 608 B
     uint64_t moves[kWin];                                   // 2 560 B
-    float4 lut[8];
+    float4 lut[kLutEntries];
 };
 
 // V: face variant or -1 (no face).  MODE: see enum Mode.
@@ -333,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             epoch = ws.h->epoch; autostep = ws.h->auto_step;
         }
         if (!o.static_tiles) t = __shfl_sync(FULL, t, 0);
-        if (lane < 5) sm.lut[lane] = make_float4(lane > 0 ? 1.f : 0.f, lane > 1 ? 1.f : 0.f, lane > 2 ? 1.f : 0.f, lane > 3 ? 1.f : 0.f);
+        if (lane < kLutEntries) sm.lut[lane] = lut_entry(lane);
         __syncwarp();
     }
     if (t < nt) {
@@ -392,11 +428,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                     const uint64_t want = choice_raw;
                     const int have = a.prev_cap > 0 ? (int)max(0ll, min((long long)cnt, a.prev_cap - base)) : cnt;
                     for (int i = 0; i < have; i++) if (a.actions[base + i] == want) { idx = i; break; }
+                    if (idx < 0 && have < cnt) idx = cut_list_find(hand_to_move(e), trick_of(e), want, have, cnt);
                 }
-                if (a.prev_cap > 0 && idx >= 0 && (long long)base + idx >= a.prev_cap) idx = -1;   // dropped by an overflow
-                if (idx < 0 || idx >= cnt) { e.meta |= 0x20u; sf += 32u; }
+                // A list cut off by an overflow of the action buffer (stats[7] said so when it was written) does not stop
+                // the env: the entry that was dropped is recomputed in closed form from the state (select_legal).
+                const bool cut = a.prev_cap > 0 && idx >= 0 && (long long)base + idx >= a.prev_cap;
+                uint64_t mv = ~0ull;
+                if (idx >= 0 && idx < cnt) mv = cut ? cut_list_move(hand_to_move(e), trick_of(e), (int)idx) : a.actions[base + idx];
+                if (mv == ~0ull) { e.meta |= 0x20u; sf += 32u; }
                 else {
-                    StepOut so = apply_move(e, a.actions[base + idx], a.rewards);
+                    StepOut so = apply_move(e, mv, a.rewards);
                     o_r = so.r; o_cat = so.cat; rw0 = so.reward[0]; rw1 = so.reward[1]; rw2 = so.reward[2];
                     sf |= 1u | (so.pass ? 2u : 0u);
                     if (so.done) sf |= 4u | ((unsigned int)so.winner << 3);
@@ -489,7 +530,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             if (w0 == 0) trace(t, 7);
 
             if (w0 == 0) {
-                base = tile_lookback(ws, t, epoch_tag, total, lane, stats);
+                bool timed_out;
+                base = tile_lookback(ws, t, epoch_tag, total, lane, stats, timed_out);
                 if (valid) o.offsets[b] = (int32_t)(base + local);
                 if (t == nt - 1 && lane == 0) {
                     o.offsets[B] = (int32_t)(base + total);
@@ -498,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
                         if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
                     }
                 }
-                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // rows of this warp that fit
+                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0 || timed_out) lim = 0;   // rows of this warp that fit
                 trace(t, 5);
             }
 
@@ -538,6 +580,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
 #endif
 #ifndef DDZ_FLAT_ARENA
 #define DDZ_FLAT_ARENA 512
+#endif
+#ifndef DDZ_FLAT_PAIR
+#define DDZ_FLAT_PAIR 0     // 1: the two moves of a lane are decoded in one interleaved loop (measured 12 % slower), 0: one after the other
 #endif
 constexpr int kFlatWarps = DDZ_FLAT_WARPS;
 constexpr int kFlatArena = DDZ_FLAT_ARENA;      // >= 160: the most groups any 15-rank hand can have is 155
@@ -612,7 +657,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* 
             __syncwarp();
             if (first) {
                 first = false;
-                base = tile_lookback(ws, t, epoch_tag, total, lane, stats);
+                bool timed_out;
+                base = tile_lookback(ws, t, epoch_tag, total, lane, stats, timed_out);
                 if (valid) o.offsets[b] = (int32_t)(base + local);
                 if (t == nt - 1 && lane == 0) {
                     o.offsets[B] = (int32_t)(base + total);
@@ -621,7 +667,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* 
                         if (base + total > o.cap) atomicAdd((unsigned long long*)&stats[7], 1ull);
                     }
                 }
-                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0) lim = 0;   // moves of this tile that fit
+                lim = o.cap - base; if (lim > total) lim = total; if (lim < 0 || timed_out) lim = 0;   // moves of this tile that fit
             }
             // ---- phase B: moves [m0, mEnd) of the tile, 64 per iteration, lane <-> two consecutive list slots
             const int mEnd = (int)min((long long)m1, lim);
@@ -647,7 +693,12 @@ __global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* 
                     uint64_t mv0, mv1;
                     const flat::Desc d0 = sm.arena[g0], d1 = sm.arena[g1];
                     const int c0 = (int)(sm.arena[g0 + 1].start - d0.start), c1 = (int)(sm.arena[g1 + 1].start - d1.start);
+#if DDZ_FLAT_PAIR
                     flat::decode2(d0.prm, i0 - (int)d0.start, c0, v0, d1.prm, i0 + 1 - (int)d1.start, c1, v1, s_table, sm.lists, mv0, mv1);
+#else
+                    mv0 = v0 ? flat::decode(d0.prm, i0 - (int)d0.start, c0, s_table, sm.lists) : 0ull;
+                    mv1 = v1 ? flat::decode(d1.prm, i0 + 1 - (int)d1.start, c1, s_table, sm.lists) : 0ull;
+#endif
                     uint64_t* dst = o.actions_u64 + (base + i0);          // base + i0 is even: 16-byte aligned
                     if (v0 && v1) *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(mv0, mv1);
                     else if (v0) dst[0] = mv0;
@@ -691,8 +742,8 @@ __global__ void __launch_bounds__(kEnvs) k_face(const void* state, float4* __res
         int row = i / 15, rank = i - row * 15;
         int env = row / C, c = row - env * C;
         float s = (c >= C - 2) ? s_p[env * 2 + (c - (C - 2))] : 1.f;
-        uint32_t cnt = (uint32_t)(s_planes[row] >> (4 * rank)) & 15u;
-        dst[i] = make_float4(cnt > 0 ? s : 0.f, cnt > 1 ? s : 0.f, cnt > 2 ? s : 0.f, cnt > 3 ? s : 0.f);
+        const float4 q = lut_entry((int)((uint32_t)(s_planes[row] >> (4 * rank)) & 15u));
+        dst[i] = make_float4(q.x * s, q.y * s, q.z * s, q.w * s);
     }
 }
 
@@ -707,11 +758,10 @@ __global__ void __launch_bounds__(128) k_state_actions(const void* state, const 
                                                        float4* __restrict__ out, int B) {
     constexpr int C = FaceCfg<V>::C;
     __shared__ FaceRow s_face[4][C];
-    __shared__ float4 s_lut[8];
+    __shared__ float4 s_lut[kLutEntries];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int b = blockIdx.x * 4 + wib;
-    if (threadIdx.x < 5) s_lut[threadIdx.x] = make_float4(threadIdx.x > 0 ? 1.f : 0.f, threadIdx.x > 1 ? 1.f : 0.f,
-                                                          threadIdx.x > 2 ? 1.f : 0.f, threadIdx.x > 3 ? 1.f : 0.f);
+    if (threadIdx.x < kLutEntries) s_lut[threadIdx.x] = lut_entry(threadIdx.x);
     const bool live = b < B && (!env_mask || env_mask[b]);
     int src = 0, n = 0;
     if (live) { src = offsets[b]; n = offsets[b + 1] - src; }
@@ -845,6 +895,7 @@ __global__ void __launch_bounds__(256) k_select_actions(const float* __restrict_
 using namespace ddz;
 
 static thread_local char g_err[256] = "";
+static std::atomic<int> g_tile_order{DDZ_TILES_AUTO};
 static int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
     return DDZ_E_CUDA;
@@ -861,17 +912,26 @@ static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts,
     const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem);
     Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
     const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
-    static int resident = -1;      // CTAs of this instantiation that fit on the device at once (per process, device 0's shape)
+    // CTAs of this instantiation that fit on the device at once, per device (the shapes of the devices of a box may differ)
+    static std::atomic<int> resident_of[64];
+    static std::once_flag once;
+    std::call_once(once, [] { for (auto& r : resident_of) r.store(-1); });
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    int resident = dev < 64 ? resident_of[dev].load(std::memory_order_relaxed) : -1;
     if (resident < 0) {
-        int per_sm = 0, dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        int per_sm = 0, sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env<V, MODE>, kThreads, smem) != cudaSuccess)
             return cuda_fail(cudaGetLastError(), "occupancy query");
         resident = per_sm * sms;
+        if (dev < 64) resident_of[dev].store(resident, std::memory_order_relaxed);
     }
     OutArgs oo = o;
-    oo.static_tiles = (grid <= resident) ? 1 : 0;
+    // tile = launch position needs every lower tile to be running or done when a tile waits on it: true when the whole grid
+    // is resident at once (and CTAs are dispatched in launch order, as they are in practice).  A caller whose other kernels
+    // share the GPU asks for tickets instead (ddz_set_tile_order): correct under any dispatch order.
+    oo.static_tiles = (g_tile_order.load(std::memory_order_relaxed) == DDZ_TILES_AUTO && grid <= resident) ? 1 : 0;
     k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, oo, ws, stats, B);
     DDZ_LAUNCH_CHECK("k_env");
     return 0;
@@ -934,6 +994,11 @@ int ddz_debug_set_trace(unsigned long long* buf) {
 }
 #endif
 int ddz_abi_version(void) { return DDZ_ABI_VERSION; }
+int ddz_prob_form(void) { return kProbForm; }
+int ddz_set_tile_order(int mode) {
+    if (mode != DDZ_TILES_AUTO && mode != DDZ_TILES_TICKET) return DDZ_E_ARG;
+    return g_tile_order.exchange(mode);
+}
 int ddz_face_channels(int variant) {
     static const int C[4] = {4, 7, 9, 6};
     return (variant < 0 || variant > 3) ? DDZ_E_ARG : C[variant];
@@ -1158,14 +1223,20 @@ int ddz_pipe_flush(ddz_pipe* p, void* stream) {
 }
 
 // ---- host-buffer pipeline over several env groups ---------------------------------------------------
-// One native call per env-step of ALL groups of a GPU: one H2D of the step's entropy, one launch per group on the group's
-// own stream, one D2H of every group's r | done | cat.  3 G + 6 CUDA calls per step instead of 12 G (ddz_pipe_step per
-// group), so that eight groups are not host-bound.
+// One native call per env-step of ALL groups of a GPU:
+//   copy stream  : H2D of the step's pinned entropy (one copy for all groups)                      -> event in_ready
+//   stream g     : wait in_ready; k_env of group g (its slice of the entropy; r|done|cat -> results_dev) -> event kdone[g]
+//   copy stream 2: wait every kdone[g]; D2H of all groups' results (one copy)                       -> event out_done[slot]
+// dev_choice / results_dev / results_host rotate through DDZ_PIPE_DEPTH buffers, and the step that reuses a slot first
+// makes sure (on the HOST, normally a no-op) that the D2H of the step that used it before has landed -- so no stream ever
+// waits for an older step: the groups stay unsynchronised, the only cross-stream edges are "entropy is there" and "this
+// step's kernels are done".  4 G + 4 CUDA calls per step (12 G with ddz_pipe_step per group).
 struct ddz_mpipe {
     int G;
     cudaStream_t h2d, d2h, refill;
-    cudaEvent_t in_ready[2], out_done[DDZ_PIPE_DEPTH], stage_full;
-    cudaEvent_t kdone[2][DDZ_MPIPE_MAX_GROUPS], committed[DDZ_MPIPE_MAX_GROUPS];
+    cudaEvent_t in_ready[DDZ_PIPE_DEPTH], out_done[DDZ_PIPE_DEPTH], stage_full;
+    cudaEvent_t kdone[DDZ_PIPE_DEPTH][DDZ_MPIPE_MAX_GROUPS], committed[DDZ_MPIPE_MAX_GROUPS];
+    bool out_pending[DDZ_PIPE_DEPTH];
     unsigned long long step;
     bool stage_used;
     struct { int8_t *dst_perm[DDZ_MPIPE_MAX_GROUPS], *dst_lord[DDZ_MPIPE_MAX_GROUPS]; int8_t *stage_perm, *stage_lord; bool active; } pending;
@@ -1179,18 +1250,24 @@ ddz_mpipe* ddz_mpipe_create(int groups) {
               cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&p->refill, cudaStreamNonBlocking) == cudaSuccess;
     auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-    mk(&p->in_ready[0]); mk(&p->in_ready[1]); mk(&p->stage_full);
-    for (cudaEvent_t& e : p->out_done) mk(&e);
-    for (int g = 0; g < groups; g++) { mk(&p->kdone[0][g]); mk(&p->kdone[1][g]); mk(&p->committed[g]); }
+    mk(&p->stage_full);
+    for (int k = 0; k < DDZ_PIPE_DEPTH; k++) { mk(&p->in_ready[k]); mk(&p->out_done[k]); p->out_pending[k] = false; }
+    for (int g = 0; g < groups; g++) {
+        mk(&p->committed[g]);
+        for (int k = 0; k < DDZ_PIPE_DEPTH; k++) mk(&p->kdone[k][g]);
+    }
     if (!ok) { cuda_fail(cudaGetLastError(), "ddz_mpipe_create"); delete p; return nullptr; }   // (a failed create leaks its few events)
     return p;
 }
 void ddz_mpipe_destroy(ddz_mpipe* p) {
     if (!p) return;
     cudaStreamDestroy(p->h2d); cudaStreamDestroy(p->d2h); cudaStreamDestroy(p->refill);
-    cudaEventDestroy(p->in_ready[0]); cudaEventDestroy(p->in_ready[1]); cudaEventDestroy(p->stage_full);
-    for (cudaEvent_t e : p->out_done) cudaEventDestroy(e);
-    for (int g = 0; g < p->G; g++) { cudaEventDestroy(p->kdone[0][g]); cudaEventDestroy(p->kdone[1][g]); cudaEventDestroy(p->committed[g]); }
+    cudaEventDestroy(p->stage_full);
+    for (int k = 0; k < DDZ_PIPE_DEPTH; k++) { cudaEventDestroy(p->in_ready[k]); cudaEventDestroy(p->out_done[k]); }
+    for (int g = 0; g < p->G; g++) {
+        cudaEventDestroy(p->committed[g]);
+        for (int k = 0; k < DDZ_PIPE_DEPTH; k++) cudaEventDestroy(p->kdone[k][g]);
+    }
     delete p;
 }
 // replace every group's pool slot by its part of the staged upload, each on the group's stream (between two of its steps)
@@ -1218,35 +1295,38 @@ int ddz_mpipe_step(ddz_mpipe* p, const ddz_group_step* gs, int variant, const vo
     size_t total = 0;
     for (int g = 0; g < p->G; g++) { if (gs[g].B <= 0 || !gs[g].state) return DDZ_E_ARG; total += (size_t)gs[g].B; }
     if (int rc = mpipe_commit_refill(p, gs, false)) return rc;
-    const int k = (int)(p->step & 1);
-    // the H2D of step s reuses dev_choice / results_dev of step s-2: wait until that step's results have left the device
-    if (p->step >= 2) DDZ_CUDA(cudaStreamWaitEvent(p->h2d, p->out_done[(p->step - 2) % DDZ_PIPE_DEPTH], 0), "wait out_done");
+    const int slot = (int)(p->step % DDZ_PIPE_DEPTH);
+    // the buffers of this slot were last used DDZ_PIPE_DEPTH steps ago: that step's results must have left the device
+    if (p->out_pending[slot]) { DDZ_CUDA(cudaEventSynchronize(p->out_done[slot]), "slot reuse"); p->out_pending[slot] = false; }
     DDZ_CUDA(cudaMemcpyAsync(dev_choice, host_choice, total * 4, cudaMemcpyHostToDevice, p->h2d), "H2D entropy");
-    DDZ_CUDA(cudaEventRecord(p->in_ready[k], p->h2d), "record in_ready");
+    DDZ_CUDA(cudaEventRecord(p->in_ready[slot], p->h2d), "record in_ready");
     size_t off = 0;
     for (int g = 0; g < p->G; g++) {
         const ddz_group_step& q = gs[g];
         cudaStream_t st = (cudaStream_t)q.stream;
         const size_t B = (size_t)q.B;
-        DDZ_CUDA(cudaStreamWaitEvent(st, p->in_ready[k], 0), "wait in_ready");
+        DDZ_CUDA(cudaStreamWaitEvent(st, p->in_ready[slot], 0), "wait in_ready");
         char* rd = (char*)results_dev + 3 * off;
         int rc = ddz_rollout_step(q.state, q.workspace, variant, q.prev_offsets, q.prev_actions_u64,
                                   (const char*)dev_choice + 4 * off, DDZ_CHOICE_MOD, seed, q.env0, stepno, rewards, q.perm,
                                   q.lord_pile, pool_games, (int8_t*)rd, (uint8_t*)rd + B, (int8_t*)rd + 2 * B, q.reward,
                                   q.out_offsets, q.out_actions_u64, q.out_actions_f32, q.cap, q.face, stats, q.B, q.stream);
         if (rc) return rc;
-        DDZ_CUDA(cudaEventRecord(p->kdone[k][g], st), "record kdone");
-        DDZ_CUDA(cudaStreamWaitEvent(p->d2h, p->kdone[k][g], 0), "wait kdone");
+        DDZ_CUDA(cudaEventRecord(p->kdone[slot][g], st), "record kdone");
+        DDZ_CUDA(cudaStreamWaitEvent(p->d2h, p->kdone[slot][g], 0), "wait kdone");
         off += B;
     }
     DDZ_CUDA(cudaMemcpyAsync(results_host, results_dev, 3 * total, cudaMemcpyDeviceToHost, p->d2h), "D2H results");
-    DDZ_CUDA(cudaEventRecord(p->out_done[p->step % DDZ_PIPE_DEPTH], p->d2h), "record out_done");
+    DDZ_CUDA(cudaEventRecord(p->out_done[slot], p->d2h), "record out_done");
+    p->out_pending[slot] = true;
     p->step++;
     return 0;
 }
 int ddz_mpipe_wait(ddz_mpipe* p, int slot) {
     if (!p || slot < 0 || slot >= DDZ_PIPE_DEPTH) return DDZ_E_ARG;
+    if (!p->out_pending[slot]) return 0;
     DDZ_CUDA(cudaEventSynchronize(p->out_done[slot]), "ddz_mpipe_wait");
+    p->out_pending[slot] = false;
     return 0;
 }
 int ddz_mpipe_refill(ddz_mpipe* p, const ddz_group_step* gs, int8_t* const* pool_perm_slot, int8_t* const* pool_lord_slot,

@@ -117,6 +117,7 @@ class BatchedEnv:
             # int64 [16] counters the kernels add to atomically; several envs (the groups of a GroupedEnv) may share one
             self.stats = stats if stats is not None else torch.zeros(16, dtype=torch.int64, device=dev)
             self._rewards = torch.tensor(list(rewards), dtype=torch.int32, device="cpu")
+        self._buf_gen = 0        # bumped when the list buffers are reallocated (cached pointers / captured graphs are stale)
         self._cur = 0            # which ping-pong list describes the current state
         self._fresh = False      # lists/face valid for the current state?
         self._n_total = None
@@ -219,13 +220,33 @@ class BatchedEnv:
 
     @property
     def num_actions(self):
-        """total number of legal moves over the batch (host int; synchronises)."""
+        """total number of legal moves over the batch (host int; synchronises).  If the lists did not fit the action buffer
+        (max_actions_per_env below the worst case; the launch said so in stats[7]) the buffers are grown to what the
+        offsets ask for and the state is observed once more: the caller always gets complete lists."""
         self._ensure()
         if self._n_total is None:
-            self._n_total = int(self._offsets[self._cur][self.B].item())
-            if self._n_total > self.cap:
-                raise N.DdzError("legal-move lists overflowed the action buffer (%d > cap %d)" % (self._n_total, self.cap))
+            n = int(self._offsets[self._cur][self.B].item())
+            if n > self.cap:
+                self._grow(n)
+                self.observe()
+                n = int(self._offsets[self._cur][self.B].item())
+                if n > self.cap:
+                    raise N.DdzError("legal-move lists overflowed the action buffer (%d > cap %d)" % (n, self.cap))
+            self._n_total = n
         return self._n_total
+
+    def _grow(self, need):
+        """reallocate the list buffers for at least `need` moves (+25 %); the packed lists of the other ping-pong set are kept"""
+        cap = min(self.B * N.MAX_LEGAL, max(int(need) + int(need) // 4, self.cap + 1))
+        dev = self.device
+        with torch.cuda.device(dev):
+            for i in range(2):
+                new = torch.zeros(cap, dtype=torch.int64, device=dev)
+                new[: self.cap] = self._actions_u64[i]
+                self._actions_u64[i] = new
+            self._actions_f32 = N.row_tensor((cap, 15, 4), dev)
+        self.cap = cap
+        self._buf_gen += 1
 
     @property
     def face(self):
@@ -284,6 +305,10 @@ class BatchedEnv:
 
     def _step(self, choice, mode):
         self._ensure()
+        if self.cap < self.B * N.MAX_LEGAL:
+            # ddz_step reads the lists without knowing their capacity: with a reduced max_actions_per_env make sure the
+            # observation was complete (num_actions raises on an overflow) before any index is resolved against it
+            self.num_actions
         with torch.cuda.device(self.device):
             N.check(N.lib.ddz_step(self._p(self._state), self._p(self._offsets[self._cur]),
                                    self._p(self._actions_u64[self._cur]), self._p(choice), mode,
@@ -380,6 +405,12 @@ class BatchedEnv:
         self._stepno += int(max_steps)
         return steps
 
+    def _sync_auto_step(self):
+        """write the host's step number into the device-side Philox step counter (workspace header, uint32 at byte 12).
+        Only the fused launches keep that counter up to date; step() / step_random() / playout() advance the step number
+        on the host alone, so a graph replay (stepno = DDZ_STEPNO_AUTO) after one of them re-arms the counter first."""
+        self._ws[3:4].fill_(int(self._stepno) & 0x7FFFFFFF)
+
     def _check_errors(self, what):
         if self.debug:
             err = int(self.stats[7].item())
@@ -445,10 +476,15 @@ class BatchedEnv:
         """native get_state_prob_manual (server/core.py:26-33): known60 = thermometer one-hot [.., 60] of (played cards +
         own hand), size1 / size2 = cards left of the next / next-next player.  float32 [.., 120] (SURVEY App. A form A)."""
         k = torch.as_tensor(known60, device=device).reshape(-1, 15, 4)
-        known = (k != 0).sum(-1)
-        total = torch.tensor([4] * 13 + [1, 1], device=k.device)
-        unknown = (total - known).clamp_(min=0)
-        thermo = (torch.arange(4, device=k.device)[None, None, :] < unknown[:, :, None]).to(torch.float32).reshape(-1, 60)
+        if N.lib.ddz_prob_form() == 1:     # form B build: deck60 - known60, element by element (DESIGN.md 2: the one layout nothing in the reference pins)
+            deck = torch.ones(15, 4, device=k.device)
+            deck[13:, 1:] = 0
+            thermo = (deck - (k != 0).to(torch.float32)).clamp_(min=0).reshape(-1, 60)
+        else:                              # form A: thermometer of the number of unknown cards per rank
+            known = (k != 0).sum(-1)
+            total = torch.tensor([4] * 13 + [1, 1], device=k.device)
+            unknown = (total - known).clamp_(min=0)
+            thermo = (torch.arange(4, device=k.device)[None, None, :] < unknown[:, :, None]).to(torch.float32).reshape(-1, 60)
         s1 = torch.as_tensor(size1, device=k.device, dtype=torch.float32).reshape(-1, 1)
         s2 = torch.as_tensor(size2, device=k.device, dtype=torch.float32).reshape(-1, 1)
         tot = s1 + s2
@@ -468,12 +504,13 @@ class BatchedEnv:
     def state_dict(self):
         """Exact-resume checkpoint of the env (the reference never checkpoints env state)."""
         return {"state": self._state.clone(), "stepno": self._stepno, "games_dealt": self._games_dealt,
-                "stats": self.stats.clone()}
+                "stats": self.stats.clone()}      # the device-side step counter is re-derived from stepno on load
 
     def load_state_dict(self, sd):
         self._state.copy_(sd["state"])
         self.stats.copy_(sd["stats"])
         self._stepno, self._games_dealt = int(sd["stepno"]), int(sd["games_dealt"])
+        self._sync_auto_step()
         self._fresh = False
 
     # ------------------------------------------------------------------ converters (envi.py:118-157)
@@ -527,15 +564,21 @@ class GraphedRollout:
         self._keep = (perm, lord_pile, entropy)
         self.graph = torch.cuda.CUDAGraph()
         stepno = env._stepno
+        env._sync_auto_step()
+        torch.cuda.synchronize(env.device)
         with torch.cuda.graph(self.graph):
             env.rollout_step(**kw)
             env.rollout_step(**kw)
         env._stepno = stepno          # capture launched nothing; the device counter still holds `stepno`
+        self._next = stepno
 
     def replay(self):
         """two env-steps"""
+        if self.env._stepno != self._next:        # stepped by other means since the last replay
+            self.env._sync_auto_step()
         self.graph.replay()
         self.env._stepno += 2
+        self._next = self.env._stepno
         self.env._n_total = None
 
 
@@ -617,19 +660,27 @@ class GroupedEnv:
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             stepno = env._stepno
+            with torch.cuda.stream(self.streams[g]):
+                env._sync_auto_step()
+            torch.cuda.synchronize(self.device)
             with torch.cuda.graph(graph, stream=self.streams[g]):
                 for _ in range(self.steps_per_graph):
                     env.rollout_step(perm=pg, lord_pile=lg, pool_games=P, auto_step=True)
             env._stepno = stepno
+            env._graph_next = stepno
             self.graphs.append(graph)
         torch.cuda.synchronize(self.device)
 
     def replay(self):
         for g, graph in enumerate(self.graphs):
+            env = self.envs[g]
             with torch.cuda.stream(self.streams[g]):
+                if env._stepno != env._graph_next:     # stepped by other means (eager step, host pipe) since the last replay
+                    env._sync_auto_step()
                 graph.replay()
-            self.envs[g]._stepno += self.steps_per_graph
-            self.envs[g]._n_total = None
+            env._stepno += self.steps_per_graph
+            env._graph_next = env._stepno
+            env._n_total = None
 
     @property
     def stats(self):
@@ -716,12 +767,13 @@ class HostRollout:
                     vp(env._offsets[nxt]), vp(env._actions_u64[nxt]), vp(env._actions_f32), C.c_int64(env.cap),
                     vp(env._face), vp(env.stats), C.c_int(env.B), C.c_void_p(self._main.cuda_stream)]
         self._same_device = torch.cuda.current_device() == (env.device.index or 0)
+        self._gen = env._buf_gen
 
     def step(self, entropy_h):
         """entropy_h: pinned int32 [B].  Returns the StepResults (pinned host views) this step will fill; they are
         valid after `wait(results)` (or any later synchronisation) and are reused PIPE_DEPTH steps later."""
         env, k = self.env, self.i % N.PIPE_DEPTH
-        if self._argv is None:
+        if self._argv is None or self._gen != env._buf_gen:
             self._build_args()
         cur = env._cur
         argv = self._argv[(cur, k)]
@@ -768,9 +820,10 @@ class GroupStepResults:
 
 class HostRolloutGroups:
     """HostRollout for a GroupedEnv: ONE native call per env-step of all groups (ddz_mpipe_step) -- one H2D of the step's
-    entropy (pinned int32 [B], group-major = global env order), one launch per group on its stream, one D2H of every
-    group's r | done | cat into a ring of PIPE_DEPTH pinned buffers.  3 G + 6 CUDA calls per step instead of 12 G, so the
-    host keeps up with eight groups.  refill(slot, perm [B,54], lord [B]) uploads one slot of every group's deal pool."""
+    entropy (pinned int32 [B], global env order) on a copy stream, one launch per group on its stream, one D2H of every
+    group's r | done | cat into a ring of PIPE_DEPTH pinned buffers; device buffers rotate through the same ring, so no
+    stream waits for an older step.  4 G + 4 CUDA calls per step instead of 12 G.
+    refill(slot, perm [B,54], lord [B]) uploads one slot of every group's deal pool."""
 
     def __init__(self, ge):
         import ctypes as C
@@ -780,8 +833,8 @@ class HostRolloutGroups:
         self.P = ge._pool[0][2]
         self.sizes = [e.B for e in ge.envs]
         B = sum(self.sizes)
-        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.results_d = [torch.zeros(3 * B, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.entropy_d = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(N.PIPE_DEPTH)]
+        self.results_d = [torch.zeros(3 * B, dtype=torch.uint8, device=dev) for _ in range(N.PIPE_DEPTH)]
         self.results_h = [GroupStepResults(self.sizes) for _ in range(N.PIPE_DEPTH)]
         self.h2d_bytes, self.d2h_bytes = 4 * B, 3 * B
         self._stage = None
@@ -824,8 +877,8 @@ class HostRolloutGroups:
         ge, k = self.ge, self.i % N.PIPE_DEPTH
         cur = ge.envs[0]._cur
         variant, seed, rewards, P, stats = self._const
-        args = (self._pipe, self._gs[cur], variant, entropy_h.data_ptr(), self.entropy_d[self.i & 1].data_ptr(), seed,
-                ge.envs[0]._stepno, rewards, P, self.results_d[self.i & 1].data_ptr(), self.results_h[k].buf.data_ptr(), stats)
+        args = (self._pipe, self._gs[cur], variant, entropy_h.data_ptr(), self.entropy_d[k].data_ptr(), seed,
+                ge.envs[0]._stepno, rewards, P, self.results_d[k].data_ptr(), self.results_h[k].buf.data_ptr(), stats)
         if self._same_device:
             rc = N.lib.ddz_mpipe_step(*args)
         else:

@@ -129,11 +129,28 @@ class BatchedGame:
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed((int(seed) if seed else 0) + 12345)
         self.pool_games = int(pool_games)
+        self._deal_seed = (int(seed) if seed else 0) + 777
+        self._own_deals = deals is None                  # caller-supplied deals are a closed set by the caller's choice
         if deals is None:
-            deals = random_deals(self.B, seed=(int(seed) if seed else 0) + 777, pool_games=self.pool_games)
-        self._perm = torch.as_tensor(deals[0]).to(self.device)
-        self._lord_pile = torch.as_tensor(deals[1]).to(self.device)
+            deals = random_deals(self.B, seed=self._deal_seed, pool_games=self.pool_games)
+        self._perm = torch.as_tensor(deals[0]).to(self.device).reshape(self.pool_games, self.B, 54).contiguous()
+        self._lord_pile = torch.as_tensor(deals[1]).to(self.device).reshape(self.pool_games, self.B).contiguous()
+        self._slots_made = self.pool_games               # deal number j of every env lives in slot j % pool_games
         self.env.prepare(self._perm, self._lord_pile, pool_games=self.pool_games)
+
+    def _refresh_pool(self):
+        """The reference shuffles a fresh deck for every game (game.py:170-171).  Env b takes row (deals consumed % pool) of
+        the device-resident pool, so a slot every env has passed is replaced by new host-made deals (seeded by its deal
+        number): no env ever replays a deal, however long the run."""
+        if not self._own_deals:
+            return
+        passed = int((self.env._fields()[1] >> 8).min().item())      # deals consumed by the slowest env
+        while self._slots_made - self.pool_games < passed - 1:       # slot of deal number j - pool is no longer needed
+            j = self._slots_made
+            perm, lord = random_deals(self.B, seed=self._deal_seed + 7919 * j)
+            self._perm[j % self.pool_games].copy_(torch.as_tensor(perm), non_blocking=False)
+            self._lord_pile[j % self.pool_games].copy_(torch.as_tensor(lord), non_blocking=False)
+            self._slots_made += 1
 
     # ------------------------------------------------------------------ one decision of every env
     def accumulate_loss(self, name, loss):
@@ -191,6 +208,8 @@ class BatchedGame:
                 n = w[ROLE_INDEX[role]]
                 setattr(self, "%s_total_wins" % role, getattr(self, "%s_total_wins" % role) + n)
                 setattr(self, "%s_recent_wins" % role, getattr(self, "%s_recent_wins" % role) + n)
+            if self.iterations % 16 == 0:
+                self._refresh_pool()
             env.prepare(self._perm, self._lord_pile, only_done=True, pool_games=self.pool_games)
         self.episodes += ended
         self.iterations += 1

@@ -65,6 +65,18 @@ extern "C" {
 #define DDZ_STEPNO_AUTO 0xFFFFFFFFu
 
 int ddz_abi_version(void);
+/* layout of the two probability planes of a face (get_state_prob, envi.py:94; get_state_prob_manual, server/core.py:26-33),
+ * a build-time choice because nothing in the reference pins it (oracle/SEMANTICS.md): 0 = form A, thermometer of the
+ * unknown count (default); 1 = form B, deck60 - known60 element-wise (library built with -DDDZ_PROB_FORM_B) */
+int ddz_prob_form(void);
+/* How the list-producing launches (observe / rollout_step) hand their 32-env tiles to warps.  DDZ_TILES_AUTO (default):
+ * by launch position when the whole grid fits on the device at once (saves an atomic round trip before the first load),
+ * else by an atomic ticket in start order.  DDZ_TILES_TICKET: always by ticket -- ask for it when OTHER kernels (a Q-network,
+ * a collective) share the GPU with the env launches, so that nothing depends on the grid being co-resident.  Process-wide;
+ * returns the previous mode. */
+#define DDZ_TILES_AUTO 0
+#define DDZ_TILES_TICKET 1
+int ddz_set_tile_order(int mode);
 int ddz_face_channels(int variant);          /* 4 / 7 / 9 / 6, or DDZ_E_ARG */
 size_t ddz_state_bytes(int B);
 /* Scratch for observe / rollout_step / legal_moves (n <= B): tile ticket + one look-back word per 32-env tile.
@@ -84,7 +96,9 @@ int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool
 /* env.face + env.valid_actions() for all envs  (envi.py:87-116; r.get_moves envi.py:111;
  * get_state_prob envi.py:94; batch_arr2onehot envi.py:140-146).
  * offsets int32[B+1] and actions_u64[cap] are required; actions_f32 / face may be NULL (skipped).
- * Finished envs have no legal move.  If the total exceeds cap the tail is dropped and stats[7] is bumped. */
+ * Finished envs have no legal move.  If the total exceeds cap the tail is dropped and stats[7] is bumped; the offsets
+ * are still those of the complete lists, and the envs play on: a later step whose choice falls into the dropped part
+ * recomputes that move from the state (only the observation was incomplete -- re-observe with a larger cap to see it). */
 int ddz_observe(const void* state, void* workspace, int variant, int32_t* offsets, uint64_t* actions_u64,
                 float* actions_f32, int64_t cap, float* face, int64_t* stats, int B, void* stream);
 
@@ -201,17 +215,19 @@ int ddz_pipe_flush(ddz_pipe* p, void* stream);   /* commit a staged deal-pool up
 /* ---- the same pipeline over several env groups of one GPU: ONE native call per env-step of all groups.
  * The envs of a GPU run as G independent groups (own state, workspace, ping-pong lists, stream) so that one group's
  * load-only prologue overlaps another group's store phase.  ddz_mpipe_step issues, for step s:
- *   copy stream : H2D host_choice (pinned, sum(B_g) x 4 bytes, group-major) -> dev_choice (alternate two buffers by parity)
- *   stream g    : wait; ddz_rollout_step of group g with its slice of dev_choice; r | done | cat of group g go to
- *                 results_dev + 3 * (sum of B of the groups before g)   (r[B_g] | done[B_g] | cat[B_g])
- *   copy stream : wait for all groups; D2H results_dev (3 x sum(B_g) bytes; alternate two buffers by parity) ->
- *                 results_host (pinned; rotate up to DDZ_PIPE_DEPTH buffers, ddz_mpipe_wait(slot) blocks on the D2H of the
- *                 latest step with step index % DDZ_PIPE_DEPTH == slot)
- * i.e. 3 G + 6 CUDA calls per step.  `gs` describes the groups FOR THIS STEP (prev_* = lists of the current state, out_* =
- * the other ping-pong set); reward (float32 [B_g][3], device) is optional and stays on the device.  stats may be one
- * vector shared by all groups (the kernels add atomically).  ddz_mpipe_refill uploads one slot of every group's deal pool
- * from ONE pinned host array (rows group-major) into a staging buffer; each group's slot is replaced on the group's
- * stream by the first step that finds the upload complete, or by ddz_mpipe_flush / the next refill, which wait for it. */
+ *   copy stream   : H2D host_choice (pinned, sum(B_g) x 4 bytes, group-major) -> dev_choice
+ *   stream g      : wait for it; ddz_rollout_step of group g (DDZ_CHOICE_MOD) with its slice of dev_choice; r | done | cat of
+ *                   the group -> results_dev + 3 * off_g   (r[B_g] | done[B_g] | cat[B_g]; off_g = sum of B of the groups before g)
+ *   copy stream 2 : wait for all groups' kernels; D2H results_dev (3 x sum(B_g) bytes) -> results_host (pinned)
+ * The caller rotates dev_choice, results_dev and results_host through DDZ_PIPE_DEPTH buffers each (slot = step index %
+ * DDZ_PIPE_DEPTH).  The step that reuses a slot first waits ON THE HOST (normally a no-op: the host reads results before
+ * then) until the D2H of the step that used it before has landed, so no stream ever waits for an older step and the groups
+ * never fall into lock-step.  4 G + 4 CUDA calls per step.  ddz_mpipe_wait(slot) blocks until the D2H of the latest step
+ * with that slot has landed.  `gs` describes the groups FOR THIS STEP (prev_* = lists of the current state, out_* = the other
+ * ping-pong set); reward (float32 [B_g][3], device) is optional and stays on the device.  stats may be one vector shared
+ * by all groups (the kernels add atomically).  ddz_mpipe_refill uploads one slot of every group's deal pool from ONE
+ * pinned host array (rows group-major) into a staging buffer on a third copy stream; each group's slot is replaced on the
+ * group's stream by the first step that finds the upload complete, or by ddz_mpipe_flush / the next refill, which wait. */
 #define DDZ_MPIPE_MAX_GROUPS 16
 typedef struct {
     void* state; void* workspace;

@@ -360,31 +360,50 @@ int ddz_ref_env_step(ddz_ref_env* e, const int8_t move[15], const int32_t R[3],
     return 0;
 }
 
-/* SURVEY App. A get_state_prob_manual, form (A): unknown = thermometer(total - known),
- * plane k = unknown * float(size_k)/float(size1+size2); inputs per server/core.py:26-33 */
-static void prob_planes(const int unknown[15], int size1, int size2, float out[120]) {
+/* SURVEY App. A get_state_prob_manual; inputs per server/core.py:26-33: known60 = thermometer one-hot of (played cards +
+ * own hand), size1 / size2 = cards left of the next / next-next player; plane k = unknown60 * float(size_k)/float(size1+size2).
+ * unknown60 is the one unpinned layout choice (oracle/SEMANTICS.md):
+ *   form A (default)           thermometer(total - known): ones left-aligned like every other plane,
+ *   form B (-DDDZ_PROB_FORM_B)  deck60 - known60 element by element (deck60 = 1111 x 13 ranks, 1000 per joker). */
+static int total_of(int r) { return r < 13 ? 4 : 1; }
+int ddz_ref_prob_form(void) {
+#ifdef DDZ_PROB_FORM_B
+    return 1;
+#else
+    return 0;
+#endif
+}
+static void prob_planes60(const int known60[60], int size1, int size2, float out[120]) {
     int tot = size1 + size2;
-    float p[2];
+    float p[2], unknown60[60];
     p[0] = tot > 0 ? (float)size1 / (float)tot : 0.f;
     p[1] = tot > 0 ? (float)size2 / (float)tot : 0.f;
-    for (int k = 0; k < 2; k++)
-        for (int r = 0; r < 15; r++)
-            for (int j = 0; j < 4; j++) out[k * 60 + r * 4 + j] = (j < unknown[r]) ? p[k] : 0.f;
-}
-static int total_of(int r) { return r < 13 ? 4 : 1; }
-void ddz_ref_state_prob_manual(const int32_t known60[60], int size1, int size2, float out[120]) {
-    int unknown[15];
     for (int r = 0; r < 15; r++) {
+#ifdef DDZ_PROB_FORM_B
+        for (int j = 0; j < 4; j++) {
+            int deck = j < total_of(r) ? 1 : 0, d = deck - (known60[4 * r + j] != 0);
+            unknown60[4 * r + j] = d > 0 ? 1.f : 0.f;
+        }
+#else
         int k = 0; for (int j = 0; j < 4; j++) k += known60[4 * r + j] != 0;
-        unknown[r] = total_of(r) - k; if (unknown[r] < 0) unknown[r] = 0;
+        int u = total_of(r) - k; if (u < 0) u = 0;
+        for (int j = 0; j < 4; j++) unknown60[4 * r + j] = j < u ? 1.f : 0.f;
+#endif
     }
-    prob_planes(unknown, size1, size2, out);
+    for (int k = 0; k < 2; k++) for (int i = 0; i < 60; i++) out[60 * k + i] = unknown60[i] * p[k];
 }
-void ddz_ref_state_prob(const ddz_ref_env* e, float out[120]) {
-    int unknown[15], s = e->cur;
-    for (int r = 0; r < 15; r++)
-        unknown[r] = total_of(r) - e->hist[0][r] - e->hist[1][r] - e->hist[2][r] - e->hand[s][r];
-    prob_planes(unknown, left_of(e, (s + 1) % 3), left_of(e, (s + 2) % 3), out);
+void ddz_ref_state_prob_manual(const int32_t known60[60], int size1, int size2, float out[120]) {
+    int k60[60];
+    for (int i = 0; i < 60; i++) k60[i] = known60[i] != 0;
+    prob_planes60(k60, size1, size2, out);
+}
+void ddz_ref_state_prob(const ddz_ref_env* e, float out[120]) {   /* envi.py:94: the same, from the env's own trackers */
+    int known60[60], s = e->cur;
+    for (int r = 0; r < 15; r++) {
+        int known = e->hist[0][r] + e->hist[1][r] + e->hist[2][r] + e->hand[s][r];
+        for (int j = 0; j < 4; j++) known60[4 * r + j] = j < known;
+    }
+    prob_planes60(known60, left_of(e, (s + 1) % 3), left_of(e, (s + 2) % 3), out);
 }
 
 static void thermo(const int* cnt, float* out) { /* envi.py:140-146: res[rank][:count] = 1 */

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libddz_oracle.so")
+_LIB_PATH = os.environ.get("DDZ_ORACLE_LIB") or os.path.join(_HERE, "libddz_oracle.so")   # DDZ_ORACLE_LIB: the form-B build
 _lib = None
 
 MAX_LEGAL = 512
@@ -36,7 +36,7 @@ def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("ddz_oracle.c", "ddz_oracle.h")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src):
         return _LIB_PATH
-    subprocess.check_call(["make", "-C", _HERE, "-B", "libddz_oracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
@@ -68,6 +68,7 @@ def lib():
         L.ddz_ref_env_last.restype = None
         L.ddz_ref_env_legal.argtypes = [envp, i8p, C.c_int, C.c_int]
         L.ddz_ref_env_step.argtypes = [envp, i8p, i32p, ip, ip, ip, f32p]
+        L.ddz_ref_prob_form.restype = C.c_int
         L.ddz_ref_state_prob.argtypes = [envp, f32p]
         L.ddz_ref_state_prob.restype = None
         L.ddz_ref_state_prob_manual.argtypes = [i32p, C.c_int, C.c_int, f32p]

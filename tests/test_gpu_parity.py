@@ -979,22 +979,82 @@ def test_multi_step_launch_equals_playout(D, oracle):
     assert torch.equal(traj.actions_u64[K - 1, :n], a.actions_packed) and torch.equal(traj.face[K - 1], a.face)
 
 
-def test_overflowing_lists_are_safe(D):
-    """cap smaller than the total: the tail is dropped, stats[7] says so, and a fused step whose choice falls into the
-    dropped part is an illegal choice (sticky error bit) -- never an out-of-bounds read."""
-    B = 8192
-    perm, lord = D.random_deals(B, seed=21)
+def test_overflowing_lists_are_safe(D, oracle):
+    """cap smaller than the total: the tail of the lists is dropped and stats[7] says so -- never an out-of-bounds access --
+    but the envs PLAY ON: a fused step whose choice falls into the dropped part recomputes that move from the state, so the
+    trajectories stay those of the oracle; asking for the lists grows the buffers and re-observes (complete lists again)."""
+    B, G = 8192, 2
+    perm, lord = D.random_deals(B, seed=21, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
     env = D.BatchedEnvCooperation(B, seed=2, max_actions_per_env=8)        # 20-card leads have far more than 8 moves
-    env.prepare(perm, lord)
+    env.prepare(pd, ld, pool_games=G)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=G)
     env.observe()
     torch.cuda.synchronize()
     assert int(env.stats[7].item()) >= 1 and int(env.offsets[B].item()) > env.cap
-    for _ in range(6):
-        env.rollout_step()
+    for t in range(40):
+        ref.observe(want_f32=False, want_face=False)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
+        ref.step(mode=2, seed=2, env0=0, step=t)
+        ref.deal(perm, lord, only_done=True, pool_games=G)
     torch.cuda.synchronize()
     meta = env._fields()[1].cpu().numpy().view(np.uint32)
-    assert ((meta >> 5) & 1).sum() > 0                                      # envs whose move was in the dropped tail
-    assert int(env.stats[4].item()) > 0                                     # the others played on
+    assert ((meta >> 5) & 1).sum() == 0                                     # nobody was stopped by the overflow
+    assert int(env.stats[4].item()) == 40 * B == ref.stats[4] and int(env.stats[0].item()) == ref.stats[0] > 0
+    _compare_state(env, ref, 40)
+    small = env.cap
+    n = _compare_observation(env, ref, 40)                                  # grows the buffers, re-observes, complete lists
+    assert env.cap >= n > small
+    # explicit moves that were cut off are still recognised as legal (CHOICE_MOVE searches the closed form past the cut)
+    env2 = D.BatchedEnv(64, seed=1, max_actions_per_env=4)
+    p2, l2 = D.random_deals(64, seed=5)
+    env2.prepare(p2, l2)
+    ref2 = oracle.RefBatch(64, 0)
+    ref2.deal(p2, l2)
+    off, au, _, _ = ref2.observe(want_f32=False, want_face=False)
+    last_moves = torch.as_tensor(au[off[1:] - 1].view(np.int64)).cuda()    # every env's LAST legal move: far past the cut
+    env2.observe()
+    r, done, cat = env2.rollout_step(last_moves, mode=D.native.CHOICE_MOVE)
+    ref2.step((off[1:] - off[:-1] - 1).astype(np.int32), mode=0)
+    torch.cuda.synchronize()
+    _compare_state(env2, ref2, 1)
+
+
+def test_ticket_tiles_with_a_concurrent_kernel(D, oracle):
+    """Other kernels share the GPU with the env launches (BASELINE config 3: the Q-network): with ddz_set_tile_order(ticket)
+    nothing depends on the env grid being co-resident.  A matmul loop runs on another stream while two env groups step;
+    results equal the oracle's and no look-back ever times out (stats[7] == 0).  The default order is checked the same way."""
+    B, P = 32768, 2
+    perm, lord = D.random_deals(B, seed=9, pool_games=P)
+    pr = perm.reshape(P, B, 54)[:, :2048].reshape(-1, 54); lr = lord.reshape(P, B)[:, :2048].reshape(-1)
+    for mode in ("ticket", "auto"):
+        prev = D.native.set_tile_order(mode)
+        try:
+            ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=2, seed=6, max_actions_per_env=160)
+            ge.prepare(perm, lord, pool_games=P)
+            ref = oracle.RefBatch(2048, 2)                                 # the oracle follows the first 2048 envs
+            ref.deal(pr, lr, pool_games=P)
+            side = torch.cuda.Stream()
+            a = torch.randn(4096, 4096, device="cuda")
+            for t in range(30):
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        a = (a @ a).clamp_(-1, 1)                           # keeps every SM busy next to the env launches
+                ge.rollout_step()
+                ref.observe(want_f32=False, want_face=False)
+                ref.step(mode=2, seed=6, env0=0, step=t)
+                ref.deal(pr, lr, only_done=True, pool_games=P)
+            ge.join()
+            torch.cuda.synchronize()
+            assert int(ge.stats[7].item()) == 0, mode
+            f, meta = ref.export()
+            ef, em = ge.envs[0]._fields()
+            assert np.array_equal(ef[:, :2048].cpu().numpy().view(np.uint64), f), mode
+            assert np.array_equal(em[:2048].cpu().numpy().view(np.uint32), meta), mode
+        finally:
+            D.native.set_tile_order(prev)
+    assert D.native.set_tile_order("auto") == "auto"
 
 
 def test_batched_game_trains_and_competes(D):
@@ -1191,3 +1251,140 @@ def test_compressible_row_buffers(D):
         assert torch.equal(env.face, plain.face) and torch.equal(env.valid_actions()[0], plain.valid_actions()[0])
     finally:
         del os.environ["DDZ_NO_COMPRESSION"]
+
+
+# ------------------------------------------------------------------ round 2: getters, multi-group host pipe, flat lists
+def test_get_last_two_cards_batched_and_view(D, oracle, golden):
+    """get_last_two_cards (envi.py:103-109; the rule bot reads it, rule_based/utils/rule_based_model.py:17-33): the batched
+    getter against the oracle's envs every step (and its first non-empty entry against ddz_ref_env_last, the trick to
+    beat), the B=1 view against the golden trace of the unmodified envi.py."""
+    import ctypes as C
+    B, G = 512, 2
+    perm, lord = D.random_deals(B, seed=21, pool_games=G)
+    env = D.BatchedEnvCooperation(B, seed=8)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env.prepare(pd, ld, pool_games=G)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=G)
+    L = oracle.lib()
+    for t in range(90):
+        got = env.get_last_two_cards().cpu().numpy()
+        cur = ref.envs["cur"].astype(np.int64)
+        rec = ref.envs["recent"]
+        ar = np.arange(B)
+        want = np.stack([rec[ar, (cur + 2) % 3], rec[ar, (cur + 1) % 3]], 1)
+        assert np.array_equal(got, want), t
+        for b in range(0, B, 37):                                # the trick to beat = first non-empty of the two
+            last = np.zeros(15, np.int8)
+            L.ddz_ref_env_last(C.c_void_p(ref.envs.ctypes.data + b * oracle.ENV_DTYPE.itemsize), last.ctypes.data_as(C.POINTER(C.c_int8)))
+            first = got[b, 0] if got[b, 0].any() else got[b, 1]
+            assert np.array_equal(first, last), (t, b)
+        ref.observe(want_f32=False, want_face=False)
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
+        ref.step(mode=2, seed=8, env0=0, step=t)
+        ref.deal(perm, lord, only_done=True, pool_games=G)
+    # B = 1 view: lists of card values like the reference's, replayed over the golden envi.py trace
+    t = golden.envi_trace
+    env1 = D.EnvCooperation()
+    for g in range(3):
+        env1.reset()
+        env1.prepare(t["perms"][g][None], np.zeros(1, np.int8))
+        prev = np.zeros((3, 15), np.int8)
+        for s in np.flatnonzero(t["game"] == g):
+            cur = int(t["role"][s])
+            two = env1.get_last_two_cards()
+            assert [list(map(int, x)) for x in two] == [list(D.Env.arr2cards(prev[(cur + 2) % 3])), list(D.Env.arr2cards(prev[(cur + 1) % 3]))]
+            acts = env1.valid_actions()
+            env1.step_manual(acts[int(t["choice"][s])])
+            prev = t["recent"][s]
+
+
+def test_host_rollout_groups_matches_oracle(D, oracle):
+    """HostRolloutGroups: ONE native call per env-step of all groups of a GroupedEnv (ddz_mpipe_step) -- one H2D of the
+    pinned entropy, one launch per group, one D2H of r/done/cat -- plus pool refills from the host.  Every step's results
+    and the final state must equal the oracle's; all groups add to one shared stats vector."""
+    B, P, NG = 2048, 2, 4
+    rng = np.random.default_rng(77)
+    perm, lord = D.random_deals(B, seed=19, pool_games=P)
+    pool = [np.array(perm.reshape(P, B, 54)), np.array(lord.reshape(P, B))]
+    ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=NG, seed=3)
+    ge.prepare(perm, lord, pool_games=P)
+    assert all(e.stats.data_ptr() == ge.stats.data_ptr() for e in ge.envs)
+    host = D.HostRolloutGroups(ge)
+    assert host.h2d_bytes == 4 * B and host.d2h_bytes == 3 * B
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=P)
+    ents = [torch.as_tensor(rng.integers(0, 1 << 31, B).astype(np.int32)).pin_memory() for _ in range(5)]
+    pending = []
+    Bg = B // NG
+    for t in range(130):
+        if t % 40 == 20:
+            slot = (t // 40) % P
+            p2, l2 = D.random_deals(B, seed=500 + t)
+            host.refill(slot, torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory(), now=(t != 60))
+            if t == 60:
+                host.flush()
+            pool[0][slot], pool[1][slot] = p2, l2
+        res = host.step(ents[t % 5])
+        ref.observe(want_f32=False, want_face=False)
+        rr, rd, rc, _ = ref.step(ents[t % 5].numpy(), mode=1)
+        ref.deal(pool[0].reshape(-1, 54), pool[1].reshape(-1), only_done=True, pool_games=P)
+        pending.append((res, rr.copy(), rd.copy(), rc.copy(), t))
+        if len(pending) == 3:                         # read two steps late, as a pipelined host would
+            got, rr, rd, rc, tt = pending.pop(0)
+            D.HostRolloutGroups.wait(got)
+            for g in range(NG):
+                sl = slice(g * Bg, (g + 1) * Bg)
+                assert np.array_equal(got.r[g], rr[sl]) and np.array_equal(got.done[g], rd[sl]) and np.array_equal(got.cat[g], rc[sl]), (tt, g)
+    ge.join()
+    torch.cuda.synchronize()
+    f, meta = ref.export()
+    got_f = torch.cat([e._fields()[0] for e in ge.envs], 1).cpu().numpy().view(np.uint64)
+    got_m = torch.cat([e._fields()[1] for e in ge.envs]).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got_f, f) and np.array_equal(got_m, meta)
+    st = ge.stats.cpu().numpy()
+    assert st[7] == 0 and st[4] == ref.stats[4] == 130 * B and st[0] == ref.stats[0] > 0
+    for g, e in enumerate(ge.envs):                   # the lists after the last step are those of the final state
+        off = e.offsets.cpu().numpy()
+        sub = oracle.RefBatch(Bg, 2)
+        sub.envs[:] = ref.envs[g * Bg:(g + 1) * Bg]
+        want_off, want_au, _, want_face = sub.observe(want_f32=False)
+        assert np.array_equal(off, want_off) and np.array_equal(e.actions_packed.cpu().numpy().view(np.uint64), want_au)
+        assert np.array_equal(e.face.cpu().numpy(), want_face)
+
+
+def test_legal_moves_multi_round_tiles_and_long_lists(D, oracle):
+    """ddz_legal_moves (k_legal_flat) on tiles made only of the heaviest hands: several arena rounds per tile, windows that
+    straddle hands and rounds, an odd list base, plus a tile of tiny hands behind them."""
+    rng = np.random.default_rng(3)
+    heavy = D.ADVERSARIAL_POOL[[0, 1, 3, 8, 9]]
+    hands = np.concatenate([heavy[rng.integers(0, len(heavy), 75)], _rand_hands(rng, 40, 1, 4), heavy[rng.integers(0, len(heavy), 45)]])
+    n = len(hands)
+    z = np.zeros(15, np.int8)
+    lasts = np.zeros((n, 15), np.int8)
+    lasts[0] = np.eye(15, dtype=np.int8)[2]               # an odd number of moves in front of everything else
+    for i in range(1, n, 3):
+        om = oracle.get_moves(heavy[rng.integers(0, len(heavy))], z, fast=True)
+        lasts[i] = om[rng.integers(0, len(om))]
+    packed, offsets = D.get_moves(hands, lasts)
+    for i, got in enumerate(_split(packed, offsets)):
+        want = oracle.pack(oracle.get_moves(hands[i], lasts[i], fast=True))
+        assert np.array_equal(got, np.atleast_1d(want)), (i, hands[i], lasts[i])
+
+
+def test_prob_form_b_build_matches_form_b_oracle(D):
+    """The build switch for the one layout nothing in the reference pins (oracle/SEMANTICS.md, server/core.py:26-33): the
+    library and the oracle compiled with -DDDZ_PROB_FORM_B agree bit for bit on all four faces (the default build, form A,
+    is what every other test checks)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_b = os.path.join(root, "doudizhu-rl_b200", "libddz_b200_formB.so")
+    ora_b = os.path.join(root, "oracle", "libddz_oracle_formB.so")
+    if not (os.path.exists(lib_b) and os.path.exists(ora_b)):
+        import __graft_entry__
+        __graft_entry__.build()
+    assert D.native.lib.ddz_prob_form() == 0
+    env = dict(os.environ, DDZ_LIB=lib_b, DDZ_ORACLE_LIB=ora_b)
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "form_b_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "form B ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -231,3 +231,40 @@ def test_config1_thousand_seeded_games_random_play(oracle):
     assert st[0] == n and st[1] + st[2] + st[3] == n
     per_game, nbar, passes = st[4] / n, moves / st[4], st[9] / st[4]
     assert 58 < per_game < 66 and 5.0 < nbar < 6.2 and 0.47 < passes < 0.55, (per_game, nbar, passes)
+
+
+def test_prob_plane_forms_follow_their_definitions(golden):
+    """get_state_prob_manual (server/core.py:26-33) in both layouts of oracle/SEMANTICS.md, on the known60 inputs the
+    unmodified server/core.py built for 591 payloads: form A = thermometer(total - known), form B = deck60 - known60."""
+    import ctypes as C
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = golden.core_payloads
+    # server/core.py:26-31 get_prob: known = thermometer(all played cards + own hand), sizes of the next / next-next player
+    role = g["role"].astype(np.int64)
+    counts = g["history"].sum(1).astype(np.int64) + g["hand"]
+    known = (np.arange(4)[None, None, :] < counts[:, :, None]).astype(np.int32).reshape(-1, 60)
+    ar = np.arange(len(role))
+    s1, s2 = g["left"][ar, (role + 1) % 3], g["left"][ar, (role + 2) % 3]
+    deck = np.ones((15, 4), np.float32); deck[13:, 1:] = 0
+    from oracle import ddz_oracle as O
+    O.build()
+    for name, form in (("libddz_oracle.so", 0), ("libddz_oracle_formB.so", 1)):
+        L = C.CDLL(os.path.join(os.path.dirname(here), "oracle", name))
+        assert L.ddz_ref_prob_form() == form
+        for i in range(0, len(known), 7):
+            k = (known[i].reshape(15, 4) != 0)
+            if form == 0:
+                u = np.clip(np.array([4] * 13 + [1, 1]) - k.sum(-1), 0, None)
+                unk = (np.arange(4)[None, :] < u[:, None]).astype(np.float32)
+            else:
+                unk = np.clip(deck - k.astype(np.float32), 0, None)
+            tot = int(s1[i]) + int(s2[i])
+            p = [np.float32(s1[i]) / np.float32(tot), np.float32(s2[i]) / np.float32(tot)] if tot else [0, 0]
+            want = np.concatenate([(unk * p[0]).reshape(60), (unk * p[1]).reshape(60)]).astype(np.float32)
+            out = np.zeros(120, np.float32)
+            kk = np.ascontiguousarray(known[i], dtype=np.int32)
+            L.ddz_ref_state_prob_manual(kk.ctypes.data_as(C.POINTER(C.c_int32)), int(s1[i]), int(s2[i]), out.ctypes.data_as(C.POINTER(C.c_float)))
+            assert np.array_equal(out, want), (name, i)
+            if form == 0:      # the default form is what the unmodified Predictor.face produced over the oracle shim
+                assert np.array_equal(out.reshape(2, 15, 4), g["face"][i][4:6]), i
