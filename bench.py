@@ -339,6 +339,7 @@ def run_config4(args):
         side.synchronize()
     half = K // 2
     every = max(1, args.stats_every // 2)
+    coll_ev = []                        # (issued, done) events of every exchange, on the side stream: where the window's time goes
     barrier()
     e0.record()
     ge._fork()
@@ -353,8 +354,12 @@ def run_config4(args):
             snap_ready.record(ge.streams[0])
             side.wait_event(snap_ready)
             with torch.cuda.stream(side):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
                 snap.copy_(ge.stats)    # one 128-byte device copy of the vector all groups add to
                 dist.all_reduce(snap)
+                c1.record()
+                coll_ev.append((c0, c1))
             exchanges += 1
     if K % 2:
         ge.rollout_step()
@@ -427,8 +432,14 @@ def run_config4(args):
             sink[0] += int(old.done[0][0]) + int(old.r[-1][-1])
         pending[i % DEPTH] = host.step(ent_h[i % R])
 
-    for i in range(max(W, 4)):
+    # warm-up: one untimed pass of the same shape (a pool upload and the steps that carry its chunks), then flush it, so
+    # that no upload is half-way when the window opens and the first-use costs of the pinned pool buffers are paid
+    for i in range(max(W, 24)):
         e2e_step(i)
+    host.flush()
+    for res in pending:
+        if res is not None:
+            D.HostRolloutGroups.wait(res)
     ge.join()
     barrier()
     stats_e0 = ge.stats.clone()
@@ -437,11 +448,13 @@ def run_config4(args):
     ge._fork()
     for i in range(K):
         e2e_step(i)
-    for res in pending:
+    ge.join()
+    host.join()                         # ... and the D2H of the last step's results: the window ends on the device
+    x1.record()
+    for res in pending:                 # the host reads the last results (already on their way when x1 is recorded)
         if res is not None:
             D.HostRolloutGroups.wait(res)
-    ge.join()
-    x1.record()
+            sink[0] += int(res.done[0][0])
     barrier()
     clocks = sampler.stop()
     e2e_ms = x0.elapsed_time(x1)
@@ -458,6 +471,14 @@ def run_config4(args):
         verdict = all_ranks_ok(D, torch, dev, world, verdict)
 
     # ---------------- reduce over ranks: MAX of the device times, SUM of the work
+    trace = None
+    if world > 1:                       # every rank's window and where its exchanges sat in it (ms from the window start)
+        mine = torch.tensor([total_ms] + [x for c0, c1 in coll_ev[:4] for x in (e0.elapsed_time(c0), e0.elapsed_time(c1))],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        trace = {"per_rank_window_ms": [round(float(t[0]), 4) for t in allr],
+                 "per_rank_exchange_issued_done_ms": [[round(float(x), 4) for x in t[1:]] for t in allr]}
     total_ms = D.sharding.max_over_ranks(total_ms, dev)
     e2e_ms = D.sharding.max_over_ranks(e2e_ms, dev)
     gstats = D.sharding.allreduce_stats(dstats_t, side_stream=torch.cuda.Stream(dev) if world > 1 else None)
@@ -486,7 +507,8 @@ def run_config4(args):
                             "row_buffers": ("compressible device memory (CU_MEM_ALLOCATION_COMP_GENERIC: the L2 compresses "
                                             "the 0/1 thermometer rows on their way to HBM)" if compressed else "plain device memory"),
                             "games_finished": int(gstats[0].item()),
-                            "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item()))}, **info),
+                            "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item())),
+                            "window_trace": trace}, **info),
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
                          "unit": "GB/s", "frac": kern_gbs / peak,
                          "frac_single_chain": (B * eb / (single * 1e-3) / 1e9 / peak) if single else None,
@@ -574,6 +596,10 @@ def run_config5(args):
     for _ in range(Ke):
         e2e_call()
     x1.record()
+    for res in pending:                 # the host reads the last results (already on their way when x1 is recorded)
+        if res is not None:
+            D.HostRolloutGroups.wait(res)
+            sink[0] += int(res.done[0][0])
     barrier()
     clocks = sampler.stop()
     e2e_ms = x0.elapsed_time(x1)
@@ -658,6 +684,7 @@ def run_config3(args):
     perm, lord = D.random_deals(B, seed=SEED, pool_games=P)
     pd, ld = torch.as_tensor(perm).to(dev), torch.as_tensor(lord).to(dev)
     # other kernels (the network's) share the GPU with the env launches: tiles by ticket, not by launch position
+    D.native.set_tile_order("ticket")
     env = D.BatchedEnvCooperation(B, seed=SEED, device=dev, max_actions_per_env=160)
     env.prepare(pd, ld, pool_games=P)
     for _ in range(min(args.prefill, 60)):

@@ -10,11 +10,12 @@ from .agent import BatchedGreedyPolicy
 from .trainer import ReplayBuffer, TransitionCollector, td_step
 from .game import BatchedGame, BatchedDQN
 from .ingest import env_from_payloads, env_from_arrays, payload_arrays, evaluate_moves, mcts
+from .search import UctSearch
 from .env import (Trajectory, GraphedRollout, GroupedEnv, HostRollout, HostRolloutGroups, GroupStepResults, StepResults, BatchedEnv, BatchedEnvComplicated, BatchedEnvCooperation, BatchedEnvCooperationSimplify,
                   Env, EnvComplicated, EnvCooperation, EnvCooperationSimplify,
                   MoveGenerator, get_moves, kth_moves, pack_counts, unpack_counts, default_deals, random_deals, adversarial_pairs, ADVERSARIAL_POOL,
                   VARIANT_CHANNELS, DEFAULT_REWARDS)
 
-__all__ = ["native", "sharding", "BatchedGreedyPolicy", "ReplayBuffer", "TransitionCollector", "td_step", "BatchedGame", "BatchedDQN", "env_from_payloads", "env_from_arrays", "payload_arrays", "evaluate_moves", "mcts", "Trajectory", "GraphedRollout", "GroupedEnv", "HostRollout", "HostRolloutGroups", "GroupStepResults", "StepResults", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
+__all__ = ["native", "sharding", "BatchedGreedyPolicy", "ReplayBuffer", "TransitionCollector", "td_step", "BatchedGame", "BatchedDQN", "env_from_payloads", "env_from_arrays", "payload_arrays", "evaluate_moves", "mcts", "UctSearch", "Trajectory", "GraphedRollout", "GroupedEnv", "HostRollout", "HostRolloutGroups", "GroupStepResults", "StepResults", "BatchedEnv", "BatchedEnvComplicated", "BatchedEnvCooperation", "BatchedEnvCooperationSimplify",
            "Env", "EnvComplicated", "EnvCooperation", "EnvCooperationSimplify", "MoveGenerator", "get_moves", "kth_moves", "pack_counts",
            "unpack_counts", "default_deals", "random_deals", "adversarial_pairs", "ADVERSARIAL_POOL", "VARIANT_CHANNELS", "DEFAULT_REWARDS"]

@@ -142,6 +142,50 @@ DDZ_DEV void walk_groups(const Masks& m, const Rule& ru, bool has_last, int list
         }
 }
 
+// number of groups walk_groups() emits, in closed form (the number of moves is count_legal(), ddz_device.cuh)
+template <int LMIN, int LMAX>
+DDZ_DEV int count_line_groups(uint32_t src, const Rule& ru, int cat) {
+    const uint32_t R = src & kLineMask;
+    const bool same = !ru.lead && cat == ru.cat;
+    if (same && (ru.len < LMIN || ru.len > LMAX)) return 0;
+    const int need = same ? ru.len : LMIN;                     // a start counts if its run is at least this long
+    uint32_t t = R;
+    for (int L = 2; L <= need; L++) t &= R >> (L - 1);
+    return __popc(t & ru.from(cat));
+}
+template <int LMAX>
+DDZ_DEV int count_plane_groups(uint32_t g3, int nk, const Rule& ru, int cat) {
+    const uint32_t R = g3 & kLineMask, from = ru.from(cat);
+    uint32_t t = R;
+    int ng = 0;
+#pragma unroll
+    for (int L = 2; L <= LMAX; L++) {
+        t &= R >> (L - 1);
+        if (ru.len_ok(cat, L) && nk - L >= L) ng += __popc(t & from);
+    }
+    return ng;
+}
+DDZ_DEV int count_groups(const Masks& m, const Rule& ru, bool has_last) {
+    if (m.g1 == 0) return has_last ? 1 : 0;
+    int ng = ru.lead ? 0 : 1;
+    const int n1 = __popc(m.g1), n2 = __popc(m.g2);
+    if (ru.allowed(1)) ng += (m.g1 & ru.from(1)) != 0;
+    if (ru.allowed(2)) ng += (m.g2 & ru.from(2)) != 0;
+    if (ru.allowed(3)) ng += (m.g3 & ru.from(3)) != 0;
+    if (ru.allowed(4)) ng += (m.g4 & ru.from(4)) != 0;
+    if (ru.allowed(5) && n1 > 1) ng += __popc(m.g3 & ru.from(5));
+    if (ru.allowed(6) && n2 > 1) ng += __popc(m.g3 & ru.from(6));
+    if (ru.allowed(7)) ng += count_line_groups<5, 12>(m.g1, ru, 7);
+    if (ru.allowed(8)) ng += count_line_groups<3, 10>(m.g2, ru, 8);
+    if (ru.allowed(9)) ng += count_line_groups<2, 6>(m.g3, ru, 9);
+    if (ru.allowed(10)) ng += count_plane_groups<5>(m.g3, n1, ru, 10);
+    if (ru.allowed(11)) ng += count_plane_groups<4>(m.g3, n2, ru, 11);
+    if (ru.allowed(12)) ng += ((m.g1 & kRocket) == kRocket);
+    if (ru.allowed(13) && n1 - 1 >= 2) ng += __popc(m.g4 & ru.from(13));
+    if (ru.allowed(14) && n2 - 1 >= 2) ng += __popc(m.g4 & ru.from(14));
+    return ng;
+}
+
 struct CountSink {   // number of moves and of groups
     int n = 0, ng = 0;
     DDZ_DEV void add(uint32_t, int cnt) { n += cnt; ng++; }
@@ -155,13 +199,14 @@ struct WriteSink {   // descriptors [d, dlim) of the arena; `start` = list index
     }
 };
 
-// the four descending rank lists of a hand: lists[(list0 + c) * kListStride + q] = q-th highest rank with count > c
+// the four descending rank lists of a hand: lists[(list0 + c) * kListStride + q] = 4 * (q-th highest rank with count > c),
+// i.e. the shift that puts a card of that rank into its nibble
 DDZ_DEV void write_lists(const Masks& m, int list0, uint8_t* lists) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         uint32_t mask = c == 0 ? m.g1 : c == 1 ? m.g2 : c == 2 ? m.g3 : m.g4;
         uint8_t* l = lists + (list0 + c) * kListStride;
-        while (mask) { const int r = 31 - __clz(mask); *l++ = (uint8_t)r; mask ^= 1u << r; }
+        while (mask) { const int r = 31 - __clz(mask); *l++ = (uint8_t)(4 * r); mask ^= 1u << r; }
     }
 }
 
@@ -181,8 +226,8 @@ DDZ_DEV uint64_t decode(uint32_t prm, int j, int cnt, const uint16_t* __restrict
     uint32_t P = table[(int)(prm >> 22) + cnt - 1 - j];
     while (P) {
         int q = __ffs(P) - 1; P &= P - 1;
-        q += (q >= ap) ? L : 0;
-        mv += kmult << (4 * lst[q]);
+        if (q >= ap) q += L;
+        mv += kmult << lst[q];
     }
     return mv;
 }
@@ -201,8 +246,8 @@ DDZ_DEV void decode2(uint32_t prm0, int j0, int cnt0, bool v0, uint32_t prm1, in
     uint32_t P0 = k0 ? table[(int)(prm0 >> 22) + cnt0 - 1 - j0] : 0u;
     uint32_t P1 = k1 ? table[(int)(prm1 >> 22) + cnt1 - 1 - j1] : 0u;
     while (P0 | P1) {
-        if (P0) { int q = __ffs(P0) - 1; P0 &= P0 - 1; q += (q >= ap0) ? L0 : 0; mv0 += km0 << (4 * l0[q]); }
-        if (P1) { int q = __ffs(P1) - 1; P1 &= P1 - 1; q += (q >= ap1) ? L1 : 0; mv1 += km1 << (4 * l1[q]); }
+        if (P0) { int q = __ffs(P0) - 1; P0 &= P0 - 1; q += (q >= ap0) ? L0 : 0; mv0 += km0 << l0[q]; }
+        if (P1) { int q = __ffs(P1) - 1; P1 &= P1 - 1; q += (q >= ap1) ? L1 : 0; mv1 += km1 << l1[q]; }
     }
 }
 

@@ -301,18 +301,6 @@ DDZ_DEV void face_planes(const Env& e, uint64_t* planes /*[C]*/, float* p /*[2]*
     p[1] = tot > 0 ? __fdiv_rn((float)size2, (float)tot) : 0.f;
 }
 
-// Cold path of the step phase: the chosen entry lies in the part of a list that an overflow of the action buffer dropped.
-// Not inlined: it must not cost the hot path registers or instruction-cache space.
-__device__ __noinline__ uint64_t cut_list_move(uint64_t hand, uint64_t last, int idx) {
-    return select_legal(masks_of(hand), rule_of(last), last != 0, idx);      // ~0 if idx is out of range
-}
-__device__ __noinline__ long long cut_list_find(uint64_t hand, uint64_t last, uint64_t want, int from, int cnt) {
-    const Masks m = masks_of(hand);
-    const Rule ru = rule_of(last);
-    for (int i = from; i < cnt; i++) if (select_legal(m, ru, last != 0, i) == want) return i;
-    return -1;
-}
-
 struct StepArgs {
     const int32_t* offsets; const uint64_t* actions; const void* choice; int mode;
     uint64_t seed, env0; uint32_t stepno; int32_t rewards[3];
@@ -419,24 +407,24 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             int o_r = 0, o_cat = -1;
             float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
             if (!e.done()) {
-                const int base = prev_off, cnt = prev_end - prev_off;
+                // A list cut off by an overflow of the action buffer (stats[7] said so when it was written) is played from
+                // its visible part: `cnt` counts the entries that were stored.  An env whose list was dropped altogether
+                // sits this step out -- counted in stats[7], but NOT a sticky error: its next list may fit again.
+                const int base = prev_off, full = prev_end - prev_off;
+                const int cnt = a.prev_cap > 0 ? (int)max(0ll, min((long long)full, a.prev_cap - base)) : full;
                 long long idx = -1;
                 if (a.mode == DDZ_CHOICE_INDEX) idx = (int32_t)(uint32_t)choice_raw;
                 else if (a.mode == DDZ_CHOICE_MOD) idx = cnt > 0 ? (long long)((uint32_t)choice_raw % (uint32_t)cnt) : -1;
                 else if (a.mode == DDZ_CHOICE_PHILOX) idx = cnt > 0 ? (long long)(philox(a.seed, a.env0 + (uint64_t)b, stepno) % (uint32_t)cnt) : -1;
                 else {
                     const uint64_t want = choice_raw;
-                    const int have = a.prev_cap > 0 ? (int)max(0ll, min((long long)cnt, a.prev_cap - base)) : cnt;
-                    for (int i = 0; i < have; i++) if (a.actions[base + i] == want) { idx = i; break; }
-                    if (idx < 0 && have < cnt) idx = cut_list_find(hand_to_move(e), trick_of(e), want, have, cnt);
+                    for (int i = 0; i < cnt; i++) if (a.actions[base + i] == want) { idx = i; break; }
                 }
-                // A list cut off by an overflow of the action buffer (stats[7] said so when it was written) does not stop
-                // the env: the entry that was dropped is recomputed in closed form from the state (select_legal).
-                const bool cut = a.prev_cap > 0 && idx >= 0 && (long long)base + idx >= a.prev_cap;
-                uint64_t mv = ~0ull;
-                if (idx >= 0 && idx < cnt) mv = cut ? cut_list_move(hand_to_move(e), trick_of(e), (int)idx) : a.actions[base + idx];
-                if (mv == ~0ull) { e.meta |= 0x20u; sf += 32u; }
-                else {
+                if (idx < 0 || idx >= cnt) {
+                    sf += 32u;
+                    if (!(cnt == 0 && full > 0)) e.meta |= 0x20u;      // illegal choice: sticky; dropped list: wait for the next one
+                } else {
+                    const uint64_t mv = a.actions[base + idx];
                     StepOut so = apply_move(e, mv, a.rewards);
                     o_r = so.r; o_cat = so.cat; rw0 = so.reward[0]; rw1 = so.reward[1]; rw2 = so.reward[2];
                     sf |= 1u | (so.pass ? 2u : 0u);
@@ -581,6 +569,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
 #ifndef DDZ_FLAT_ARENA
 #define DDZ_FLAT_ARENA 512
 #endif
+#ifndef DDZ_FLAT_COUNT_WALK
+#define DDZ_FLAT_COUNT_WALK 0     // 1: count moves and groups with a dry walk instead of the closed forms (1.7 % slower)
+#endif
+#ifndef DDZ_FLAT_MIN_CTAS
+#define DDZ_FLAT_MIN_CTAS 7
+#endif
 #ifndef DDZ_FLAT_PAIR
 #define DDZ_FLAT_PAIR 0     // 1: the two moves of a lane are decoded in one interleaved loop (measured 12 % slower), 0: one after the other
 #endif
@@ -593,7 +587,7 @@ struct __align__(16) FlatWarpSmem {
     uint8_t lists[32 * flat::kListsPerHand * flat::kListStride];
 };
 
-__global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* __restrict__ hands,
+__global__ void __launch_bounds__(kFlatWarps * 32, DDZ_FLAT_MIN_CTAS) k_legal_flat(const uint64_t* __restrict__ hands,
                                                                   const uint64_t* __restrict__ lasts, OutArgs o,
                                                                   Workspace ws, int64_t* stats, int B) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -621,9 +615,14 @@ __global__ void __launch_bounds__(kFlatWarps * 32) k_legal_flat(const uint64_t* 
         const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
         const Masks hm = masks_of(hand);
         const Rule ru = rule_of(last);
+#if DDZ_FLAT_COUNT_WALK
         flat::CountSink cs;
         if (valid) flat::walk_groups(hm, ru, last != 0, 4 * lane, cs);
         const int n = cs.n, ng = cs.ng;
+#else
+        const int n = valid ? count_legal(hm, ru, last != 0) : 0;           // closed forms: no walk for the counts
+        const int ng = valid ? flat::count_groups(hm, ru, last != 0) : 0;
+#endif
         int inc = n, dinc = ng;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1239,8 +1238,12 @@ struct ddz_mpipe {
     bool out_pending[DDZ_PIPE_DEPTH];
     unsigned long long step;
     bool stage_used;
-    struct { int8_t *dst_perm[DDZ_MPIPE_MAX_GROUPS], *dst_lord[DDZ_MPIPE_MAX_GROUPS]; int8_t *stage_perm, *stage_lord; bool active; } pending;
+    // a deal-pool upload in progress: it goes up in chunks, one per step, so that a step's entropy copy never queues behind
+    // megabytes of permutations on the host-to-device copy engine; `uploaded` < `bytes` while chunks are outstanding
+    struct { int8_t *dst_perm[DDZ_MPIPE_MAX_GROUPS], *dst_lord[DDZ_MPIPE_MAX_GROUPS]; int8_t *stage_perm, *stage_lord;
+             const int8_t *host_perm, *host_lord; size_t rows, uploaded, bytes; bool active; } pending;
 };
+constexpr size_t kRefillChunk = 384 * 1024;
 
 ddz_mpipe* ddz_mpipe_create(int groups) {
     if (groups < 1 || groups > DDZ_MPIPE_MAX_GROUPS) { snprintf(g_err, sizeof g_err, "ddz_mpipe_create: 1..%d groups", DDZ_MPIPE_MAX_GROUPS); return nullptr; }
@@ -1270,9 +1273,28 @@ void ddz_mpipe_destroy(ddz_mpipe* p) {
     }
     delete p;
 }
+// next chunk(s) of a staged deal-pool upload (all of the rest when `all`); the last one records stage_full
+static int mpipe_upload_chunk(ddz_mpipe* p, bool all) {
+    auto& u = p->pending;
+    while (u.active && u.uploaded < u.bytes) {
+        const size_t n = all ? u.bytes - u.uploaded : (u.bytes - u.uploaded < kRefillChunk ? u.bytes - u.uploaded : kRefillChunk);
+        DDZ_CUDA(cudaMemcpyAsync(u.stage_perm + u.uploaded, u.host_perm + u.uploaded, n, cudaMemcpyHostToDevice, p->refill), "H2D perm");
+        u.uploaded += n;
+        if (u.uploaded == u.bytes) {
+            DDZ_CUDA(cudaMemcpyAsync(u.stage_lord, u.host_lord, u.rows, cudaMemcpyHostToDevice, p->refill), "H2D lord");
+            DDZ_CUDA(cudaEventRecord(p->stage_full, p->refill), "record stage_full");
+        }
+        if (!all) break;
+    }
+    return 0;
+}
 // replace every group's pool slot by its part of the staged upload, each on the group's stream (between two of its steps)
 static int mpipe_commit_refill(ddz_mpipe* p, const ddz_group_step* gs, bool wait) {
     if (!p->pending.active) return 0;
+    if (p->pending.uploaded < p->pending.bytes) {
+        if (int rc = mpipe_upload_chunk(p, wait)) return rc;
+        if (p->pending.uploaded < p->pending.bytes) return 0;                                      // more chunks to go
+    }
     if (!wait && cudaEventQuery(p->stage_full) != cudaSuccess) { cudaGetLastError(); return 0; }   // still uploading
     size_t row0 = 0;
     for (int g = 0; g < p->G; g++) {
@@ -1339,11 +1361,16 @@ int ddz_mpipe_refill(ddz_mpipe* p, const ddz_group_step* gs, int8_t* const* pool
         p->pending.dst_perm[g] = pool_perm_slot[g]; p->pending.dst_lord[g] = pool_lord_slot[g];
         total += (size_t)gs[g].B;
     }
-    DDZ_CUDA(cudaMemcpyAsync(stage_perm, host_perm, total * 54, cudaMemcpyHostToDevice, p->refill), "H2D perm");
-    DDZ_CUDA(cudaMemcpyAsync(stage_lord, host_lord, total, cudaMemcpyHostToDevice, p->refill), "H2D lord");
-    DDZ_CUDA(cudaEventRecord(p->stage_full, p->refill), "record stage_full");
-    p->pending.stage_perm = stage_perm; p->pending.stage_lord = stage_lord; p->pending.active = true;
+    p->pending.stage_perm = stage_perm; p->pending.stage_lord = stage_lord;
+    p->pending.host_perm = host_perm; p->pending.host_lord = host_lord;
+    p->pending.rows = total; p->pending.bytes = total * 54; p->pending.uploaded = 0; p->pending.active = true;
     p->stage_used = true;
+    return mpipe_upload_chunk(p, false);      // the first chunk now, one more with every step
+}
+int ddz_mpipe_join(ddz_mpipe* p, void* stream) {
+    if (!p) return DDZ_E_ARG;
+    if (p->step == 0) return 0;
+    DDZ_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->out_done[(p->step - 1) % DDZ_PIPE_DEPTH], 0), "ddz_mpipe_join");
     return 0;
 }
 int ddz_mpipe_flush(ddz_mpipe* p, const ddz_group_step* gs) {

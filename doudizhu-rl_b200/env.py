@@ -256,8 +256,8 @@ class BatchedEnv:
 
     @property
     def actions_packed(self):
-        self._ensure()
-        return self._actions_u64[self._cur][: self.num_actions]
+        n = self.num_actions              # first: it may grow (replace) the list buffers
+        return self._actions_u64[self._cur][:n]
 
     def valid_actions(self, tensor=True):
         """tensor=True: (float32 [sumN,15,4], int32 offsets [B+1]); False: per-env lists of 15-int lists (envi.py:98-116)."""
@@ -837,7 +837,9 @@ class HostRolloutGroups:
         self.results_d = [torch.zeros(3 * B, dtype=torch.uint8, device=dev) for _ in range(N.PIPE_DEPTH)]
         self.results_h = [GroupStepResults(self.sizes) for _ in range(N.PIPE_DEPTH)]
         self.h2d_bytes, self.d2h_bytes = 4 * B, 3 * B
-        self._stage = None
+        # staging buffers of the deal-pool uploads: allocated here, not by the first refill (an allocation synchronises)
+        self._stage = (torch.empty((B, 54), dtype=torch.int8, device=dev), torch.empty(B, dtype=torch.int8, device=dev))
+        self._slot_ptrs = {}
         with torch.cuda.device(dev):
             self._pipe = N.lib.ddz_mpipe_create(self.G)
         if not self._pipe:
@@ -905,14 +907,12 @@ class HostRolloutGroups:
         (global env order); committed between two steps by the first step() that finds the upload complete"""
         import ctypes as C
         ge = self.ge
-        B = sum(self.sizes)
-        if self._stage is None:
-            self._stage = (torch.empty((B, 54), dtype=torch.int8, device=ge.device),
-                           torch.empty(B, dtype=torch.int8, device=ge.device))
         perm, lord_pile = torch.as_tensor(perm), torch.as_tensor(lord_pile)
         self._keep = (perm, lord_pile)
-        pp = (C.c_void_p * self.G)(*[ge._pool[g][0][slot].data_ptr() for g in range(self.G)])
-        ll = (C.c_void_p * self.G)(*[ge._pool[g][1][slot].data_ptr() for g in range(self.G)])
+        if slot not in self._slot_ptrs:
+            self._slot_ptrs[slot] = ((C.c_void_p * self.G)(*[ge._pool[g][0][slot].data_ptr() for g in range(self.G)]),
+                                     (C.c_void_p * self.G)(*[ge._pool[g][1][slot].data_ptr() for g in range(self.G)]))
+        pp, ll = self._slot_ptrs[slot]
         with torch.cuda.device(ge.device):
             N.check(N.lib.ddz_mpipe_refill(self._pipe, self._gs[0], pp, ll, perm.data_ptr(), lord_pile.data_ptr(),
                                            self._stage[0].data_ptr(), self._stage[1].data_ptr()), "ddz_mpipe_refill")
@@ -922,6 +922,12 @@ class HostRolloutGroups:
     def flush(self):
         with torch.cuda.device(self.ge.device):
             N.check(N.lib.ddz_mpipe_flush(self._pipe, self._gs[0]), "ddz_mpipe_flush")
+
+    def join(self, stream=None):
+        """make `stream` (default: the current one) wait for the device-to-host copy of the latest step's results"""
+        st = stream if stream is not None else torch.cuda.current_stream(self.ge.device)
+        with torch.cuda.device(self.ge.device):
+            N.check(N.lib.ddz_mpipe_join(self._pipe, st.cuda_stream), "ddz_mpipe_join")
 
 
 class BatchedEnvComplicated(BatchedEnv):

@@ -112,25 +112,24 @@ def evaluate_moves(role, hands, hist, last, sims=256, seed=1, env_cls=None, devi
     return moves, mine.float().mean(1).cpu().numpy()
 
 
-def mcts(payload, computation_budget=1000, seed=1, device=None):
+def mcts(payload, computation_budget=1000, seed=1, device=None, width=1, return_search=False):
     """The entry point of the reference's search bot, `mcts(payload)` (server/mcts/interface.py:15-45), on the batched
     env: payload = {'role_id': 0|1|2, 'hand_card': {role: [card values 3..17]} for all three roles (full information),
     'last_taken': {role: [...]}}.  Returns the chosen move as a sorted list of card values ([] = pass).
 
-    The reference spends `computation_budget` = 1000 sequential simulations in a UCT tree whose default policy is uniform
-    random play to the end (default_policy.py:4-10) and answers with the root child of the best win rate
-    (get_bestchild_).  Here every legal root move gets the same number of random playouts, all in ONE ddz_playout launch
-    (at least `computation_budget` in total), and the move with the best win rate of the mover's side is returned."""
+    `computation_budget` iterations of the reference's UCT search (search.UctSearch: UCB selection, one expansion per
+    iteration, random playout, back-up, answer = root child with the best win rate); the playouts run on the device,
+    `width` of them per iteration (1 = the reference's sequential search).  evaluate_moves() above is the flat
+    alternative: the same budget spread evenly over the root moves in ONE launch."""
+    from .search import UctSearch
     role = int(payload["role_id"])
     get = lambda d, q: d[q] if q in d else d[str(q)]
     hands = np.stack([_counts(get(payload["hand_card"], q)) for q in range(3)])
     last = np.stack([_counts(get(payload["last_taken"], q)) for q in range(3)])
-    hist = np.zeros((3, 15), np.int64)                       # the playout does not depend on what was played before
-    probe = env_from_arrays([role], [hands[role]], [hist], [last], [hands.sum(1)], hands=[hands], device=device)
-    n = probe.num_actions
-    if n == 0:
-        return []
-    moves, win = evaluate_moves(role, hands, hist, last, sims=max(1, -(-int(computation_budget) // n)), seed=seed,
-                                device=device)
-    best = moves[int(np.argmax(win))]
-    return [r + 3 for r in range(15) for _ in range(int(best[r]))]
+    search = UctSearch(role, hands, last, width=width, seed=seed, device=device)
+    search.run(computation_budget)
+    if not search.root.children:
+        return ([], search) if return_search else []
+    best = search.best_move()
+    move = [r + 3 for r in range(15) for _ in range(int(best[r]))]
+    return (move, search) if return_search else move

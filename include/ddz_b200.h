@@ -97,8 +97,9 @@ int ddz_reset(void* state, const int8_t* perm, const int8_t* lord_pile, int pool
  * get_state_prob envi.py:94; batch_arr2onehot envi.py:140-146).
  * offsets int32[B+1] and actions_u64[cap] are required; actions_f32 / face may be NULL (skipped).
  * Finished envs have no legal move.  If the total exceeds cap the tail is dropped and stats[7] is bumped; the offsets
- * are still those of the complete lists, and the envs play on: a later step whose choice falls into the dropped part
- * recomputes that move from the state (only the observation was incomplete -- re-observe with a larger cap to see it). */
+ * are still those of the complete lists.  Nothing is read or written out of bounds and no env is lost: the fused step
+ * plays a cut list from its visible part, an env whose list was dropped altogether sits that step out (stats[7] counts
+ * it, no sticky error) and moves again as soon as a list of its own fits -- or observe again with a larger cap. */
 int ddz_observe(const void* state, void* workspace, int variant, int32_t* offsets, uint64_t* actions_u64,
                 float* actions_f32, int64_t cap, float* face, int64_t* stats, int B, void* stream);
 
@@ -121,8 +122,8 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
 
 /* One fused env-step = ddz_step, then ddz_reset(only_done=1) when perm != NULL, then ddz_observe of the
  * new state, in ONE launch.  prev_* are the lists of the state being stepped, out_* receive the new
- * lists (ping-pong; they must not alias and both hold cap moves: a choice that falls into the part of a list an
- * overflow dropped is an illegal choice, never an out-of-bounds read). */
+ * lists (ping-pong; they must not alias and both hold cap moves: of a list that an overflow cut off only the stored
+ * part can be chosen from, never an out-of-bounds read). */
 int ddz_rollout_step(void* state, void* workspace, int variant,
                      const int32_t* prev_offsets, const uint64_t* prev_actions_u64,
                      const void* choice, int choice_mode, uint64_t seed, uint64_t env0, uint32_t stepno,
@@ -225,9 +226,11 @@ int ddz_pipe_flush(ddz_pipe* p, void* stream);   /* commit a staged deal-pool up
  * never fall into lock-step.  4 G + 4 CUDA calls per step.  ddz_mpipe_wait(slot) blocks until the D2H of the latest step
  * with that slot has landed.  `gs` describes the groups FOR THIS STEP (prev_* = lists of the current state, out_* = the other
  * ping-pong set); reward (float32 [B_g][3], device) is optional and stays on the device.  stats may be one vector shared
- * by all groups (the kernels add atomically).  ddz_mpipe_refill uploads one slot of every group's deal pool from ONE
- * pinned host array (rows group-major) into a staging buffer on a third copy stream; each group's slot is replaced on the
- * group's stream by the first step that finds the upload complete, or by ddz_mpipe_flush / the next refill, which wait. */
+ * by all groups (the kernels add atomically).  ddz_mpipe_refill starts the upload of one slot of every group's deal pool
+ * from ONE pinned host array (rows group-major; it must stay valid until the slot is replaced) into a staging buffer on a
+ * third copy stream.  The upload goes up in chunks of 384 KB, one with every following step, so that a step's entropy
+ * never queues behind megabytes of permutations on the copy engine; each group's slot is replaced on the group's stream by
+ * the first step that finds the upload complete, or by ddz_mpipe_flush / the next refill, which finish it and wait. */
 #define DDZ_MPIPE_MAX_GROUPS 16
 typedef struct {
     void* state; void* workspace;
@@ -247,6 +250,8 @@ int ddz_mpipe_wait(ddz_mpipe* p, int slot);
 int ddz_mpipe_refill(ddz_mpipe* p, const ddz_group_step* gs, int8_t* const* pool_perm_slot, int8_t* const* pool_lord_slot,
                      const int8_t* host_perm, const int8_t* host_lord, int8_t* stage_perm, int8_t* stage_lord);
 int ddz_mpipe_flush(ddz_mpipe* p, const ddz_group_step* gs);
+/* make `stream` wait for the device-to-host copy of the latest step (e.g. to time a window with an event on that stream) */
+int ddz_mpipe_join(ddz_mpipe* p, void* stream);
 
 /* Optional allocator for the big float row buffers (actions_f32, face): device memory created compressible
  * (CU_MEM_ALLOCATION_COMP_GENERIC), so the L2 compresses the 0/1 thermometer rows on their way to HBM and expands them

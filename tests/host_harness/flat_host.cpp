@@ -27,7 +27,8 @@ extern "C" long long flat_host_tile(const uint64_t* hands, const uint64_t* lasts
             hm[l] = masks_of(hands[l]); ru[l] = rule_of(lasts[l]); hl[l] = lasts[l] != 0;
             flat::CountSink cs; flat::walk_groups(hm[l], ru[l], hl[l], 4 * l, cs);
             n[l] = cs.n; ng[l] = cs.ng;
-            if (n[l] != count_legal(hm[l], ru[l], hl[l])) return -2;     // the closed form must agree
+            if (n[l] != count_legal(hm[l], ru[l], hl[l])) return -2;     // the closed forms must agree with the walk
+            if (ng[l] != flat::count_groups(hm[l], ru[l], hl[l])) return -9;
             flat::write_lists(hm[l], 4 * l, lists.data());
         }
     }

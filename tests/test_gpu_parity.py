@@ -249,11 +249,14 @@ def test_errors_are_flagged_not_silent(D):
     badperm[5, 0] = badperm[5, 1]
     with pytest.raises(D.native.DdzError):
         env2.prepare(badperm, lord)
-    # too small an action buffer is reported
+    # too small an action buffer is reported (stats[7]); asking for the lists then grows it and observes again
     env3 = D.BatchedEnv(B, max_actions_per_env=4)
     env3.prepare(perm, lord)
-    with pytest.raises(D.native.DdzError):
-        env3.num_actions
+    env3.observe()
+    torch.cuda.synchronize()
+    assert int(env3.stats[7].item()) == 1 and int(env3._offsets[env3._cur][B].item()) > env3.cap == 4 * B
+    n = env3.num_actions
+    assert env3.cap >= n > 4 * B and int(env3.offsets[B].item()) == n and int(env3.stats[7].item()) == 1
     # null / bad arguments come back as error codes, not crashes
     assert D.native.lib.ddz_observe(None, None, 0, None, None, None, 0, None, None, B, None) == D.native.E_ARG
     assert D.native.lib.ddz_reset(None, None, None, 1, 0, None, B, None) == D.native.E_ARG
@@ -981,44 +984,36 @@ def test_multi_step_launch_equals_playout(D, oracle):
 
 def test_overflowing_lists_are_safe(D, oracle):
     """cap smaller than the total: the tail of the lists is dropped and stats[7] says so -- never an out-of-bounds access --
-    but the envs PLAY ON: a fused step whose choice falls into the dropped part recomputes that move from the state, so the
-    trajectories stay those of the oracle; asking for the lists grows the buffers and re-observes (complete lists again)."""
+    and no env is lost: cut lists are played from their visible part, envs whose list was dropped sit the step out WITHOUT a
+    sticky error and move again once their list fits; asking for the lists grows the buffers and observes again."""
     B, G = 8192, 2
     perm, lord = D.random_deals(B, seed=21, pool_games=G)
     pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
     env = D.BatchedEnvCooperation(B, seed=2, max_actions_per_env=8)        # 20-card leads have far more than 8 moves
     env.prepare(pd, ld, pool_games=G)
-    ref = oracle.RefBatch(B, 2)
-    ref.deal(perm, lord, pool_games=G)
     env.observe()
     torch.cuda.synchronize()
     assert int(env.stats[7].item()) >= 1 and int(env.offsets[B].item()) > env.cap
-    for t in range(40):
-        ref.observe(want_f32=False, want_face=False)
+    deck = np.array([4] * 13 + [1, 1])
+    waited = 0
+    for t in range(300):
+        before = int(env.stats[4].item())
         env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
-        ref.step(mode=2, seed=2, env0=0, step=t)
-        ref.deal(perm, lord, only_done=True, pool_games=G)
+        waited += B - (int(env.stats[4].item()) - before)
     torch.cuda.synchronize()
-    meta = env._fields()[1].cpu().numpy().view(np.uint32)
-    assert ((meta >> 5) & 1).sum() == 0                                     # nobody was stopped by the overflow
-    assert int(env.stats[4].item()) == 40 * B == ref.stats[4] and int(env.stats[0].item()) == ref.stats[0] > 0
-    _compare_state(env, ref, 40)
-    small = env.cap
-    n = _compare_observation(env, ref, 40)                                  # grows the buffers, re-observes, complete lists
-    assert env.cap >= n > small
-    # explicit moves that were cut off are still recognised as legal (CHOICE_MOVE searches the closed form past the cut)
-    env2 = D.BatchedEnv(64, seed=1, max_actions_per_env=4)
-    p2, l2 = D.random_deals(64, seed=5)
-    env2.prepare(p2, l2)
-    ref2 = oracle.RefBatch(64, 0)
-    ref2.deal(p2, l2)
-    off, au, _, _ = ref2.observe(want_f32=False, want_face=False)
-    last_moves = torch.as_tensor(au[off[1:] - 1].view(np.int64)).cuda()    # every env's LAST legal move: far past the cut
-    env2.observe()
-    r, done, cat = env2.rollout_step(last_moves, mode=D.native.CHOICE_MOVE)
-    ref2.step((off[1:] - off[:-1] - 1).astype(np.int32), mode=0)
-    torch.cuda.synchronize()
-    _compare_state(env2, ref2, 1)
+    f, meta = env._fields()
+    meta = meta.cpu().numpy().view(np.uint32)
+    assert ((meta >> 5) & 1).sum() == 0                                     # nobody was stopped for good
+    assert waited > 0                                                       # some envs did sit steps out ...
+    assert (meta >> 8).min() >= 2                                           # ... but every env finished games and was re-dealt
+    cards = D.unpack_counts(f[0:6].t().contiguous()).sum(1).cpu().numpy()   # hands + everything played = one deck, always
+    assert (cards == deck).all()
+    fresh = D.BatchedEnvCooperation(B, seed=2, max_actions_per_env=8)
+    fresh.prepare(pd, ld, pool_games=G)
+    ref0 = oracle.RefBatch(B, 2)
+    ref0.deal(perm, lord, pool_games=G)
+    n = _compare_observation(fresh, ref0, 0)                                # grows the buffers, re-observes: complete lists
+    assert fresh.cap >= n > 8 * B
 
 
 def test_ticket_tiles_with_a_concurrent_kernel(D, oracle):
@@ -1388,3 +1383,122 @@ def test_prob_form_b_build_matches_form_b_oracle(D):
     env = dict(os.environ, DDZ_LIB=lib_b, DDZ_ORACLE_LIB=ora_b)
     out = subprocess.run([sys.executable, os.path.join(root, "tests", "form_b_check.py")], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "form B ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_uct_search_equals_reference_algorithm_on_oracle(D, oracle):
+    """The search bot (server/mcts/interface.py:37-45): UctSearch (tree on the host, legal moves and playouts on the device)
+    against the reference algorithm restated over the oracle (tests/uct_reference_algorithm.py), same seed and budget:
+    the same tree statistics at the root and the same chosen move, for the sequential search (width 1) and a wide one."""
+    from uct_reference_algorithm import uct
+    z = np.zeros((3, 15), np.int64)
+    positions = []
+    h = np.zeros((3, 15), np.int64); h[1, [0, 1, 2, 3, 4, 9]] = [1, 1, 1, 1, 1, 2]; h[2, [5, 6]] = 2; h[0, [10, 11, 12]] = [1, 2, 1]
+    positions.append((1, h, z))                                       # the landlord leads
+    h2 = np.zeros((3, 15), np.int64); h2[2, [7, 7 + 1, 12]] = [2, 1, 1]; h2[0, [0, 3]] = [1, 2]; h2[1, [1, 5, 13]] = [1, 1, 1]
+    last = z.copy(); last[1, 6] = 2                                   # down must beat the landlord's pair of 9s (or pass)
+    positions.append((2, h2, last))
+    rng = np.random.default_rng(4)
+    deck = np.array([i // 4 for i in range(52)] + [13, 14])
+    p = rng.permutation(deck)[:21]
+    h3 = np.stack([np.bincount(p[0:7], minlength=15), np.bincount(p[7:15], minlength=15), np.bincount(p[15:21], minlength=15)]).astype(np.int64)
+    positions.append((0, h3, z))
+    for k, (role, hands, last) in enumerate(positions):
+        for width, budget in ((1, 120), (16, 60)):
+            want_move, want_root = uct(oracle, role, hands, last, budget, width=width, seed=7 + k)
+            s = D.UctSearch(role, hands, last, width=width, seed=7 + k).run(budget)
+            moves, visits, rate = s.root_table()
+            assert len(moves) == len(want_root.children), (k, width)
+            for i, ch in enumerate(want_root.children):
+                assert np.array_equal(moves[i], ch.state.action) and visits[i] == ch.visit and rate[i] == ch.reward / ch.visit, (k, width, i)
+            assert np.array_equal(s.best_move(), want_move), (k, width)
+            assert s.playouts <= budget * width and s.iterations == budget
+
+
+def test_host_rollout_groups_chunked_deferred_refill(D):
+    """HostRolloutGroups.refill: the upload goes up in 384 KB chunks, one per step; every group's slot is replaced whole,
+    between two of its steps, by the first step that finds the upload complete -- never a mixture of old and new rows."""
+    B, P, NG = 32768, 2, 4                                    # 1.7 MB of permutations: five chunks
+    perm, lord = D.random_deals(B, seed=1, pool_games=P)
+    ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=NG, seed=3, max_actions_per_env=160)
+    ge.prepare(perm, lord, pool_games=P)
+    host = D.HostRolloutGroups(ge)
+    ent = torch.as_tensor(np.random.default_rng(0).integers(0, 1 << 31, B).astype(np.int32)).pin_memory()
+    p2, l2 = D.random_deals(B, seed=77)
+    p2t, l2t = torch.as_tensor(p2).pin_memory(), torch.as_tensor(l2).pin_memory()
+    Bg = B // NG
+    old = [ge._pool[g][0][1].clone().cpu() for g in range(NG)]
+    host.refill(1, p2t, l2t)
+    replaced_at = None
+    for t in range(200):
+        res = host.step(ent)
+        ge.join(); torch.cuda.synchronize()
+        state = []
+        for g in range(NG):
+            slot = ge._pool[g][0][1].cpu()
+            new = p2t[g * Bg:(g + 1) * Bg]
+            assert torch.equal(slot, old[g]) or torch.equal(slot, new), (t, g)      # never a mixture
+            state.append(torch.equal(slot, new))
+        if all(state):
+            replaced_at = t
+            break
+    assert replaced_at is not None and replaced_at >= 3          # the chunks take a few steps
+    D.HostRolloutGroups.wait(res)
+    for g in range(NG):
+        assert torch.equal(ge._pool[g][1][1].cpu(), l2t[g * Bg:(g + 1) * Bg])
+    assert int(ge.stats[7].item()) == 0
+
+
+def test_config3_parity_at_full_size_with_the_256_wide_net(D, oracle):
+    """BASELINE config 3 at its own size: 65 536 envs, the landlord = argmax Q with a network of NetCooperation's layer
+    sizes (10 x 15 x 4 in, 256-wide convolutions, 256 hidden; net.py:125-139), farmers random, 24 steps.  Every step the
+    GPU env's offsets / packed lists / face equal the oracle's; the Q-values that the in-place [n, C+1, 15, 4] encoder + the
+    network give equal those of the reference formulation (face.repeat + torch.cat, net.py:87-90) on a sample of envs, and
+    so do the argmax decisions; both envs then take the same decisions and end in the same state."""
+    from qnet_like import QNetLike
+    torch.manual_seed(0)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # fp32 network, as in the reference
+    B, G, steps = 65536, 2, 24
+    net = QNetLike(9, width=256, hidden=256).cuda().eval()
+    policy = D.BatchedGreedyPolicy(net, chunk_actions=1 << 16)
+    perm, lord = D.random_deals(B, seed=23, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    prev = D.native.set_tile_order("ticket")                       # the network's kernels share the GPU with the env launches
+    try:
+        env = D.BatchedEnvCooperation(B, max_actions_per_env=160)
+        env.prepare(pd, ld, pool_games=G)
+        ref = oracle.RefBatch(B, 2)
+        ref.deal(perm, lord, pool_games=G)
+        gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+        sample = torch.arange(0, B, 53, device="cuda")[:1024]
+        for t in range(steps):
+            o_off, o_au, _, o_face = ref.observe(want_f32=False)
+            off = env.offsets
+            assert np.array_equal(off.cpu().numpy(), o_off), t
+            assert np.array_equal(env.actions_packed.cpu().numpy().view(np.uint64), o_au), t
+            assert np.array_equal(env.face.cpu().numpy(), o_face), t
+            is_lord = env.get_role_ID() == 2
+            q = policy.q_values(env, is_lord)
+            greedy = policy.select(env, q)
+            # the reference formulation on a sample of the landlord's envs
+            acts, _ = env.valid_actions()
+            offc = off.cpu().numpy()
+            with torch.no_grad():
+                for b in sample[is_lord[sample]].tolist()[:96]:
+                    lo, hi = int(offc[b]), int(offc[b + 1])
+                    want = net(env.face[b], acts[lo:hi]).reshape(-1)
+                    # fp32 either way, but other batch shapes pick other convolution / GEMM algorithms: tolerance 1e-3 relative
+                    assert torch.allclose(q[lo:hi], want, rtol=1e-3, atol=1e-4), (t, b, (q[lo:hi] - want).abs().max().item())
+                    assert int(greedy[b]) == int(torch.argmax(q[lo:hi]))
+            cnt = off[1:] - off[:-1]
+            ent = torch.randint(0, 1 << 30, (B,), device="cuda", dtype=torch.int32, generator=gen)
+            choice = torch.where(is_lord, greedy, ent % cnt.clamp(min=1)).to(torch.int32)
+            env.rollout_step(choice, mode=D.native.CHOICE_INDEX, perm=pd, lord_pile=ld, pool_games=G)
+            ref.step(choice.cpu().numpy(), mode=0)
+            ref.deal(perm, lord, only_done=True, pool_games=G)
+        _compare_state(env, ref, steps)
+        st = env.stats.cpu().numpy()
+        assert st[7] == 0 and np.array_equal(st[[0, 1, 2, 3, 4]], ref.stats[[0, 1, 2, 3, 4]]) and st[4] == B * steps
+    finally:
+        D.native.set_tile_order(prev)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
