@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--no-single", action="store_true", help="skip the single-chain information run")
     ap.add_argument("--no-verify", action="store_true", help="skip the post-run check of a 512-env sample against the oracle")
     ap.add_argument("--stats-every", type=int, default=64, help="env-steps between two statistics all-reduces (multi-GPU)")
+    ap.add_argument("--clock-interval-ms", type=int, default=20, help="nvidia-smi polling interval of the clock sampler (0 = off)")
     ap.add_argument("--net-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="config 3: the consumer network")
     args = ap.parse_args()
     if args.envs is None:
@@ -109,13 +110,15 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, interval_ms=20):
+        self.gpu, self.proc, self.lines, self.interval = gpu_index, None, [], int(interval_ms)
 
     def start(self):
+        if self.interval <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -308,7 +311,7 @@ def run_config4(args):
     perm, lord = D.random_deals(B, seed=SEED + 1000 * rank, pool_games=P)
     barrier = make_barrier(torch, dev, world)
 
-    sampler = ClockSampler(local)       # samples from here to the end of the e2e region: the same kernel runs throughout
+    sampler = ClockSampler(local, args.clock_interval_ms)       # samples from here to the end of the e2e region: the same kernel runs throughout
     if rank == 0:
         sampler.start()
 
@@ -550,7 +553,7 @@ def run_config5(args):
     D, torch, rank, local, world, dev = setup_rank()
     n, K, W = args.envs, args.steps, max(args.warmup, 3)
     barrier = make_barrier(torch, dev, world)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_interval_ms)
     if rank == 0:
         sampler.start()
     hands_np, lasts_np = D.adversarial_pairs(n, seed=5 + rank)
@@ -596,10 +599,6 @@ def run_config5(args):
     for _ in range(Ke):
         e2e_call()
     x1.record()
-    for res in pending:                 # the host reads the last results (already on their way when x1 is recorded)
-        if res is not None:
-            D.HostRolloutGroups.wait(res)
-            sink[0] += int(res.done[0][0])
     barrier()
     clocks = sampler.stop()
     e2e_ms = x0.elapsed_time(x1)
@@ -679,7 +678,7 @@ def run_config3(args):
                     return inner.forward_state_action(x).float()
         net = Autocast()
     policy = D.BatchedGreedyPolicy(net, chunk_actions=1 << 16)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_interval_ms)
     sampler.start()
     perm, lord = D.random_deals(B, seed=SEED, pool_games=P)
     pd, ld = torch.as_tensor(perm).to(dev), torch.as_tensor(lord).to(dev)
