@@ -426,14 +426,14 @@ def run_config4(args):
     pending = [None] * DEPTH
 
     def e2e_step(i):
-        if i % REFILL == 0:
-            pp, ll = pool_h[(i // REFILL) % 2]
-            host.refill((i // REFILL) % P, pp, ll)
         old = pending[i % DEPTH]
         if old is not None:                                       # the host reads the results of step i-DEPTH
             D.HostRolloutGroups.wait(old)
             sink[0] += int(old.done[0][0]) + int(old.r[-1][-1])
         pending[i % DEPTH] = host.step(ent_h[i % R])
+        if i % REFILL == 0:                                       # after the step is on its way: the GPU never waits for it
+            pp, ll = pool_h[(i // REFILL) % 2]
+            host.refill((i // REFILL) % P, pp, ll)
 
     # warm-up: one untimed pass of the same shape (a pool upload and the steps that carry its chunks), then flush it, so
     # that no upload is half-way when the window opens and the first-use costs of the pinned pool buffers are paid
