@@ -9,6 +9,8 @@
     of the rank's slice (ddz_rollout_step: apply the chosen move, re-deal finished envs, generate the legal moves of the
     new state, write face [B,9,15,4] and the action one-hots).  A step writes ~0.5 GB, more than the 126 MB L2: no flush
     between iterations is needed.
+--config 2 (configs[1]): the same rollout with 4096 envs in one chain of launches (latency-bound; its parity test is
+    tests/test_gpu_parity.py::test_fused_rollout_bit_exact).
 --config 5 (configs[4]): legal-move microbench, 131 072 adversarial (hand, last) pairs per GPU, one
     "step" = one ddz_legal_moves call over all pairs; value = legal moves/s.
 --config 3 (configs[2]): 65 536 envs, the landlord = argmax Q over its legal moves with a NetCooperation-shaped 256-wide
@@ -60,12 +62,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5], help="BASELINE.json config number (1-based)")
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5], help="BASELINE.json config number (1-based)")
     ap.add_argument("--envs", type=int, default=None, help="envs (config 5: pairs) per GPU; default 131072 (config 3: 65536)")
     ap.add_argument("--prefill", type=int, default=150, help="untimed env-steps that bring the games to their steady-state mix")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=4, help="stream-parallel env groups per GPU (1 = one chain of launches)")
+    ap.add_argument("--groups", type=int, default=None, help="stream-parallel env groups per GPU (default 4; config 2: 1 = one chain of launches)")
     ap.add_argument("--no-single", action="store_true", help="skip the single-chain information run")
     ap.add_argument("--no-verify", action="store_true", help="skip the post-run check of a 512-env sample against the oracle")
     ap.add_argument("--stats-every", type=int, default=64, help="env-steps between two statistics all-reduces (multi-GPU)")
@@ -73,7 +75,9 @@ def parse_args():
     ap.add_argument("--net-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="config 3: the consumer network")
     args = ap.parse_args()
     if args.envs is None:
-        args.envs = 65536 if args.config == 3 else 131072
+        args.envs = {2: 4096, 3: 65536}.get(args.config, 131072)
+    if args.groups is None:
+        args.groups = 1 if args.config == 2 else 4
     return args
 
 
@@ -160,6 +164,10 @@ def workload_text(args):
     if args.config == 3:
         return ("BASELINE config 3: %d envs on 1 GPU, landlord = argmax Q over its legal moves (NetCooperation-shaped 256-wide "
                 "torch network, random-init), farmers uniform random; EnvCooperation face C=9" % args.envs)
+    if args.config == 2:
+        return ("BASELINE config 2: %d batched envs on 1 GPU, lord-vs-random rollout (all seats uniform random legal move, Philox "
+                "stream), EnvCooperation face C=9, fused step+redeal+legal+encode -- the latency-bound regime (less than one warp "
+                "per SM)" % args.envs)
     return ("BASELINE config 4 per-GPU slice: %d envs/GPU, lord-vs-random rollout (all seats uniform random legal move, "
             "Philox stream), EnvCooperation face C=9, fused step+redeal+legal+encode" % args.envs)
 
@@ -499,14 +507,16 @@ def run_config4(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": dict({"workload": workload_text(args), "baseline_config": 4,
+            "config": dict({"workload": workload_text(args), "baseline_config": args.config,
                             "envs_per_gpu": B, "env_groups_per_gpu": NG, "face_channels": CHANNELS, "mean_legal_moves": nbar,
                             "prefill_steps": args.prefill, "pool_games": P, "parallelism": "env-shard x%d" % world,
                             "launch": "CUDA graph replay of the 2-launch ping-pong pair, one chain per env group",
                             "collectives": ("none (single GPU)" if world == 1 else
                                             "stats all-reduce (int64[16], NCCL LL) %d time(s) in the timed region, every %d steps "
                                             "from the middle of the interval, on a side stream" % (exchanges, 2 * every)),
-                            "l2_policy": "per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6),
+                            "l2_policy": ("per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6) if B * eb > 126e6 else
+                                          "per-step output (%.0f MB) FITS the 126 MB L2 and is not flushed between steps: a latency "
+                                          "measurement of the launch chain, not a bandwidth line" % (B * eb / 1e6)),
                             "row_buffers": ("compressible device memory (CU_MEM_ALLOCATION_COMP_GENERIC: the L2 compresses "
                                             "the 0/1 thermometer rows on their way to HBM)" if compressed else "plain device memory"),
                             "games_finished": int(gstats[0].item()),
@@ -776,7 +786,7 @@ def main():
             if os.path.exists(lib) and time.time() - os.path.getmtime(lib) > 2.0:
                 break
             time.sleep(0.5)
-    {4: run_config4, 5: run_config5, 3: run_config3}[args.config](args)
+    {2: run_config4, 4: run_config4, 5: run_config5, 3: run_config3}[args.config](args)
 
 
 if __name__ == "__main__":

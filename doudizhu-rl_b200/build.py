@@ -31,5 +31,18 @@ def build_native(force=False, verbose=False, form_b=False):
     return lib
 
 
+def build_all(force=True):
+    """both layouts of the library (default + -DDDZ_PROB_FORM_B), compiled side by side"""
+    cmds = []
+    for form_b, lib in ((False, LIB), (True, LIB_FORM_B)):
+        if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in SRC):
+            continue
+        cmds.append(subprocess.Popen([nvcc_path()] + NVCC_FLAGS + (["-DDDZ_PROB_FORM_B"] if form_b else []) + ["-o", lib, SRC[0]]))
+    for p in cmds:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed (exit code %d)" % p.returncode)
+    return LIB, LIB_FORM_B
+
+
 if __name__ == "__main__":
     print(build_native(force=True, verbose=True))

@@ -44,11 +44,11 @@ class StepResults:
     """Outputs of one step in ONE contiguous buffer (a single D2H copy fetches them): r int8[B] | done uint8[B] |
     cat int8[B] | pad | reward float32[B,3]."""
 
-    def __init__(self, B, device, pin=False):
+    def __init__(self, B, device, pin=False, buf=None):
         self.B = B
         self.off_reward = _align(3 * B, 16)
         self.nbytes = self.off_reward + 12 * B
-        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.buf = buf if buf is not None else torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
         if pin:
             self.buf = self.buf.pin_memory()
         self.r = self.buf[0:B].view(torch.int8)
@@ -469,7 +469,7 @@ class BatchedEnv:
 
     def get_state_prob(self):
         """native get_state_prob (envi.py:94): float32 [B,120] = the two probability planes of the face, flattened."""
-        return self.face[:, self.C - 2:].reshape(self.B, 120)
+        return BatchedEnv.face.fget(self)[:, self.C - 2:].reshape(self.B, 120)
 
     @classmethod
     def get_state_prob_manual(cls, known60, size1, size2, device=None):
@@ -1022,13 +1022,28 @@ class Env(BatchedEnv):
 
     def __init__(self, debug=False, seed=None, device=None):
         self.old_cards = dict()                      # role -> hand before its latest move (envi.py:27, 65)
-        self._snap_key, self._snap_val = None, None
+        self._snap_key, self._snap_val, self._raw = None, None, None
+        self._last_results = (0, False, -1)
+        self._face_copy = self._acts_copy = None
         self.verbose = bool(debug)                   # envi.py:44-61 narrates every move when debug=True
         super().__init__(1, debug=debug, seed=seed, device=device)
+        # Everything the single-env loop of game.py asks for after a decision lives in ONE 160-byte device block -- the
+        # state (19 words), both result sets (r | done | cat | reward) and both offset pairs -- mirrored to pinned host
+        # memory by one async copy: ONE synchronisation per decision instead of one per getter.
+        dev = self.device
+        self._blob = torch.zeros(40, dtype=torch.int32, device=dev)
+        self._state = self._blob[0:19]
+        self._results = [StepResults(1, dev, buf=self._blob[20 + 8 * i:27 + 8 * i].view(torch.uint8)) for i in range(2)]
+        self._offsets = [self._blob[36:38], self._blob[38:40]]
+        self._mirror = torch.zeros(40, dtype=torch.int32).pin_memory()
+        self._mirror_np = self._mirror.numpy()
+        self._choice_h = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._choice_d = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.reset()
 
     def reset(self):
         self.old_cards = dict()
-        self._snap_val = None
+        self._snap_val = self._face_copy = self._acts_copy = None
         return super().reset()
 
     @classmethod
@@ -1046,56 +1061,106 @@ class Env(BatchedEnv):
             print("\n%s %s手牌: %s" % (char, name, self.cards2str(before)))
             print("%s %s出牌： %s，分别剩余： %s" % (char, name, self.cards2str(played), self.left))
 
+    # The reference returns NEW tensors from face / valid_actions (envi.py:96,113): game.py keeps them across later steps
+    # (s0, a0 of a transition, game.py:95-127).  The batched buffers are overwritten by the next observation, so the view
+    # hands out copies (one per state).
     @property
     def face(self):
-        return BatchedEnv.face.fget(self)[0]
+        if self._face_copy is None or self._face_copy[0] != self._key():
+            f = BatchedEnv.face.fget(self)[0].clone()
+            self._face_copy = (self._key(), f)
+        return self._face_copy[1]
 
     def valid_actions(self, tensor=True):
-        if tensor:
-            return super().valid_actions(True)[0]
-        return super().valid_actions(False)[0]
+        if not tensor:
+            return super().valid_actions(False)[0]
+        if self._acts_copy is None or self._acts_copy[0] != self._key():
+            a = super().valid_actions(True)[0].clone()
+            self._acts_copy = (self._key(), a)
+        return self._acts_copy[1]
 
-    # One 80-byte D2H per state serves every getter of the reference API (role, hands, hand-outs, history, left): the
+    def _key(self):
+        return (self._stepno, self._games_dealt, self._cur, self._fresh)
+
+    def _refresh_mirror(self, with_results=False):
+        """state, results of the latest step and the length of the fresh lists -> host: one copy, one synchronisation"""
+        self._mirror.copy_(self._blob, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        host = self._mirror_np
+        self._raw = host[:19].copy()
+        self._snap_val = None
+        self._snap_key = self._key()
+        if with_results:
+            b = host[20 + 8 * self._res:21 + 8 * self._res].view(np.int8)
+            self._last_results = (int(b[0]), bool(b[1]), int(b[2]))
+        if self._fresh:
+            self._n_total = int(host[37 + 2 * self._cur])
+
+    # One small D2H per state serves every getter of the reference API (role, hands, hand-outs, history, left): the
     # single-env loop of game.py asks for several of them per decision, and each would otherwise be its own sync.
     def _snap(self):
-        key = (self._stepno, self._games_dealt, self._cur, self._fresh)
-        if self._snap_key != key or self._snap_val is None:
-            host = self._state.cpu().numpy()                 # B = 1: nine uint64 fields + the meta word = 76 bytes
-            cnt = ((host[:18].view(np.uint64)[:, None] >> self._NIBBLE_SHIFTS) & 15).astype(np.int64)
-            m = int(host[18]) & 0xFFFFFFFF
-            self._snap_val = {"hand": cnt[0:3], "hist": cnt[3:6], "recent": cnt[6:9], "role": m & 3,
-                              "done": bool((m >> 2) & 1), "winner": (m >> 3) & 3}
-            self._snap_key = key
+        if self._snap_key != self._key() or self._raw is None:
+            self._refresh_mirror()
+        if self._snap_val is None:
+            cnt = ((self._raw[:18].view(np.uint64)[:, None] >> self._NIBBLE_SHIFTS) & 15).astype(np.int64)
+            meta = int(self._raw[18]) & 0xFFFFFFFF
+            self._snap_val = {"hand": cnt[0:3], "hist": cnt[3:6], "recent": cnt[6:9], "role": meta & 3,
+                              "done": bool((meta >> 2) & 1), "winner": (meta >> 3) & 3, "error": bool((meta >> 5) & 1)}
         return self._snap_val
 
-    def _results_host(self):
-        """(r, done, cat) of the latest step with one D2H (the three lie next to each other in the results buffer)"""
-        b = self._results[self._res].buf[:3].cpu().numpy()
-        return int(b[0:1].view(np.int8)[0]), bool(b[1]), int(b[2:3].view(np.int8)[0])
+    def observe(self):
+        super().observe()
+        self._refresh_mirror()
+        return self
+
+    def _decide(self, value, mode):
+        """One decision of the single-env loop = ONE launch (apply the move, legal moves + face of the new state:
+        ddz_rollout_step without re-deal) and ONE synchronisation.  value: python int (index / entropy / packed move)."""
+        self._ensure()
+        sn = self._snap()
+        role, before = sn["role"], self.arr2cards(sn["hand"][sn["role"]])
+        choice = None
+        if mode != N.CHOICE_PHILOX:
+            self._choice_h.view(torch.int64)[0] = int(value)
+            self._choice_d.copy_(self._choice_h, non_blocking=True)
+            choice = self._choice_d.view(torch.int64) if mode == N.CHOICE_MOVE else self._choice_d[0:1]
+        BatchedEnv.rollout_step(self, choice, mode=mode)
+        self._refresh_mirror(with_results=True)
+        if self.debug and self._snap()["error"]:
+            raise N.DdzError("step: the env flagged an error (illegal choice)")
+        self._note_move(role, before)
+        return self._last_results
 
     def step_manual(self, onehot_cards):
-        role, before = self.get_role_ID() - 1, self.get_curr_handcards()
-        super().step_manual(torch.as_tensor(onehot_cards, device=self.device).reshape(1, 15, 4))
-        self._snap_val = None
-        self._note_move(role, before)
-        return self._results_host()
+        """envi.py:63-70.  A row of valid_actions() (what dqn.py returns) is recognised by its address: no conversion."""
+        oh = onehot_cards
+        if (torch.is_tensor(oh) and oh.is_cuda and oh.dtype == torch.float32 and oh.numel() == 60 and oh.is_contiguous()
+                and self._acts_copy is not None and self._acts_copy[0] == self._key()):
+            off = oh.data_ptr() - self._acts_copy[1].data_ptr()
+            if 0 <= off < 240 * self._acts_copy[1].shape[0] and off % 240 == 0:
+                return self._decide(off // 240, N.CHOICE_INDEX)
+        if torch.is_tensor(oh):
+            oh = oh.detach().cpu().numpy()
+        counts = np.asarray(oh).reshape(15, 4).sum(-1).round().astype(np.int64)
+        packed = int((counts.astype(np.uint64) << (4 * np.arange(15, dtype=np.uint64))).sum())
+        return self._decide(packed, N.CHOICE_MOVE)
 
     def step_random(self, entropy=None):
-        role, before = self.get_role_ID() - 1, self.get_curr_handcards()
-        if entropy is not None:
-            entropy = np.asarray([entropy], dtype=np.uint32)
-        super().step_random(entropy)
-        self._snap_val = None
-        self._note_move(role, before)
-        return self._results_host()
+        if entropy is None:
+            return self._decide(0, N.CHOICE_PHILOX)
+        return self._decide(int(entropy) & 0xFFFFFFFF, N.CHOICE_MOD)
 
     def prepare(self, *args, **kw):
-        self._snap_val = None
+        self._raw = None
         return super().prepare(*args, **kw)
 
     def load_state_dict(self, sd):
-        self._snap_val = None
+        self._raw = None
         return super().load_state_dict(sd)
+
+    def get_state_prob(self):
+        """native get_state_prob (envi.py:94): float32 [120]"""
+        return super().get_state_prob()[0].clone()
 
     def get_role_ID(self):
         return self._snap()["role"] + 1

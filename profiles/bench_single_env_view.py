@@ -31,8 +31,24 @@ def main(games=40):
             steps += 1
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print(json.dumps({"workload": "EnvCooperation (B=1 view): face + valid_actions + step_random per decision",
-                      "games": games, "decisions": steps, "decisions_per_s": steps / dt, "us_per_decision": dt / steps * 1e6}))
+    out = {"workload": "EnvCooperation (B=1 view): face + valid_actions + step_random per decision",
+           "games": games, "decisions": steps, "decisions_per_s": steps / dt, "us_per_decision": dt / steps * 1e6}
+    # the agent's path (game.py:95-104): step_manual with a row of valid_actions(), as dqn.py returns it
+    steps2 = 0
+    t0 = time.perf_counter()
+    for g in range(games):
+        env.reset()
+        env.prepare()
+        done = False
+        while not done:
+            face = env.face
+            actions = env.valid_actions()
+            _, done, _ = env.step_manual(actions[(steps2 * 7) % actions.shape[0]])
+            steps2 += 1
+    torch.cuda.synchronize()
+    dt2 = time.perf_counter() - t0
+    out["step_manual_us_per_decision"] = dt2 / steps2 * 1e6
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

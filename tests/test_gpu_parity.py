@@ -1502,3 +1502,27 @@ def test_config3_parity_at_full_size_with_the_256_wide_net(D, oracle):
     finally:
         D.native.set_tile_order(prev)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_legal_moves_respect_the_list_capacity(D, oracle):
+    """ddz_legal_moves with a buffer smaller than the lists: the stored prefix is exact, nothing is written past `cap`
+    (odd and even caps: the kernel stores pairs of moves), the offsets are those of the complete lists, stats[7] says so."""
+    rng = np.random.default_rng(8)
+    hands = np.concatenate([D.ADVERSARIAL_POOL[rng.integers(0, 10, 40)], _rand_hands(rng, 60, 5, 21)]).astype(np.int8)
+    lasts = np.zeros_like(hands)
+    want = [np.atleast_1d(oracle.pack(oracle.get_moves(h, l, fast=True))) for h, l in zip(hands, lasts)]
+    flat = np.concatenate(want)
+    hp = D.pack_counts(torch.as_tensor(hands).cuda()).contiguous()
+    lp = torch.zeros(len(hands), dtype=torch.int64, device="cuda")
+    for cap in (len(flat) + 5, len(flat), len(flat) - 1, 1001, 1000, 7, 0):
+        gen = D.MoveGenerator(len(hands), max_moves_per_hand=1)
+        gen.cap = cap
+        gen.actions = torch.full((len(flat) + 64,), -1, dtype=torch.int64, device="cuda")
+        acts, offs = gen.generate(hp, lp)
+        torch.cuda.synchronize()
+        got = acts.cpu().numpy()
+        keep = min(cap, len(flat))
+        assert np.array_equal(got[:keep].view(np.uint64), flat[:keep]), cap
+        assert (got[keep:] == -1).all(), cap
+        assert np.array_equal(offs.cpu().numpy(), np.concatenate([[0], np.cumsum([len(w) for w in want])])), cap
+        assert int(gen.stats[7].item()) == (1 if cap < len(flat) else 0), cap
