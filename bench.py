@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--groups", type=int, default=None, help="stream-parallel env groups per GPU (default 4; config 2: 1 = one chain of launches)")
+    ap.add_argument("--steps-per-graph", type=int, default=2, help="env-steps captured in one CUDA graph per env group (even)")
     ap.add_argument("--no-single", action="store_true", help="skip the single-chain information run")
     ap.add_argument("--no-verify", action="store_true", help="skip the post-run check of a 512-env sample against the oracle")
     ap.add_argument("--stats-every", type=int, default=64, help="env-steps between two statistics all-reduces (multi-GPU)")
@@ -330,8 +331,9 @@ def run_config4(args):
     ge.prepare(perm, lord, pool_games=P)
     for _ in range(args.prefill):
         ge.rollout_step()
-    ge.capture(steps_per_graph=2)       # the loop is launch-bound from Python: replay the ping-pong pair as a CUDA graph
-    for _ in range(max(W, 3)):
+    SPG = args.steps_per_graph if (args.steps_per_graph % 2 == 0 and K % args.steps_per_graph == 0) else 2
+    ge.capture(steps_per_graph=SPG)     # the loop is launch-bound from Python: replay SPG steps per group as one CUDA graph
+    for _ in range(max(-(-max(W, 3) // SPG), 2)):
         ge.replay()
     ge.join()
     torch.cuda.synchronize(dev)
@@ -348,8 +350,8 @@ def run_config4(args):
         with torch.cuda.stream(side):
             dist.all_reduce(snap)
         side.synchronize()
-    half = K // 2
-    every = max(1, args.stats_every // 2)
+    half = K // SPG                     # graph replays in the window
+    every = max(1, args.stats_every // SPG)
     coll_ev = []                        # (issued, done) events of every exchange, on the side stream: where the window's time goes
     barrier()
     e0.record()
@@ -361,7 +363,7 @@ def run_config4(args):
         # (reference game.py:209-226 logs these counters every log_every episodes).  It is issued from the MIDDLE of each
         # interval, never straight after the barrier: whatever skew the ranks have leaving the barrier is absorbed by the
         # steps already queued, instead of landing on the rank that arrives first.
-        if side is not None and i % every == min(every // 2, half // 2):
+        if side is not None and (i == (half - 1) // 2 if half <= every else i % every == every // 2):
             snap_ready.record(ge.streams[0])
             side.wait_event(snap_ready)
             with torch.cuda.stream(side):
@@ -372,7 +374,7 @@ def run_config4(args):
                 c1.record()
                 coll_ev.append((c0, c1))
             exchanges += 1
-    if K % 2:
+    for _ in range(K - half * SPG):
         ge.rollout_step()
     ge.join()
     if side is not None:
@@ -510,10 +512,10 @@ def run_config4(args):
             "config": dict({"workload": workload_text(args), "baseline_config": args.config,
                             "envs_per_gpu": B, "env_groups_per_gpu": NG, "face_channels": CHANNELS, "mean_legal_moves": nbar,
                             "prefill_steps": args.prefill, "pool_games": P, "parallelism": "env-shard x%d" % world,
-                            "launch": "CUDA graph replay of the 2-launch ping-pong pair, one chain per env group",
+                            "launch": "CUDA graph replay, %d env-steps per graph, one chain per env group" % SPG,
                             "collectives": ("none (single GPU)" if world == 1 else
                                             "stats all-reduce (int64[16], NCCL LL) %d time(s) in the timed region, every %d steps "
-                                            "from the middle of the interval, on a side stream" % (exchanges, 2 * every)),
+                                            "from the middle of the interval, on a side stream" % (exchanges, SPG * every)),
                             "l2_policy": ("per-step output (%.0f MB) exceeds the 126 MB L2; no flush" % (B * eb / 1e6) if B * eb > 126e6 else
                                           "per-step output (%.0f MB) FITS the 126 MB L2 and is not flushed between steps: a latency "
                                           "measurement of the launch chain, not a bandwidth line" % (B * eb / 1e6)),

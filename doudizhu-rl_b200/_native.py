@@ -14,7 +14,7 @@ CHOICE_INDEX, CHOICE_MOD, CHOICE_PHILOX, CHOICE_MOVE = range(4)
 MAX_LEGAL = 512
 STEPNO_AUTO = 0xFFFFFFFF
 PIPE_DEPTH = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

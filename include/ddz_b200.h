@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DDZ_ABI_VERSION 1
+#define DDZ_ABI_VERSION 2   /* 2: ddz_mpipe_*, ddz_set_tile_order, ddz_prob_form; cut lists are played from their visible part */
 #define DDZ_MAX_LEGAL 512  /* upper bound of legal moves of one decision (worst known hand: 497) */
 
 #define DDZ_E_ARG -1     /* bad argument (NULL pointer, B <= 0, unknown variant/mode) */
