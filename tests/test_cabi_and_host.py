@@ -158,3 +158,52 @@ def test_replay_buffer_and_td_step_on_cpu():
     assert float(dqn.target_net.w.detach()) != 7.0
     dqn.update_target(20)
     assert float(dqn.target_net.w.detach()) == 7.0
+
+
+def test_reference_arm_never_loads_the_product(oracle):
+    """bench.py --impl reference is the CPU arm: numpy + oracle/libddz_oracle.so only.  It must not import the product
+    package or map libddz_b200.so (the synthetic inputs come from doudizhu-rl_b200/deals.py, loaded by path)."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, io, contextlib\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '2', '--warmup', '1', '--config', '%d']\n"
+        "sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        "    bench.main()\n"
+        "line = json.loads(buf.getvalue().strip().splitlines()[-1])\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "bad = [m for m in sys.modules if m.startswith('doudizhu-rl_b200') or m == 'ddz_b200' or m == 'torch']\n"
+        "print(json.dumps({'line': line, 'bad_modules': bad, 'product_so': 'libddz_b200' in maps, 'oracle_so': 'libddz_oracle' in maps}))\n")
+    for cfg in (4, 5):
+        out = subprocess.run([sys.executable, "-c", code % (cfg, ROOT)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        assert res["bad_modules"] == [] and not res["product_so"] and res["oracle_so"]
+        line = res["line"]
+        assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+        assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+        assert line["unit"] == ("moves/s" if cfg == 5 else "env-steps/s")
+
+
+def test_adversarial_pool_fixture_matches_the_oracle(oracle):
+    """doudizhu-rl_b200/data/adversarial_pool.npz (BASELINE config 5's "previous moves"): the legal lead moves of the ten
+    pool hands, as the oracle's definitional generator gives them; adversarial_pairs is deterministic and half-leading."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ddz_deals_t", os.path.join(ROOT, "doudizhu-rl_b200", "deals.py"))
+    deals = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(deals)
+    f = np.load(deals.POOL_FILE)
+    assert np.array_equal(f["pool"], deals.ADVERSARIAL_POOL)
+    z = np.zeros(15, np.int8)
+    for i, h in enumerate(deals.ADVERSARIAL_POOL):
+        want = oracle.pack(oracle.get_moves(h, z, fast=False))
+        assert np.array_equal(f["lead_moves"][f["lead_off"][i]:f["lead_off"][i + 1]], want)
+    assert f["lead_off"][1] - f["lead_off"][0] == 497                      # the worst hand of all 20-card hands
+    h1, l1 = deals.adversarial_pairs(4096, seed=9)
+    h2, l2 = deals.adversarial_pairs(4096, seed=9)
+    assert np.array_equal(h1, h2) and np.array_equal(l1, l2) and 0.4 < (l1 == 0).mean() < 0.6
+    assert set(h1.tolist()) <= set(deals.pack_counts_np(deals.ADVERSARIAL_POOL).tolist())
