@@ -571,11 +571,19 @@ class GraphedRollout:
             env.rollout_step(**kw)
         env._stepno = stepno          # capture launched nothing; the device counter still holds `stepno`
         self._next = stepno
+        self._cur0 = env._cur         # the ping-pong set the graph's first launch reads
+        self._gen = env._buf_gen
 
     def replay(self):
         """two env-steps"""
-        if self.env._stepno != self._next:        # stepped by other means since the last replay
-            self.env._sync_auto_step()
+        env = self.env
+        if env._buf_gen != self._gen:
+            raise N.DdzError("the list buffers were reallocated after the capture: capture again")
+        if env._cur != self._cur0:                # an odd number of eager fused steps in between: the graph reads the other set
+            env._cur, env._fresh = self._cur0, False
+        env._ensure()                             # e.g. after step() / step_random(): lists of the CURRENT state, in that set
+        if env._stepno != self._next:             # stepped by other means since the last replay
+            env._sync_auto_step()
         self.graph.replay()
         self.env._stepno += 2
         self._next = self.env._stepno
@@ -667,14 +675,19 @@ class GroupedEnv:
                 for _ in range(self.steps_per_graph):
                     env.rollout_step(perm=pg, lord_pile=lg, pool_games=P, auto_step=True)
             env._stepno = stepno
-            env._graph_next = stepno
+            env._graph_next, env._graph_cur0, env._graph_gen = stepno, env._cur, env._buf_gen
             self.graphs.append(graph)
         torch.cuda.synchronize(self.device)
 
     def replay(self):
         for g, graph in enumerate(self.graphs):
             env = self.envs[g]
+            if env._buf_gen != env._graph_gen:
+                raise N.DdzError("the list buffers were reallocated after the capture: capture again")
             with torch.cuda.stream(self.streams[g]):
+                if env._cur != env._graph_cur0:        # an odd number of eager / host-pipe steps in between
+                    env._cur, env._fresh = env._graph_cur0, False
+                env._ensure()
                 if env._stepno != env._graph_next:     # stepped by other means (eager step, host pipe) since the last replay
                     env._sync_auto_step()
                 graph.replay()
@@ -863,6 +876,7 @@ class HostRolloutGroups:
                 q.reward = e._results[nxt].reward.data_ptr()
                 q.cap, q.env0, q.B, q.stream = e.cap, e.env0, e.B, ge.streams[g].cuda_stream
             self._gs[cur] = arr
+        self._gens = [e._buf_gen for e in ge.envs]
         e0 = ge.envs[0]
         self._const = (C.c_int(e0.VARIANT), C.c_uint64(e0.seed), C.c_void_p(e0._rewards.data_ptr()), C.c_int(self.P),
                        C.c_void_p(ge.stats.data_ptr()))
@@ -877,6 +891,13 @@ class HostRolloutGroups:
         """entropy_h: pinned int32 [B] (global env order).  Returns the GroupStepResults this step fills; valid after
         wait(results), reused PIPE_DEPTH steps later."""
         ge, k = self.ge, self.i % N.PIPE_DEPTH
+        if [e._buf_gen for e in ge.envs] != self._gens:
+            raise N.DdzError("an env's list buffers were reallocated: build a new HostRolloutGroups")
+        for g, e in enumerate(ge.envs):
+            if not e._fresh or e._cur != ge.envs[0]._cur:      # stepped eagerly in between: lists of the current state first
+                with torch.cuda.stream(ge.streams[g]):
+                    e._cur, e._fresh = ge.envs[0]._cur, e._fresh and e._cur == ge.envs[0]._cur
+                    e._ensure()
         cur = ge.envs[0]._cur
         variant, seed, rewards, P, stats = self._const
         args = (self._pipe, self._gs[cur], variant, entropy_h.data_ptr(), self.entropy_d[k].data_ptr(), seed,

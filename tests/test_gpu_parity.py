@@ -1526,3 +1526,46 @@ def test_legal_moves_respect_the_list_capacity(D, oracle):
         assert (got[keep:] == -1).all(), cap
         assert np.array_equal(offs.cpu().numpy(), np.concatenate([[0], np.cumsum([len(w) for w in want])])), cap
         assert int(gen.stats[7].item()) == (1 if cap < len(flat) else 0), cap
+
+
+def test_graph_replay_after_steps_that_bypass_the_device_counter(D, oracle):
+    """Only the fused launches keep the device-side Philox step counter up to date.  step_random() (ddz_step) and a state
+    restored with load_state_dict advance / set the step number on the host alone: a graph replay after them must re-arm
+    the counter, or it would draw moves from step numbers that were already used."""
+    B, G, seed = 512, 4, 77
+    perm, lord = D.random_deals(B, seed=2, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    env = D.BatchedEnvCooperation(B, seed=seed)
+    env.prepare(pd, ld, pool_games=G)
+    ref = oracle.RefBatch(B, 2)
+    ref.deal(perm, lord, pool_games=G)
+    t = 0
+
+    def ref_steps(k):
+        nonlocal t
+        for _ in range(k):
+            ref.observe(want_f32=False, want_face=False)
+            ref.step(mode=2, seed=seed, step=t); ref.deal(perm, lord, only_done=True, pool_games=G); t += 1
+
+    gr = D.GraphedRollout(env, pd, ld, G)
+    for _ in range(5):
+        gr.replay()
+    ref_steps(10)
+    for _ in range(3):                                   # eager steps through ddz_step: the device counter does not see them
+        env.step_random()
+        env.prepare(pd, ld, only_done=True, pool_games=G)
+    ref_steps(3)
+    for _ in range(4):
+        gr.replay()
+    ref_steps(8)
+    _compare_state(env, ref, t)
+    sd = env.state_dict()
+    for _ in range(3):
+        gr.replay()
+    env.load_state_dict(sd)                              # back to step 21: the counter must follow
+    for _ in range(2):
+        gr.replay()
+    ref_steps(4)
+    _compare_state(env, ref, t)
+    _compare_observation(env, ref, t)
+    assert int(env.stats[7].item()) == 0
