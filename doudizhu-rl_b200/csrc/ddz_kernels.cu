@@ -74,7 +74,7 @@ constexpr int kHeavy = DDZ_HEAVY;                       // envs with more legal 
 DDZ_DEV bool kFaceSecond(int t) { return DDZ_PHASE_ORDER == 0 ? (t & 1) != 0 : DDZ_PHASE_ORDER == 2; }
 constexpr int kLookBack = DDZ_LOOKBACK;                     // look-back windows (of 32 predecessor tiles) fetched per round trip
 
-enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2, kRaw = 3 };
+enum Mode { kStepOnly = 0, kObserve = 1, kStepObserve = 2 };
 
 // The two probability planes of a face (native get_state_prob, envi.py:94; get_state_prob_manual, server/core.py:26-33) are
 // "cards nobody has shown yet", scaled by the share of each opponent's hand.  Their layout inside a rank's four slots is
@@ -331,8 +331,7 @@ struct __align__(128) WarpSmem {
 
 // V: face variant or -1 (no face).  MODE: see enum Mode.
 template <int V, int MODE>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, const uint64_t* __restrict__ raw_hands,
-                                                  const uint64_t* __restrict__ raw_lasts, StepArgs a, OutArgs o,
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, StepArgs a, OutArgs o,
                                                   Workspace ws, int64_t* stats, int B) {
     constexpr bool STEP = (MODE == kStepOnly || MODE == kStepObserve);
     constexpr bool EMIT = (MODE != kStepOnly);
@@ -374,15 +373,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
     Rule ru{true, 0, 1, 0};
     int n = 0;
     unsigned int sf = 0;   // per-lane step summary for the stats: bit0 stepped, bit1 pass, bit2 game over, bits3-4 winner, bits5-6 errors
-    if (MODE == kRaw) {
-        if (valid) {
-            hand = raw_hands[b]; last = raw_lasts[b];
-            hm = masks_of(hand); ru = rule_of(last); n = count_legal(hm, ru, last != 0);
-        }
-    }
     int prev_off = 0, prev_end = 0;
     uint64_t choice_raw = 0;
-    if (MODE != kRaw && valid) {
+    if (valid) {
         if (STEP) {   // independent of the state: all of these loads are in flight together
             prev_off = a.offsets[b]; prev_end = a.offsets[b + 1];
             if (a.mode == DDZ_CHOICE_MOVE) choice_raw = ((const uint64_t*)a.choice)[b];
@@ -402,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         if (STEP && a.stepno == DDZ_STEPNO_AUTO) stepno = autostep;
     }
     const unsigned long long epoch_tag = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
-    if (MODE != kRaw && valid) {
+    if (valid) {
         if (STEP) {
             int o_r = 0, o_cat = -1;
             float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f;
@@ -437,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
             if (a.reward) { a.reward[3 * (size_t)b] = rw0; a.reward[3 * (size_t)b + 1] = rw1; a.reward[3 * (size_t)b + 2] = rw2; }
         }
     }
-    if (MODE != kRaw) {
+    {
         if (STEP) {
             if (a.perm) {   // re-deal the finished envs, the whole warp working on one of them at a time
                 const unsigned int need = __ballot_sync(FULL, valid && e.done());
@@ -489,8 +482,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) k_env(void* state, co
         // global base -- whatever wait it has is hidden behind the enumeration; then packed list + one-hot rows out
         long long base = 0, lim = 0;
         int w0 = 0;
-        // without a face the face-row buffer is free: the window grows from kWin to kWin + 576 moves (fewer passes over
-        // long lists in ddz_legal_moves)
+        // without a face (ddz_legal_emit) the face-row buffer is free: the window grows from kWin to kWin + 576 moves
         uint64_t* const wbuf = (V < 0) ? reinterpret_cast<uint64_t*>(sm.face) : sm.moves;
         const int win = (V < 0) ? (int)(sizeof(sm.face) / 8) + kWin : kWin;
 #pragma unroll 1
@@ -906,8 +898,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 template <int V, int MODE>
-static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts, const StepArgs& a, const OutArgs& o,
-                      void* workspace, int64_t* stats, int B, cudaStream_t st) {
+static int launch_env(void* state, const StepArgs& a, const OutArgs& o, void* workspace, int64_t* stats, int B, cudaStream_t st) {
     const size_t smem = (MODE == kStepOnly) ? 0 : kWarpsPerCta * sizeof(WarpSmem);
     Workspace ws = workspace ? ws_of(workspace) : Workspace{nullptr, nullptr};
     const int grid = (ntiles(B) + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -931,19 +922,19 @@ static int launch_env(void* state, const uint64_t* hands, const uint64_t* lasts,
     // is resident at once (and CTAs are dispatched in launch order, as they are in practice).  A caller whose other kernels
     // share the GPU asks for tickets instead (ddz_set_tile_order): correct under any dispatch order.
     oo.static_tiles = (g_tile_order.load(std::memory_order_relaxed) == DDZ_TILES_AUTO && grid <= resident) ? 1 : 0;
-    k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, hands, lasts, a, oo, ws, stats, B);
+    k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, a, oo, ws, stats, B);
     DDZ_LAUNCH_CHECK("k_env");
     return 0;
 }
 template <int MODE>
 static int launch_env_v(int variant, bool want_face, void* state, const StepArgs& a, const OutArgs& o, void* workspace,
                         int64_t* stats, int B, cudaStream_t st) {
-    if (!want_face) return launch_env<-1, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+    if (!want_face) return launch_env<-1, MODE>(state, a, o, workspace, stats, B, st);
     switch (variant) {
-        case 0: return launch_env<0, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
-        case 1: return launch_env<1, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
-        case 2: return launch_env<2, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
-        case 3: return launch_env<3, MODE>(state, nullptr, nullptr, a, o, workspace, stats, B, st);
+        case 0: return launch_env<0, MODE>(state, a, o, workspace, stats, B, st);
+        case 1: return launch_env<1, MODE>(state, a, o, workspace, stats, B, st);
+        case 2: return launch_env<2, MODE>(state, a, o, workspace, stats, B, st);
+        case 3: return launch_env<3, MODE>(state, a, o, workspace, stats, B, st);
     }
     return DDZ_E_ARG;
 }
@@ -1059,7 +1050,7 @@ int ddz_step(void* state, const int32_t* offsets, const uint64_t* actions_u64, c
     int rc = fill_step_args(a, offsets, actions_u64, choice, choice_mode, seed, env0, stepno, rewards, r, done, cat, reward);
     if (rc) return rc;
     OutArgs o{nullptr, nullptr, nullptr, 0, nullptr, 0};
-    return launch_env<-1, kStepOnly>(state, nullptr, nullptr, a, o, nullptr, stats, B, (cudaStream_t)stream);
+    return launch_env<-1, kStepOnly>(state, a, o, nullptr, stats, B, (cudaStream_t)stream);
 }
 
 int ddz_rollout_step(void* state, void* workspace, int variant,
