@@ -766,3 +766,110 @@ int ddz_ref_max_lead_moves_exhaustive(int nthreads, int8_t best_hand[15], long l
     if (visited) *visited = vis;
     return best;
 }
+
+/* ------------------------------------------------------------------ */
+/* the search bot's move list (server/mcts/evaluator.py, get_moves.py)  */
+/* ------------------------------------------------------------------ */
+/* the cards of a universe entry in the order card.py:34-159 writes them (rank indices 0..14): mains first, ascending,
+ * then the kickers ascending -- and for pair kickers the kicker LIST twice (`list(extra) * 2`, card.py:130,154) */
+static int action_cards(const act_t* a, int* out) {
+    int n = 0, main_mult = 0;
+    switch (a->cat) {
+        case 0: return 0;
+        case 1: case 2: case 3: case 4: main_mult = a->cat; break;
+        case 5: case 6: case 9: case 10: case 11: main_mult = 3; break;
+        case 7: main_mult = 1; break;
+        case 8: main_mult = 2; break;
+        case 12: out[0] = 13; out[1] = 14; return 2;
+        default: main_mult = 4; break;                       /* 13, 14 */
+    }
+    int L = (a->cat >= 7 && a->cat <= 11) ? a->len : 1;
+    for (int r = a->val; r < a->val + L; r++) for (int i = 0; i < main_mult; i++) out[n++] = r;
+    int kmult = (a->cat == 5 || a->cat == 10 || a->cat == 13) ? 1 : (a->cat == 6 || a->cat == 11 || a->cat == 14) ? 2 : 0;
+    if (kmult) {
+        int kick[8], nk = 0;
+        for (int r = 0; r < 15; r++) if ((r < a->val || r >= a->val + L) && a->cnt[r]) kick[nk++] = r;
+        if (a->cat == 6) { out[n++] = kick[0]; out[n++] = kick[0]; }          /* card.py:82  [extra] * 2 */
+        else for (int rep = 0; rep < kmult; rep++) for (int i = 0; i < nk; i++) out[n++] = kick[i];
+    }
+    return n;
+}
+
+/* evaluator.py:17-57, branch for branch; char2val = rank index + 3 (evaluator.py:4-9) */
+double ddz_ref_cards_value(const int8_t counts[15]) {
+    ensure();
+    for (int i = 0; i < 15; i++) if (counts[i] < 0 || counts[i] > 4) return -1e30;
+    int u = lookup(ddz_ref_pack(counts));
+    if (u < 0 || U[u].extra) return -1e30;                     /* not a key of cards_value: KeyError in the reference */
+    const act_t* act = &U[u];
+    int a[24], n = action_cards(act, a), c = act->cat;
+#define VAL(i) (a[i] + 3)
+    double v = 0;
+    if (c == 0) v = 0;
+    else if (c <= 3) {
+        v = VAL(0) - 10;
+        if (c == 2 && v > 0) v *= 1.5;
+        if (c == 3 && v > 0) v *= 2;
+    } else if (c == 4) v = 9;
+    else if (c <= 6) {
+        v = VAL(0) - 10;
+        if (v > 0) v *= 1.5;
+    } else if (c <= 9) {
+        v = (VAL(n - 1) - 10) / 2.0; if (v < 0) v = 0;
+    } else if (c == 10) {
+        int main_len = n / 4 * 3;
+        v = (VAL(n - 1) - 10) / 2.0; if (v < 0) v = 0;
+        for (int i = main_len; i < n; i++) if (VAL(i) > 10) v += VAL(i) - 10;
+    } else if (c == 11) {
+        int main_len = n / 5 * 3;
+        v = (VAL(n - 1) - 10) / 2.0; if (v < 0) v = 0;
+        for (int i = main_len; i < main_len + main_len / 3; i++) if (VAL(i) > 10) v += 1.5 * (VAL(i) - 10);
+    } else if (c == 12) v = 12;
+    else v = VAL(0) - 10;
+#undef VAL
+    return v;
+}
+
+/* get_moves.py:36-69: the r.get_moves list, pruned when it has more than 10 entries -- the rocket-kicker moves go
+ * (:22-34,:56-57), the rest is ranked by  cards_value - 0.1 * (cards left in hand after the move)  with Python's stable
+ * sort (:60), and the list becomes  lowest, highest, 2nd lowest, 2nd highest, ...  for int(length/3 + 1) rounds (:61-63),
+ * `length` counting the dropped moves too.  An index past the kept moves (IndexError in the reference; cannot happen
+ * for hands of one deck) is clamped.  Returns the number of entries (only cap are written). */
+int ddz_ref_mcts_moves(const int8_t hand[15], const int8_t last[15], int8_t* out, int cap) {
+    int8_t all[DDZ_REF_MAX_LEGAL * 15];
+    int length = ddz_ref_get_moves_fast(hand, last, all, DDZ_REF_MAX_LEGAL);
+    if (length < 0 || length > DDZ_REF_MAX_LEGAL) return -1;
+    if (length <= 10) {
+        for (int i = 0; i < length && i < cap; i++) memcpy(out + 15 * i, all + 15 * i, 15);
+        return length;
+    }
+    int handnum = 0;
+    for (int r = 0; r < 15; r++) handnum += hand[r];
+    int kept[DDZ_REF_MAX_LEGAL], order[DDZ_REF_MAX_LEGAL], m = 0;
+    double values[DDZ_REF_MAX_LEGAL];
+    for (int i = 0; i < length; i++) {
+        const int8_t* mv = all + 15 * i;
+        int u = lookup(ddz_ref_pack(mv));
+        if (u < 0) return -2;
+        if (U[u].extra) continue;                              /* sidaihuojian / sandaihuojian */
+        int cards = 0;
+        for (int r = 0; r < 15; r++) cards += mv[r];
+        volatile double left = 0.1 * (handnum - cards);        /* two roundings, as Python does: no fused multiply-add */
+        values[m] = ddz_ref_cards_value(mv) - left;
+        kept[m] = i; order[m] = m; m++;
+    }
+    for (int i = 1; i < m; i++) {                              /* stable insertion sort by value */
+        int o = order[i], j = i;
+        while (j > 0 && values[order[j - 1]] > values[o]) { order[j] = order[j - 1]; j--; }
+        order[j] = o;
+    }
+    int rounds = length / 3 + 1, n = 0;
+    for (int k = 0; k < rounds; k++) {
+        int lo = k < m ? k : m - 1, hi = m - 1 - k >= 0 ? m - 1 - k : 0;
+        if (n < cap) memcpy(out + 15 * n, all + 15 * kept[order[lo]], 15);
+        n++;
+        if (n < cap) memcpy(out + 15 * n, all + 15 * kept[order[hi]], 15);
+        n++;
+    }
+    return n;
+}

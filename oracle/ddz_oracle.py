@@ -94,6 +94,9 @@ def lib():
         L.ddz_ref_rollout.restype = C.c_int64
         L.ddz_ref_get_moves_batch.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, i32p, u64p, C.POINTER(C.c_double)]
         L.ddz_ref_get_moves_batch.restype = C.c_int64
+        L.ddz_ref_cards_value.argtypes = [i8p]
+        L.ddz_ref_cards_value.restype = C.c_double
+        L.ddz_ref_mcts_moves.argtypes = [i8p, i8p, i8p, C.c_int]
         L.ddz_ref_count_lead_closed.argtypes = [i8p]
         L.ddz_ref_max_lead_moves_exhaustive.argtypes = [C.c_int, i8p, C.POINTER(C.c_longlong)]
         _lib = L
@@ -137,6 +140,23 @@ def get_moves(hand, last, fast=False):
     n = f(_ptr(h, C.c_int8), _ptr(l, C.c_int8), _ptr(out, C.c_int8), MAX_LEGAL)
     if n < 0 or n > MAX_LEGAL:
         raise ValueError("get_moves failed: %d" % n)
+    return out[:n].copy()
+
+
+def cards_value(counts):
+    """cards_value[tuple(counts)] of server/mcts/evaluator.py; None for a vector that is not in that table"""
+    a = _i8(counts)
+    v = float(lib().ddz_ref_cards_value(_ptr(a, C.c_int8)))
+    return None if v < -1e29 else v
+
+
+def mcts_moves(hand, last):
+    """mcts.get_moves.get_moves(hand, last) (server/mcts/get_moves.py:36-69) -> int8[M,15] in the reference's order"""
+    h, l = _i8(hand), _i8(last)
+    out = np.zeros((MAX_LEGAL, 15), np.int8)
+    n = lib().ddz_ref_mcts_moves(_ptr(h, C.c_int8), _ptr(l, C.c_int8), _ptr(out, C.c_int8), MAX_LEGAL)
+    if n < 0 or n > MAX_LEGAL:
+        raise ValueError("mcts_moves failed: %d" % n)
     return out[:n].copy()
 
 

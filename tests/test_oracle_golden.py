@@ -268,3 +268,30 @@ def test_prob_plane_forms_follow_their_definitions(golden):
             assert np.array_equal(out, want), (name, i)
             if form == 0:      # the default form is what the unmodified Predictor.face produced over the oracle shim
                 assert np.array_equal(out.reshape(2, 15, 4), g["face"][i][4:6]), i
+
+
+def test_cards_value_matches_evaluator_py(oracle, golden):
+    """server/mcts/evaluator.py:17-57, the whole table: every key of the reference's cards_value, exact."""
+    g = golden.mcts_moves
+    keys, vals = g["value_keys"], g["value_vals"]
+    assert len(keys) == oracle.NACTIONS_CARD_PY
+    got = np.array([oracle.cards_value(k) for k in keys], np.float64)
+    assert np.array_equal(got, vals)
+    counts, _, _, _, extra = oracle.universe()
+    for c in counts[extra == 1]:
+        assert oracle.cards_value(c) is None            # KeyError in the reference (get_moves.py:56 drops them first)
+
+
+def test_mcts_moves_match_get_moves_py(oracle, golden):
+    """server/mcts/get_moves.py:36-69 run unmodified (over oracle/pyshim/r.py) on 769 positions: the pruned list, in order."""
+    g = golden.mcts_moves
+    offs = g["offsets"]
+    pruned = 0
+    for i, (h, l) in enumerate(zip(g["hands"], g["lasts"])):
+        want = g["moves"][offs[i]:offs[i + 1]]
+        got = oracle.mcts_moves(h, l)
+        assert np.array_equal(got, want), i
+        n = int(g["full_counts"][i])
+        assert len(got) == (n if n <= 10 else 2 * (n // 3 + 1))
+        pruned += n > 10
+    assert pruned > 100
