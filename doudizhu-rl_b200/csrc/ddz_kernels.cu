@@ -35,6 +35,7 @@
 #include "../../include/ddz_b200.h"
 #include "ddz_device.cuh"
 #include "ddz_flat.cuh"
+#include "ddz_search.cuh"
 
 namespace ddz {
 
@@ -824,6 +825,14 @@ __global__ void __launch_bounds__(256) k_kth_moves(const uint64_t* __restrict__ 
 // philox(seed, env, stepno0 + t) % N of the canonical list each time -- the same stream the stepping API uses, so a
 // playout equals max_steps calls of ddz_rollout_step without re-deal.  No lists, no features, no inter-env traffic:
 // the state stays in registers, one load and one store per env.
+// PRUNED: the default policy the reference's search bot really plays -- a uniform draw from ITS move list, the pruned one
+// of server/mcts/get_moves.py:36-69 (tree.py:83-91 calls it for every playout move): the draw picks an entry of the pruned
+// list, search::pruned_pick finds which move of the full list that is.  The keys of one decision live in local memory.
+struct KeySink {
+    uint16_t* keys; int n, handnum;
+    DDZ_DEV void operator()(uint64_t mv) { keys[n++] = (uint16_t)search::value_key(mv, handnum); }
+};
+template <bool PRUNED>
 __global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0,
                                                  int32_t rw0, int32_t rw1, int32_t rw2, int32_t* __restrict__ steps_taken,
                                                  int64_t* stats, int B) {
@@ -839,7 +848,14 @@ __global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uin
             const Rule ru = rule_of(last);
             const int n = count_legal(m, ru, last != 0);
             if (n <= 0) break;
-            const int k = (int)(philox(seed, env0 + (uint64_t)b, stepno0 + (uint32_t)t) % (uint32_t)n);
+            const uint32_t u = philox(seed, env0 + (uint64_t)b, stepno0 + (uint32_t)t);
+            int k;
+            if (PRUNED && n > search::kPruneAbove) {
+                uint16_t keys[DDZ_MAX_LEGAL];
+                KeySink ks{keys, 0, card_count(hand)};
+                enumerate_legal(m, ru, last != 0, ks);
+                k = search::pruned_pick(keys, n, (int)(u % (uint32_t)search::pruned_size(n)));
+            } else k = (int)(u % (uint32_t)n);
             const StepOut so = apply_move(e, select_legal(m, ru, last != 0, k), rewards);
             steps++; passes += so.pass;
             if (so.done) { over = 1; winner = so.winner; }
@@ -851,6 +867,65 @@ __global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uin
     stat_add(stats, 1, over && winner == 1); stat_add(stats, 2, over && winner == 2); stat_add(stats, 3, over && winner == 0);
     stat_add(stats, 5, over ? (winner == 1 ? rw1 : -rw1) : 0);
     stat_add(stats, 6, over ? (winner == 1 ? -(rw0 + rw2) : rw0 + rw2) : 0);
+}
+
+// mcts.get_moves.get_moves for n independent (hand, last) pairs (server/mcts/get_moves.py:36-69), one warp per pair: the
+// full list is expanded into shared memory by the whole warp, every kept move gets its position in the stable ascending
+// order of the keys by counting (no sort: position = how many kept moves come before it), and goes to the slots of the
+// pruned list that position owns -- entry 2k for the k-th lowest, entry 2k+1 for the k-th highest.
+constexpr int kSearchWarps = 4;
+struct SlotEmitter {
+    uint64_t* out;
+    DDZ_DEV void operator()(int idx, uint64_t mv) { if ((unsigned)idx < (unsigned)DDZ_MAX_LEGAL) out[idx] = mv; }
+};
+__global__ void __launch_bounds__(kSearchWarps * 32) k_mcts_moves(const uint64_t* __restrict__ hands,
+                                                                  const uint64_t* __restrict__ lasts,
+                                                                  uint64_t* __restrict__ out, int32_t* __restrict__ counts,
+                                                                  int npairs) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ uint64_t s_moves[kSearchWarps][DDZ_MAX_LEGAL];
+    __shared__ uint16_t s_keys[kSearchWarps][DDZ_MAX_LEGAL];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pair = blockIdx.x * kSearchWarps + wib;
+    if (pair >= npairs) return;
+    const uint64_t hand = hands[pair], last = lasts[pair];
+    const Masks hm = masks_of(hand);
+    const Rule ru = rule_of(last);
+    uint64_t* moves = s_moves[wib];
+    uint16_t* keys = s_keys[wib];
+    SlotEmitter em{moves};
+    const int n = enumerate_legal_warp(hm, ru, last != 0, lane, em);
+    __syncwarp();
+    uint64_t* dst = out + (size_t)pair * DDZ_MCTS_MAX_MOVES;
+    int count = n;
+    if (n <= search::kPruneAbove) {
+        for (int i = lane; i < n; i += 32) dst[i] = moves[i];
+    } else {
+        const int handnum = card_count(hand);
+        int kept = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t key = search::value_key(moves[i], handnum);
+            keys[i] = (uint16_t)key;
+            kept += key != search::kDropped;
+        }
+        const int m = __reduce_add_sync(FULL, kept);
+        __syncwarp();
+        const int rounds = n / 3 + 1;
+        count = 2 * rounds;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t key = keys[i];
+            if (key == search::kDropped) continue;
+            int pos = 0;
+            for (int j = 0; j < n; j++) { const uint32_t kj = keys[j]; pos += (kj < key) | ((kj == key) & (j < i)); }
+            const uint64_t mv = moves[i];
+            const int top = m - 1 - pos;
+            if (pos < rounds) dst[2 * pos] = mv;
+            if (top < rounds) dst[2 * top + 1] = mv;
+            if (pos == m - 1) for (int k = m; k < rounds; k++) dst[2 * k] = mv;       // clamped positions (never for one deck)
+            if (pos == 0) for (int k = m; k < rounds; k++) dst[2 * k + 1] = mv;
+        }
+    }
+    if (lane == 0) counts[pair] = count;
 }
 
 // Batched dqn.py:50-71: per env, the index of the best-scoring legal move (first maximum, like torch.argmax), or with
@@ -1472,9 +1547,28 @@ int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32
     static const int32_t defR[3] = {50, 100, 50};
     if (!state || B <= 0 || max_steps < 0) return DDZ_E_ARG;
     const int32_t* R = rewards ? rewards : defR;
-    k_playout<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(state, max_steps, seed, env0, stepno0, R[0], R[1], R[2],
-                                                                   steps_taken, stats, B);
+    k_playout<false><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(state, max_steps, seed, env0, stepno0, R[0], R[1], R[2],
+                                                                          steps_taken, stats, B);
     DDZ_LAUNCH_CHECK("k_playout");
+    return 0;
+}
+
+int ddz_playout_pruned(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
+                       int32_t* steps_taken, int64_t* stats, int B, void* stream) {
+    static const int32_t defR[3] = {50, 100, 50};
+    if (!state || B <= 0 || max_steps < 0) return DDZ_E_ARG;
+    const int32_t* R = rewards ? rewards : defR;
+    k_playout<true><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(state, max_steps, seed, env0, stepno0, R[0], R[1], R[2],
+                                                                         steps_taken, stats, B);
+    DDZ_LAUNCH_CHECK("k_playout<pruned>");
+    return 0;
+}
+
+int ddz_mcts_moves(const uint64_t* hands, const uint64_t* lasts, uint64_t* moves, int32_t* counts, int n, void* stream) {
+    if (!hands || !lasts || !moves || !counts || n <= 0) return DDZ_E_ARG;
+    k_mcts_moves<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, (cudaStream_t)stream>>>(hands, lasts, moves,
+                                                                                                        counts, n);
+    DDZ_LAUNCH_CHECK("k_mcts_moves");
     return 0;
 }
 

@@ -392,15 +392,20 @@ class BatchedEnv:
         self._stepno += K
         return traj
 
-    def playout(self, max_steps=256):
+    def playout(self, max_steps=256, policy="uniform"):
         """Random playout of every env (MCTS default policy, server/mcts/default_policy.py:4-10): up to max_steps random
         legal moves per env or to the end of its game, Philox stream continued from the env's step counter.  One launch,
-        no lists / features written.  Returns int32 [B] decisions played; winners are in `winner`, counters in `stats`."""
+        no lists / features written.  Returns int32 [B] decisions played; winners are in `winner`, counters in `stats`.
+        policy "uniform": every legal move is equally likely (step_random, envi.py:79-85); "search": the draw is from the
+        search bot's own pruned move list (server/mcts/get_moves.py:36-69), as the reference's playouts do."""
+        if policy not in ("uniform", "search"):
+            raise ValueError("policy must be 'uniform' or 'search'")
+        fn = N.lib.ddz_playout if policy == "uniform" else N.lib.ddz_playout_pruned
         steps = torch.zeros(self.B, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            N.check(N.lib.ddz_playout(self._p(self._state), int(max_steps), self.seed, self.env0, self._stepno,
-                                      self._rewards.data_ptr(), steps.data_ptr(), self._p(self.stats), self.B,
-                                      self._stream()), "ddz_playout")
+            N.check(fn(self._p(self._state), int(max_steps), self.seed, self.env0, self._stepno,
+                       self._rewards.data_ptr(), steps.data_ptr(), self._p(self.stats), self.B,
+                       self._stream()), "ddz_playout")
         self._fresh = False
         self._stepno += int(max_steps)
         return steps
@@ -1003,6 +1008,23 @@ def kth_moves(hands, lasts, idx, device=None):
     with torch.cuda.device(dev):
         N.check(N.lib.ddz_kth_moves(h.data_ptr(), l.data_ptr(), k.data_ptr(), out.data_ptr(), cnt.data_ptr(), h.numel(),
                                     torch.cuda.current_stream(dev).cuda_stream), "ddz_kth_moves")
+    return out, cnt
+
+
+def mcts_moves(hands, lasts, device=None):
+    """Batched mcts.get_moves.get_moves (server/mcts/get_moves.py:36-69): the search bot's move list -- r.get_moves, pruned
+    to its lowest- and highest-valued thirds when it has more than 10 entries, in the reference's order.
+    hands/lasts int [n,15] -> (packed int64 [n, 344], counts int32 [n]) on the device."""
+    if not torch.cuda.is_available():
+        raise N.DdzError("mcts_moves needs a CUDA device")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    h = pack_counts(torch.as_tensor(np.asarray(hands)).reshape(-1, 15).to(dev)).contiguous()
+    l = pack_counts(torch.as_tensor(np.asarray(lasts)).reshape(-1, 15).to(dev)).contiguous()
+    out = torch.zeros((h.numel(), N.MCTS_MAX_MOVES), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(h.numel(), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ddz_mcts_moves(h.data_ptr(), l.data_ptr(), out.data_ptr(), cnt.data_ptr(), h.numel(),
+                                     torch.cuda.current_stream(dev).cuda_stream), "ddz_mcts_moves")
     return out, cnt
 
 

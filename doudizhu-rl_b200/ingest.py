@@ -112,21 +112,22 @@ def evaluate_moves(role, hands, hist, last, sims=256, seed=1, env_cls=None, devi
     return moves, mine.float().mean(1).cpu().numpy()
 
 
-def mcts(payload, computation_budget=1000, seed=1, device=None, width=1, return_search=False):
+def mcts(payload, computation_budget=1000, seed=1, device=None, width=1, return_search=False, prune=True):
     """The entry point of the reference's search bot, `mcts(payload)` (server/mcts/interface.py:15-45), on the batched
     env: payload = {'role_id': 0|1|2, 'hand_card': {role: [card values 3..17]} for all three roles (full information),
     'last_taken': {role: [...]}}.  Returns the chosen move as a sorted list of card values ([] = pass).
 
     `computation_budget` iterations of the reference's UCT search (search.UctSearch: UCB selection, one expansion per
     iteration, random playout, back-up, answer = root child with the best win rate); the playouts run on the device,
-    `width` of them per iteration (1 = the reference's sequential search).  evaluate_moves() above is the flat
+    `width` of them per iteration (1 = the reference's sequential search); tree and playouts use the bot's pruned move
+    lists (server/mcts/get_moves.py:36-69) unless prune=False.  evaluate_moves() above is the flat
     alternative: the same budget spread evenly over the root moves in ONE launch."""
     from .search import UctSearch
     role = int(payload["role_id"])
     get = lambda d, q: d[q] if q in d else d[str(q)]
     hands = np.stack([_counts(get(payload["hand_card"], q)) for q in range(3)])
     last = np.stack([_counts(get(payload["last_taken"], q)) for q in range(3)])
-    search = UctSearch(role, hands, last, width=width, seed=seed, device=device)
+    search = UctSearch(role, hands, last, width=width, seed=seed, device=device, prune=prune)
     search.run(computation_budget)
     if not search.root.children:
         return ([], search) if return_search else []

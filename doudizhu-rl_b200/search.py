@@ -12,9 +12,15 @@ The reference algorithm, kept as it is:
   * back-up (backup.py:1-5): visit += 1, reward += reward on the path to the root;
   * answer: the root child with the best reward / visit (get_bestchild_.py:35-42).
 
-What runs where: a node's legal moves come from ddz_legal_moves, the default policy is ddz_playout -- `width` random
-playouts of the expanded node in one launch (Philox stream keyed by the iteration), backed up as `width` visits; width = 1
-is the reference's sequential search.  The tree itself (a few thousand nodes, pointer chasing) stays on the host.
+  * both the tree and the default policy take their moves from the bot's OWN move list, mcts.get_moves.get_moves
+    (get_moves.py:36-69; tree.py:33,86): a list of more than 10 moves loses its rocket-kicker moves, is ranked by
+    cards_value - 0.1 * cards left (evaluator.py:17-57) and keeps its lowest- and highest-valued thirds.  `prune=True`
+    (the default) does the same; `prune=False` searches and plays over the full r.get_moves lists.
+
+What runs where: a node's move list comes from ddz_mcts_moves (ddz_legal_moves without pruning), the default policy is
+ddz_playout_pruned (ddz_playout) -- `width` random playouts of the expanded node in one launch (Philox stream keyed by the
+iteration), backed up as `width` visits; width = 1 is the reference's sequential search.  The tree itself (a few thousand
+nodes, pointer chasing) stays on the host.
 Exact ties, which the reference breaks with np.random.choice, go to the first candidate; the untried move to expand is
 drawn from a seeded numpy generator.  With the same seed the search is reproducible, and the same algorithm written
 over the CPU restatement of the env (tests/uct_reference_algorithm.py) picks the same move.
@@ -47,11 +53,11 @@ def _trick(recent, cur):
 
 
 class UctSearch:
-    def __init__(self, role, hands, last_taken, width=1, c=UCB_C, seed=1, device=None):
+    def __init__(self, role, hands, last_taken, width=1, c=UCB_C, seed=1, device=None, prune=True):
         if not torch.cuda.is_available():
             raise N.DdzError("UctSearch needs a CUDA device")
         self.me = int(role)
-        self.width, self.c, self.seed = int(width), float(c), int(seed)
+        self.width, self.c, self.seed, self.prune = int(width), float(c), int(seed), bool(prune)
         self.rng = np.random.Generator(np.random.PCG64(self.seed))
         self.env = BatchedEnv(self.width, seed=self.seed if self.seed else None, device=device)
         self.env.seed = self.seed
@@ -59,6 +65,8 @@ class UctSearch:
         self.gen = MoveGenerator(1, device=self.dev)
         self._pair = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._pair_d = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self._list_d = torch.zeros(N.MCTS_MAX_MOVES + 1, dtype=torch.int64, device=self.dev)     # pruned list | its length
+        self._list_h = torch.zeros(N.MCTS_MAX_MOVES + 1, dtype=torch.int64).pin_memory()
         self._state_h = torch.zeros(10, dtype=torch.int64).pin_memory()
         self._state_d = torch.zeros(10, dtype=torch.int64, device=self.dev)
         hands = np.asarray(hands, np.int64).reshape(3, 15).copy()
@@ -69,13 +77,25 @@ class UctSearch:
 
     # ------------------------------------------------------------------ device work
     def _legal_moves(self, node):
-        """int64 [n,15]: r.get_moves(hand of the player to move, trick to beat) in canonical order"""
+        """int64 [n,15]: the move list of the player to move against the trick to beat -- the bot's pruned list in the
+        reference's order, or r.get_moves in canonical order"""
         self._pair[0] = int(pack_counts_np(node.hands[node.cur]).astype(np.int64))
         self._pair[1] = int(pack_counts_np(_trick(node.recent, node.cur)).astype(np.int64))
         self._pair_d.copy_(self._pair, non_blocking=True)
-        acts, offs = self.gen.generate(self._pair_d[0:1], self._pair_d[1:2])
-        n = int(offs[1].item())
-        packed = acts[:n].cpu().numpy().view(np.uint64)
+        if self.prune:
+            count = self._list_d[N.MCTS_MAX_MOVES:].view(torch.int32)
+            with torch.cuda.device(self.dev):
+                N.check(N.lib.ddz_mcts_moves(self._pair_d[0:1].data_ptr(), self._pair_d[1:2].data_ptr(),
+                                             self._list_d.data_ptr(), count.data_ptr(), 1,
+                                             torch.cuda.current_stream(self.dev).cuda_stream), "ddz_mcts_moves")
+            self._list_h.copy_(self._list_d, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            n = int(self._list_h[N.MCTS_MAX_MOVES:].view(torch.int32)[0])
+            packed = self._list_h[:n].numpy().view(np.uint64).copy()
+        else:
+            acts, offs = self.gen.generate(self._pair_d[0:1], self._pair_d[1:2])
+            n = int(offs[1].item())
+            packed = acts[:n].cpu().numpy().view(np.uint64)
         return ((packed[:, None] >> (np.arange(15, dtype=np.uint64) * np.uint64(4))) & np.uint64(15)).astype(np.int64)
 
     def _default_policy(self, node, it):
@@ -93,7 +113,7 @@ class UctSearch:
         meta.copy_(self._state_d[9:10].expand(W).to(torch.int32))
         env._fresh = False
         env.env0, env._stepno = it * W, 0            # Philox counters of this iteration's playouts
-        env.playout(max_steps=400)
+        env.playout(max_steps=400, policy="search" if self.prune else "uniform")
         winner = (env._fields()[1] >> 3) & 3
         lord_won = int((winner == 1).sum().item())
         self.playouts += W

@@ -42,7 +42,8 @@
 extern "C" {
 #endif
 
-#define DDZ_ABI_VERSION 2   /* 2: ddz_mpipe_*, ddz_set_tile_order, ddz_prob_form; cut lists are played from their visible part */
+#define DDZ_ABI_VERSION 3   /* 3: ddz_mcts_moves, ddz_playout_pruned.  2: ddz_mpipe_*, ddz_set_tile_order, ddz_prob_form; cut lists are played
+                            * from their visible part */
 #define DDZ_MAX_LEGAL 512  /* upper bound of legal moves of one decision (worst known hand: 497) */
 
 #define DDZ_E_ARG -1     /* bad argument (NULL pointer, B <= 0, unknown variant/mode) */
@@ -165,6 +166,17 @@ int ddz_kth_moves(const uint64_t* hands, const uint64_t* lasts, const int32_t* i
  * without re-deal would do, but with no lists or features written.  steps_taken int32[B] may be NULL. */
 int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
                 int32_t* steps_taken, int64_t* stats, int B, void* stream);
+
+/* The search bot's own move list and default policy (server/mcts/get_moves.py:36-69, which tree.py:33,86 calls for the
+ * tree AND for every playout move): a list of more than 10 moves loses its rocket-kicker moves (:22-34,:56-57), the rest is
+ * ranked by  cards_value[move] - 0.1 * cards left in hand  (server/mcts/evaluator.py:17-57, stable sort) and the list
+ * becomes  lowest, highest, 2nd lowest, 2nd highest, ...  for int(N/3 + 1) rounds.
+ * ddz_mcts_moves: that list for n (hand, last) pairs; moves uint64[n][DDZ_MCTS_MAX_MOVES], counts int32[n].
+ * ddz_playout_pruned: ddz_playout drawing entry  philox(...) % len(pruned list)  of that list at every decision. */
+#define DDZ_MCTS_MAX_MOVES 344   /* 2 * (DDZ_MAX_LEGAL / 3 + 1), rounded up to a multiple of 8 */
+int ddz_mcts_moves(const uint64_t* hands, const uint64_t* lasts, uint64_t* moves, int32_t* counts, int n, void* stream);
+int ddz_playout_pruned(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
+                       int32_t* steps_taken, int64_t* stats, int B, void* stream);
 
 /* Env.batch_arr2onehot over packed moves (envi.py:113,140-146): out float32[n][15][4] */
 int ddz_encode_actions(const uint64_t* actions_u64, int64_t n, float* out, void* stream);

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(D.native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert D.native.lib.ddz_abi_version() == 2
+    assert D.native.lib.ddz_abi_version() == 3
     assert [D.native.lib.ddz_face_channels(v) for v in range(4)] == [4, 7, 9, 6]
     assert D.native.lib.ddz_face_channels(4) == D.native.E_ARG
     assert D.native.lib.ddz_state_bytes(1000) == 1000 * 76 and D.native.lib.ddz_state_bytes(0) == 0

@@ -802,6 +802,68 @@ def test_playout_equals_step_by_step_rollout(D, oracle):
     assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 9]], ref.stats[[0, 1, 2, 3, 4, 5, 6, 9]]) and st[7] == 0
 
 
+def test_mcts_moves_match_get_moves_py(D, oracle, golden):
+    """ddz_mcts_moves == the unmodified server/mcts/get_moves.py on the golden positions (filter, value, stable sort,
+    lowest/highest interleave), and == the oracle's restatement on random and adversarial pairs."""
+    g = golden.mcts_moves
+    offs = g["offsets"]
+    lists, counts = D.mcts_moves(g["hands"], g["lasts"])
+    lists, counts = lists.cpu().numpy().view(np.uint64), counts.cpu().numpy()
+    assert np.array_equal(counts, np.diff(offs))
+    for i in range(len(counts)):
+        assert np.array_equal(oracle.unpack(lists[i, :counts[i]]), g["moves"][offs[i]:offs[i + 1]]), i
+    rng = np.random.default_rng(23)
+    hands = _rand_hands(rng, 600, 1, 21)
+    z = np.zeros(15, np.int8)
+    lasts = []
+    for i in range(600):
+        om = oracle.get_moves(_rand_hands(rng, 1, 2, 21)[0], z, fast=True)
+        lasts.append(om[rng.integers(len(om))] if i % 2 else z)
+    ah, al = D.adversarial_pairs(256, seed=9)
+    hands = np.concatenate([hands, oracle.unpack(ah)])
+    lasts = np.concatenate([np.array(lasts, np.int8), oracle.unpack(al)])
+    lists, counts = D.mcts_moves(hands, lasts)
+    lists, counts = lists.cpu().numpy().view(np.uint64), counts.cpu().numpy()
+    pruned = 0
+    for i in range(len(hands)):
+        want = oracle.mcts_moves(hands[i], lasts[i])
+        assert counts[i] == len(want) and np.array_equal(oracle.unpack(lists[i, :counts[i]]), want), i
+        pruned += len(want) > 10
+    assert pruned > 200
+
+
+def test_search_policy_playout_equals_oracle(D, oracle):
+    """ddz_playout_pruned: every decision is entry  philox % len  of the bot's pruned move list (tree.py:83-91 over
+    get_moves.py:36-69) -- the same games, move for move, as the oracle driven with that policy."""
+    from uct_reference_algorithm import pruned_playout_step
+    B, seed = 384, 99
+    perm, lord = D.random_deals(B, seed=21)
+    env = D.BatchedEnv(B, seed=seed, env0=40)
+    env.prepare(perm, lord)
+    ref = oracle.RefBatch(B, 0)
+    ref.deal(perm, lord)
+    steps = env.playout(max_steps=9, policy="search")    # from the deal: the long lists, all pruned
+    for t in range(9):
+        pruned_playout_step(oracle, ref, seed, 40, t)
+    _compare_state(env, ref, 9)
+    assert (steps.cpu().numpy() == 9).all()
+    uni = D.BatchedEnv(B, seed=seed, env0=40)
+    uni.prepare(perm, lord)
+    uni.playout(max_steps=9)                             # the uniform policy plays different games
+    assert not torch.equal(uni._fields()[0], env._fields()[0])
+    env.playout(max_steps=300, policy="search")
+    for t in range(9, 309):
+        pruned_playout_step(oracle, ref, seed, 40, t)
+        if ref.envs["done"].all():
+            break
+    assert env.is_done.all()
+    assert np.array_equal(env.winner.cpu().numpy(), ref.envs["winner"])
+    _f, _m = ref.export()
+    assert np.array_equal(env._fields()[0].cpu().numpy().view(np.uint64), _f)
+    st = env.stats.cpu().numpy()
+    assert np.array_equal(st[[0, 1, 2, 3, 4, 9]], ref.stats[[0, 1, 2, 3, 4, 9]]) and st[7] == 0
+
+
 def test_flat_monte_carlo_move_evaluation(D, oracle):
     """evaluate_moves (the MCTS bot's job with playouts instead of a tree): a move that empties the hand wins every
     playout; win rates agree with playouts stepped on the oracle within sampling noise."""
@@ -1388,7 +1450,8 @@ def test_prob_form_b_build_matches_form_b_oracle(D):
 def test_uct_search_equals_reference_algorithm_on_oracle(D, oracle):
     """The search bot (server/mcts/interface.py:37-45): UctSearch (tree on the host, legal moves and playouts on the device)
     against the reference algorithm restated over the oracle (tests/uct_reference_algorithm.py), same seed and budget:
-    the same tree statistics at the root and the same chosen move, for the sequential search (width 1) and a wide one."""
+    the same tree statistics at the root and the same chosen move, for the sequential search (width 1) and a wide one,
+    over the full move lists and over the bot's pruned ones (the reference's own configuration)."""
     from uct_reference_algorithm import uct
     z = np.zeros((3, 15), np.int64)
     positions = []
@@ -1402,10 +1465,14 @@ def test_uct_search_equals_reference_algorithm_on_oracle(D, oracle):
     p = rng.permutation(deck)[:21]
     h3 = np.stack([np.bincount(p[0:7], minlength=15), np.bincount(p[7:15], minlength=15), np.bincount(p[15:21], minlength=15)]).astype(np.int64)
     positions.append((0, h3, z))
+    p = rng.permutation(deck)[:45]                                    # mid-game hands: lists long enough to be pruned
+    h4 = np.stack([np.bincount(p[0:14], minlength=15), np.bincount(p[14:31], minlength=15), np.bincount(p[31:45], minlength=15)]).astype(np.int64)
+    positions.append((1, h4, z))
+    assert len(oracle.get_moves(h4[1], z[0], fast=True)) > 10
     for k, (role, hands, last) in enumerate(positions):
-        for width, budget in ((1, 120), (16, 60)):
-            want_move, want_root = uct(oracle, role, hands, last, budget, width=width, seed=7 + k)
-            s = D.UctSearch(role, hands, last, width=width, seed=7 + k).run(budget)
+        for width, budget, prune in ((1, 120, False), (16, 60, False), (1, 100, True), (8, 50, True)):
+            want_move, want_root = uct(oracle, role, hands, last, budget, width=width, seed=7 + k, prune=prune)
+            s = D.UctSearch(role, hands, last, width=width, seed=7 + k, prune=prune).run(budget)
             moves, visits, rate = s.root_table()
             assert len(moves) == len(want_root.children), (k, width)
             for i, ch in enumerate(want_root.children):

@@ -1,7 +1,9 @@
 """The reference's UCT search (server/mcts/interface.py:37-45, tree.py, tree_policy.py, default_policy.py, backup.py,
 get_bestchild.py) restated over the CPU oracle, for tests: the oracle supplies r.get_moves and plays the random playouts
-(Philox index stream, the one ddz_playout uses).  TEST INFRASTRUCTURE: the product's search (doudizhu-rl_b200/search.py)
-must pick the same move with the same seed and budget."""
+(Philox index stream, the one ddz_playout uses).  With prune=True both the tree and the playouts draw from the bot's pruned
+move list (oracle.mcts_moves, pinned against the unmodified server/mcts/get_moves.py), as the reference does.
+TEST INFRASTRUCTURE: the product's search (doudizhu-rl_b200/search.py) must pick the same move with the same seed and
+budget."""
 import math
 
 import numpy as np
@@ -30,7 +32,25 @@ class State:
         return State(hands, recent, (self.player + 1) % 3, winner, move)
 
 
-def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1):
+def pruned_playout_step(oracle, rb, seed, env0, t):
+    """one decision of every unfinished env of `rb`: entry  philox(seed, env0 + b, t) % len  of the bot's pruned move list
+    (tree.py:83-91: get_moves(...) then np.random.choice)"""
+    offs, acts, _, _ = rb.observe(want_f32=False, want_face=False)
+    choice = np.zeros(rb.B, np.int32)
+    for b in range(rb.B):
+        e = rb.envs[b]
+        if e["done"]:
+            continue
+        cur = int(e["cur"])
+        prev, pp = e["recent"][(cur + 2) % 3], e["recent"][(cur + 1) % 3]
+        lst = oracle.mcts_moves(e["hand"][cur], prev if prev.any() else pp)
+        mv = lst[oracle.philox(seed, env0 + b, t) % len(lst)]
+        full = oracle.unpack(acts[offs[b]:offs[b + 1]])
+        choice[b] = int(np.flatnonzero((full == mv).all(axis=1))[0])
+    rb.step(choice, mode=0)
+
+
+def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1, prune=False):
     rng = np.random.Generator(np.random.PCG64(seed))
     me = int(role)
     root = Node(None, State(np.asarray(hands, np.int64).copy(), np.asarray(last_taken, np.int64).copy(), me, -1, None))
@@ -42,7 +62,9 @@ def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1):
         while node.state.winner == -1:
             if node.untried is None:
                 st = node.state
-                node.untried = [m.astype(np.int64) for m in oracle.get_moves(st.hands[st.player], st.last_move(), fast=True)]
+                lst = oracle.mcts_moves(st.hands[st.player], st.last_move()) if prune else \
+                    oracle.get_moves(st.hands[st.player], st.last_move(), fast=True)
+                node.untried = [m.astype(np.int64) for m in lst]
                 node.nmoves = len(node.untried)
             if len(node.children) < node.nmoves:                       # expand one untried move, chosen at random
                 mv = node.untried.pop(int(rng.integers(len(node.untried))))
@@ -66,8 +88,11 @@ def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1):
         rb.envs["winner"] = -1
         t = 0
         while not rb.envs["done"].all():
-            rb.observe(want_f32=False, want_face=False)
-            rb.step(mode=2, seed=seed, env0=it * width, step=t)        # finished envs do nothing
+            if prune:
+                pruned_playout_step(oracle, rb, seed, it * width, t)
+            else:
+                rb.observe(want_f32=False, want_face=False)
+                rb.step(mode=2, seed=seed, env0=it * width, step=t)    # finished envs do nothing
             t += 1
         return float(sum(won(int(w)) for w in rb.envs["winner"]))
 
