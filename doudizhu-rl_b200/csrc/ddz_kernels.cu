@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(256) k_kth_moves(const uint64_t* __restrict__ 
 // list, search::pruned_pick finds which move of the full list that is.  The keys of one decision live in local memory.
 struct KeySink {
     uint16_t* keys; int n, handnum;
-    DDZ_DEV void operator()(uint64_t mv) { keys[n++] = (uint16_t)search::value_key(mv, handnum); }
+    DDZ_DEV void operator()(uint64_t mv) { if (n < DDZ_MAX_LEGAL) keys[n] = (uint16_t)search::value_key(mv, handnum); n++; }
 };
 template <bool PRUNED>
 __global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0,
@@ -854,7 +854,8 @@ __global__ void __launch_bounds__(128) k_playout(void* state, int max_steps, uin
                 uint16_t keys[DDZ_MAX_LEGAL];
                 KeySink ks{keys, 0, card_count(hand)};
                 enumerate_legal(m, ru, last != 0, ks);
-                k = search::pruned_pick(keys, n, (int)(u % (uint32_t)search::pruned_size(n)));
+                const int nk = min(n, DDZ_MAX_LEGAL);            // 512 bounds every list of hands dealt from one deck
+                k = search::pruned_pick(keys, nk, (int)(u % (uint32_t)search::pruned_size(nk)));
             } else k = (int)(u % (uint32_t)n);
             const StepOut so = apply_move(e, select_legal(m, ru, last != 0, k), rewards);
             steps++; passes += so.pass;
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_mcts_moves(const uint64_t
     uint64_t* moves = s_moves[wib];
     uint16_t* keys = s_keys[wib];
     SlotEmitter em{moves};
-    const int n = enumerate_legal_warp(hm, ru, last != 0, lane, em);
+    const int n = min(enumerate_legal_warp(hm, ru, last != 0, lane, em), DDZ_MAX_LEGAL);   // 512 bounds every real list
     __syncwarp();
     uint64_t* dst = out + (size_t)pair * DDZ_MCTS_MAX_MOVES;
     int count = n;

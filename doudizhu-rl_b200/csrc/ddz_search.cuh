@@ -56,7 +56,7 @@ DDZ_DEV uint32_t value_key(uint64_t mv, int handnum) {
     const Trick t = classify(mv);
     const Masks a = masks_of(mv);
     if ((a.g1 & kRocket) == kRocket && (t.cat == 13 || (t.cat == 10 && t.len == 2))) return kDropped;
-    const int left = handnum - card_count(mv);
+    const int left = min(max(handnum - card_count(mv), 0), kLeftMax);     // a hand of one deck keeps 0..20 cards
     return g_value_rank[(value2(t, a) - kC2Min) * (kLeftMax + 1) + left];
 }
 
