@@ -21,9 +21,11 @@ What runs where: a node's move list comes from ddz_mcts_moves (ddz_legal_moves w
 ddz_playout_pruned (ddz_playout) -- `width` random playouts of the expanded node in one launch (Philox stream keyed by the
 iteration), backed up as `width` visits; width = 1 is the reference's sequential search.  The tree itself (a few thousand
 nodes, pointer chasing) stays on the host.
-Exact ties, which the reference breaks with np.random.choice, go to the first candidate; the untried move to expand is
-drawn from a seeded numpy generator.  With the same seed the search is reproducible, and the same algorithm written
-over the CPU restatement of the env (tests/uct_reference_algorithm.py) picks the same move.
+Exact ties are broken at random among the tied candidates, as the reference does with np.random.choice
+(get_bestchild.py:8,17,37 -- with one visit per child most of a young node's children tie), and the untried move to
+expand is drawn at random (tree.py:42); both draws come from ONE seeded numpy generator, so with the same seed the search
+is reproducible, and the same algorithm written over the CPU restatement of the env (tests/uct_reference_algorithm.py)
+picks the same move.
 """
 import math
 
@@ -138,7 +140,12 @@ class UctSearch:
         visit = np.array([ch.visit for ch in node.children], np.float64)
         reward = np.array([ch.reward for ch in node.children], np.float64)
         values = reward / visit + self.c * np.sqrt(2.0 * math.log(node.visit) / visit)
-        return node.children[int(np.argmax(values) if node.cur == self.me else np.argmin(values))]
+        return node.children[self._pick(values, values.max() if node.cur == self.me else values.min())]
+
+    def _pick(self, values, target):
+        """index of the entry equal to `target`; a random one of them when several tie (get_bestchild.py:8-17)"""
+        tied = np.flatnonzero(values == target)
+        return int(tied[0] if len(tied) == 1 else tied[self.rng.integers(len(tied))])
 
     def _tree_policy(self):
         node = self.root
@@ -169,6 +176,7 @@ class UctSearch:
                 np.array([c.reward / c.visit for c in ch]))
 
     def best_move(self):
-        """get_bestchild_: the root child with the best reward / visit (first one on ties); counts int64 [15]"""
+        """get_bestchild_: the root child with the best reward / visit (a random one of them on ties, get_bestchild.py:35-42);
+        counts int64 [15].  Consumes the generator when there is a tie: call it once."""
         moves, _, rate = self.root_table()
-        return moves[int(np.argmax(rate))]
+        return moves[self._pick(rate, rate.max())]

@@ -58,6 +58,10 @@ def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1, prune=F
     def won(winner):
         return 1.0 if (winner == 1) == (me == 1) else 0.0
 
+    def pick(values, target):                                          # np.random.choice among ties (get_bestchild.py)
+        tied = np.flatnonzero(values == target)
+        return int(tied[0] if len(tied) == 1 else tied[rng.integers(len(tied))])
+
     def tree_policy(node):
         while node.state.winner == -1:
             if node.untried is None:
@@ -74,7 +78,7 @@ def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1, prune=F
             visit = np.array([n.visit for n in node.children], np.float64)
             reward = np.array([n.reward for n in node.children], np.float64)
             values = reward / visit + c * np.sqrt(2.0 * math.log(node.visit) / visit)
-            node = node.children[int(np.argmax(values) if node.state.player == me else np.argmin(values))]   # UCB1 / UCB2
+            node = node.children[pick(values, values.max() if node.state.player == me else values.min())]   # UCB1 / UCB2
         return node
 
     def default_policy(node, it):
@@ -104,5 +108,5 @@ def uct(oracle, role, hands, last_taken, budget, width=1, c=0.7, seed=1, prune=F
             node.reward += reward
             node = node.parent
     rate = np.array([n.reward / n.visit for n in root.children])
-    best = root.children[int(np.argmax(rate))]
+    best = root.children[pick(rate, rate.max())]
     return best.state.action, root
