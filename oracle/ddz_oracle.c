@@ -523,18 +523,18 @@ int ddz_ref_batch_deal(ddz_ref_env* envs, int B, const int8_t* perm, const int8_
     return 0;
 }
 
-void ddz_ref_batch_export(const ddz_ref_env* envs, int B, uint64_t* f, uint32_t* meta) {
-    for (int b = 0; b < B; b++) {
-        const ddz_ref_env* e = &envs[b];
-        for (int q = 0; q < 3; q++) {
-            f[(size_t)(0 + q) * B + b] = ddz_ref_pack(e->hand[q]);
-            f[(size_t)(3 + q) * B + b] = ddz_ref_pack(e->hist[q]);
-            f[(size_t)(6 + q) * B + b] = ddz_ref_pack(e->recent[q]);
-        }
-        uint32_t w = e->done ? (uint32_t)e->winner : 0u;
-        meta[b] = (uint32_t)e->cur | ((uint32_t)e->done << 2) | (w << 3) | ((uint32_t)e->err << 5) |
-                  (((uint32_t)e->games & 0xFFFFFFu) << 8);
+static void export_one(const ddz_ref_env* e, int B, int b, uint64_t* f, uint32_t* meta) {
+    for (int q = 0; q < 3; q++) {
+        f[(size_t)(0 + q) * B + b] = ddz_ref_pack(e->hand[q]);
+        f[(size_t)(3 + q) * B + b] = ddz_ref_pack(e->hist[q]);
+        f[(size_t)(6 + q) * B + b] = ddz_ref_pack(e->recent[q]);
     }
+    uint32_t w = e->done ? (uint32_t)e->winner : 0u;
+    meta[b] = (uint32_t)e->cur | ((uint32_t)e->done << 2) | (w << 3) | ((uint32_t)e->err << 5) |
+              (((uint32_t)e->games & 0xFFFFFFu) << 8);
+}
+void ddz_ref_batch_export(const ddz_ref_env* envs, int B, uint64_t* f, uint32_t* meta) {
+    for (int b = 0; b < B; b++) export_one(&envs[b], B, b, f, meta);
 }
 
 /* ------------------------------------------------------------------ */
@@ -545,7 +545,9 @@ typedef struct {
     uint64_t seed; const int8_t* perm; const int8_t* lord;
     int64_t stats[16]; uint64_t checksum; int64_t nsteps; double seconds;
     pthread_barrier_t* bar;
+    uint64_t* out_fields; uint32_t* out_meta;   /* optional: the final state of every env (ddz_ref_rollout_export) */
 } job_t;
+static void export_one(const ddz_ref_env* e, int B, int b, uint64_t* f, uint32_t* meta);
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static void* rollout_worker(void* arg) {
@@ -592,13 +594,32 @@ static void* rollout_worker(void* arg) {
     }
     j->seconds = now_s() - t0;
     j->checksum = cs;
+    if (j->out_fields && j->out_meta)
+        for (int i = 0; i < n; i++) export_one(&envs[i], j->B, j->b0 + i, j->out_fields, j->out_meta);
     free(envs); free(moves); free(af); free(face);
     return 0;
 }
 
+static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+                            const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
+                            uint64_t* checksum, double* seconds, uint64_t* out_fields, uint32_t* out_meta);
 int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
                         const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
                         uint64_t* checksum, double* seconds) {
+    return rollout_impl(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads, stats, checksum,
+                        seconds, 0, 0);
+}
+/* the same rollout from the deal, returning the final state of EVERY env in the device's export layout
+ * (ddz_ref_batch_export): the full-size parity check -- one diverging move anywhere changes some env's state */
+int64_t ddz_ref_rollout_export(int B, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+                               const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
+                               uint64_t* fields9, uint32_t* meta) {
+    if (!fields9 || !meta) return -1;
+    return rollout_impl(B, 0, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads, stats, 0, 0, fields9, meta);
+}
+static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+                            const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
+                            uint64_t* checksum, double* seconds, uint64_t* out_fields, uint32_t* out_meta) {
     ensure();
     if (nthreads < 1) nthreads = 1;
     if (nthreads > B) nthreads = B;
@@ -613,6 +634,7 @@ int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t 
         jobs[i].b0 = (int)((int64_t)B * i / nthreads); jobs[i].b1 = (int)((int64_t)B * (i + 1) / nthreads);
         jobs[i].B = B; jobs[i].steps = steps; jobs[i].variant = variant; jobs[i].pool_games = pool_games;
         jobs[i].seed = seed; jobs[i].perm = perm_pool; jobs[i].lord = lord_pool;
+        jobs[i].out_fields = out_fields; jobs[i].out_meta = out_meta;
         pthread_create(&th[i], 0, rollout_worker, &jobs[i]);
     }
     int64_t total = 0; uint64_t cs = 0; double sec = 0;
@@ -683,6 +705,32 @@ int64_t ddz_ref_get_moves_batch(const uint64_t* hands, const uint64_t* lasts, in
     pthread_barrier_destroy(&bar);
     free(jobs); free(th);
     return total;
+}
+
+/* digests of the r.get_moves lists of n packed pairs, for full-size comparisons: *unordered = sum over all moves of
+ * pack(move) * phi, *ordered = sum of pack(move) * (2k + 1) * phi with k the move's index in ITS list (both mod 2^64);
+ * counts[n] (optional) = list lengths.  Returns the number of moves. */
+int64_t ddz_ref_get_moves_digest(const uint64_t* hands, const uint64_t* lasts, int n, int32_t* counts,
+                                 uint64_t* unordered, uint64_t* ordered) {
+    ensure();
+    int8_t* out = (int8_t*)malloc(DDZ_REF_MAX_LEGAL * 15);
+    uint64_t un = 0, ord = 0; int64_t moves = 0;
+    for (int i = 0; i < n; i++) {
+        int8_t h[15], l[15];
+        ddz_ref_unpack(hands[i], h); ddz_ref_unpack(lasts[i], l);
+        int N = ddz_ref_get_moves_fast(h, l, out, DDZ_REF_MAX_LEGAL);
+        if (N < 0 || N > DDZ_REF_MAX_LEGAL) { free(out); return -1; }
+        for (int k = 0; k < N; k++) {
+            uint64_t p = ddz_ref_pack(out + 15 * k) * 0x9E3779B97F4A7C15ULL;
+            un += p; ord += p * (uint64_t)(2 * k + 1);
+        }
+        if (counts) counts[i] = N;
+        moves += N;
+    }
+    free(out);
+    if (unordered) *unordered = un;
+    if (ordered) *ordered = ord;
+    return moves;
 }
 
 /* ------------------------------------------------------------------ */

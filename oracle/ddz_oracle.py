@@ -92,11 +92,16 @@ def lib():
         L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
                                       C.POINTER(C.c_double)]
         L.ddz_ref_rollout.restype = C.c_int64
+        L.ddz_ref_rollout_export.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
+                                             u32p]
+        L.ddz_ref_rollout_export.restype = C.c_int64
         L.ddz_ref_get_moves_batch.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, i32p, u64p, C.POINTER(C.c_double)]
         L.ddz_ref_get_moves_batch.restype = C.c_int64
         L.ddz_ref_cards_value.argtypes = [i8p]
         L.ddz_ref_cards_value.restype = C.c_double
         L.ddz_ref_mcts_moves.argtypes = [i8p, i8p, i8p, C.c_int]
+        L.ddz_ref_get_moves_digest.argtypes = [u64p, u64p, C.c_int, i32p, u64p, u64p]
+        L.ddz_ref_get_moves_digest.restype = C.c_int64
         L.ddz_ref_count_lead_closed.argtypes = [i8p]
         L.ddz_ref_max_lead_moves_exhaustive.argtypes = [C.c_int, i8p, C.POINTER(C.c_longlong)]
         _lib = L
@@ -265,6 +270,21 @@ def rollout(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_game
     return int(n), float(sec.value), stats, int(cs.value)
 
 
+def rollout_export(B, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads):
+    """the rollout above from the deal, all envs: (env_steps, stats int64[16], fields uint64[9,B], meta uint32[B])"""
+    perm_pool = _i8(perm_pool)
+    lp = None if lord_pool is None else _i8(lord_pool)
+    stats = np.zeros(16, np.int64)
+    f = np.zeros((9, int(B)), np.uint64)
+    meta = np.zeros(int(B), np.uint32)
+    n = lib().ddz_ref_rollout_export(int(B), int(steps), int(variant), int(seed), _ptr(perm_pool, C.c_int8),
+                                     _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64),
+                                     _ptr(f, C.c_uint64), _ptr(meta, C.c_uint32))
+    if n < 0:
+        raise ValueError("rollout_export failed")
+    return int(n), stats, f, meta
+
+
 def get_moves_batch(hands_packed, lasts_packed, reps=1, nthreads=1):
     """CPU baseline of config 5: (moves emitted, seconds, counts int32[n], checksum) for packed uint64 pairs"""
     h = np.ascontiguousarray(hands_packed, dtype=np.uint64)
@@ -276,6 +296,33 @@ def get_moves_batch(hands_packed, lasts_packed, reps=1, nthreads=1):
     if n < 0:
         raise ValueError("get_moves_batch failed")
     return int(n), float(sec.value), counts, int(cs.value)
+
+
+PHI = 0x9E3779B97F4A7C15
+
+
+def get_moves_digest(hands_packed, lasts_packed):
+    """(moves, counts int32[n], unordered digest, ordered digest) of the lists of packed uint64 pairs; see lists_digest"""
+    h = np.ascontiguousarray(hands_packed, dtype=np.uint64)
+    l = np.ascontiguousarray(lasts_packed, dtype=np.uint64)
+    counts = np.zeros(len(h), np.int32)
+    un, od = C.c_uint64(0), C.c_uint64(0)
+    n = lib().ddz_ref_get_moves_digest(_ptr(h, C.c_uint64), _ptr(l, C.c_uint64), len(h), _ptr(counts, C.c_int32),
+                                       C.byref(un), C.byref(od))
+    if n < 0:
+        raise ValueError("get_moves_digest failed")
+    return int(n), counts, int(un.value), int(od.value)
+
+
+def lists_digest(actions_u64, offsets):
+    """the same two digests computed from CSR lists (numpy, wrapping uint64 arithmetic)"""
+    a = np.ascontiguousarray(actions_u64).view(np.uint64)
+    off = np.asarray(offsets, np.int64)
+    a = a[:off[-1]]
+    k = np.arange(len(a), dtype=np.int64) - np.repeat(off[:-1], np.diff(off))
+    with np.errstate(over="ignore"):
+        p = a * np.uint64(PHI)
+        return int(p.sum(dtype=np.uint64)), int((p * (2 * k + 1).astype(np.uint64)).sum(dtype=np.uint64))
 
 
 def count_lead_closed(hand):

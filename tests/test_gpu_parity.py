@@ -392,6 +392,60 @@ def test_full_size_invariants(D, oracle):
     assert st[1] + st[2] + st[3] == st[0] and st[0] > B
 
 
+def test_full_size_final_states_equal_the_oracle(D, oracle):
+    """BASELINE config 4's per-GPU slice, ALL 131 072 envs: 120 fused steps from the deal (two to three games per env,
+    re-deals from the pool included), then the complete state of every env and the counters against the oracle's rollout of the same envs
+    (ddz_ref_rollout_export, all host threads).  One wrong legal list, index or transition anywhere changes a state."""
+    import os
+    B, G, seed, K = 131072, 4, 77, 120
+    perm, lord = D.random_deals(B, seed=8, pool_games=G)
+    pd, ld = torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda()
+    n, ostats, f, meta = oracle.rollout_export(B, K, 2, seed, perm, lord, G, os.cpu_count() or 1)
+    assert n == B * K
+    # one chain of launches over all envs
+    env = D.BatchedEnvCooperation(B, seed=seed, max_actions_per_env=160)
+    env.prepare(pd, ld, pool_games=G)
+    for _ in range(K):
+        env.rollout_step(perm=pd, lord_pile=ld, pool_games=G)
+    ef, emeta = env._fields()
+    assert np.array_equal(ef.cpu().numpy().view(np.uint64), f)
+    assert np.array_equal(emeta.cpu().numpy().view(np.uint32), meta)
+    st = env.stats.cpu().numpy()
+    assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 9]], ostats[[0, 1, 2, 3, 4, 5, 6, 9]]) and st[7] == 0
+    assert st[8] - env.num_actions == ostats[8]                    # every list the steps consumed, move for move in length
+    assert np.median(meta >> 8) >= 2 and (meta >> 8).max() >= 3   # deals consumed: most envs are past their first game
+    # the shipped launch shape: four stream-parallel env groups replayed from CUDA graphs
+    ge = D.GroupedEnv(D.BatchedEnvCooperation, B, groups=4, seed=seed, max_actions_per_env=160)
+    ge.prepare(pd, ld, pool_games=G)
+    ge.capture(steps_per_graph=2)
+    for _ in range(K // 2):
+        ge.replay()
+    ge.join(); torch.cuda.synchronize()
+    gf = torch.cat([e._fields()[0] for e in ge.envs], dim=1).cpu().numpy().view(np.uint64)
+    gm = torch.cat([e._fields()[1] for e in ge.envs]).cpu().numpy().view(np.uint32)
+    assert np.array_equal(gf, f) and np.array_equal(gm, meta)
+    assert np.array_equal(ge.stats.cpu().numpy()[[0, 1, 2, 3, 4, 5, 6, 9]], ostats[[0, 1, 2, 3, 4, 5, 6, 9]])
+
+
+def test_config5_full_size_lists_equal_the_oracle(D, oracle):
+    """BASELINE config 5 at the bench's size: the lists of all 131 072 adversarial pairs (18 M moves), list lengths and
+    an order-sensitive digest of every move against the oracle's generator -- content AND canonical order, not a sample."""
+    n = 131072
+    h, l = D.adversarial_pairs(n, seed=12345)
+    gen = D.MoveGenerator(n)
+    hd = torch.as_tensor(h.view(np.int64)).cuda()
+    ld = torch.as_tensor(l.view(np.int64)).cuda()
+    acts, offs = gen.generate(hd, ld)
+    torch.cuda.synchronize()
+    offs = offs.cpu().numpy()
+    moves, counts, un, od = oracle.get_moves_digest(h, l)
+    assert moves == offs[-1] and moves > 15_000_000
+    assert np.array_equal(np.diff(offs), counts)
+    gun, god = oracle.lists_digest(acts[:moves].cpu().numpy(), offs)
+    assert gun == un and god == od
+    assert int(gen.stats[7].item()) == 0
+
+
 def test_state_prob_getters(D, oracle):
     """get_state_prob (envi.py:94) and get_state_prob_manual (server/core.py:26-33) against the oracle."""
     B = 200
