@@ -26,7 +26,7 @@ EXPORTS = ("ddz_abi_version", "ddz_prob_form", "ddz_set_tile_order", "ddz_face_c
            "ddz_encode_face", "ddz_select_actions", "ddz_kth_moves", "ddz_playout", "ddz_pipe_create", "ddz_pipe_destroy",
            "ddz_pipe_step", "ddz_pipe_wait", "ddz_pipe_refill", "ddz_pipe_flush", "ddz_rollout_steps", "ddz_encode_state_actions", "ddz_legal_count", "ddz_legal_emit", "ddz_rows_alloc", "ddz_rows_free",
            "ddz_mpipe_create", "ddz_mpipe_destroy", "ddz_mpipe_step", "ddz_mpipe_wait", "ddz_mpipe_refill", "ddz_mpipe_flush", "ddz_mpipe_join",
-           "ddz_mcts_moves", "ddz_playout_pruned")
+           "ddz_mcts_moves", "ddz_playout_pruned", "ddz_q_features")
 
 lib = C.CDLL(LIB_PATH)
 _missing = [name for name in EXPORTS if not hasattr(lib, name)]
@@ -71,6 +71,7 @@ lib.ddz_playout.argtypes = [_vp, _i, _u64, _u64, _u32, _vp, _vp, _vp, _i, _vp]
 lib.ddz_playout_pruned.argtypes = lib.ddz_playout.argtypes
 lib.ddz_mcts_moves.argtypes = [_vp, _vp, _vp, _vp, _i, _vp]
 MCTS_MAX_MOVES = 344
+lib.ddz_q_features.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]
 lib.ddz_pipe_create.restype = _vp
 lib.ddz_pipe_destroy.argtypes = [_vp]
 lib.ddz_pipe_destroy.restype = None

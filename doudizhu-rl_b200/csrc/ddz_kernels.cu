@@ -34,6 +34,7 @@
 
 #include "../../include/ddz_b200.h"
 #include "ddz_device.cuh"
+#include <cuda_bf16.h>
 #include "ddz_flat.cuh"
 #include "ddz_search.cuh"
 
@@ -782,6 +783,116 @@ __global__ void __launch_bounds__(128) k_state_actions(const void* state, const 
     }
 }
 
+// The first layer of the reference's Q-networks (net.py:65-139, NetComplicated family) for every legal move, straight from
+// the packed state and the packed move lists -- the [n, C+1, 15, 4] input of net.py:90 is never built.  Every input plane is,
+// per rank, four 0/1 slots that are a function of ONE nibble, and conv_k ((1,k) kernel, stride (1,4)) produces exactly one
+// output per rank from slots 0..k-1, so
+//     conv_k[o][r] = bias_k[o] + sum_c scale_c * T[c][nibble_c(r)][k][o]        (T built on the host: agent.q_tables)
+//     x_rank[o][r] = max_k conv_k[o][r]                                          (MaxPool2d((1,4)) over the concatenation)
+//     x_line[o][j] = bias[o] + sum_{c,r} scale_c * L[c][r][o] * lut[nibble_c(r)][j]      (conv_shunzi, (15,1) kernel)
+// One CTA per env, thread <-> output channel o: the C face planes are summed ONCE per env into registers (15 ranks x 4
+// convolutions + 4 line slots), each legal move then adds its own plane, takes the maximum and leaves through shared memory as
+// one row [W*15 | W*4] of the matrix fc1 multiplies (float32 or bfloat16).  The tables (<= 0.7 MB) live in L1 / L2.
+constexpr int kQThreads = 256;
+template <int V, bool BF16>
+__global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, const int32_t* __restrict__ offsets,
+                                                           const uint64_t* __restrict__ actions,
+                                                           const uint8_t* __restrict__ env_mask,
+                                                           const int32_t* __restrict__ dst_offsets, int env_begin,
+                                                           long long row_base, const float* __restrict__ T,
+                                                           const float* __restrict__ rank_bias,
+                                                           const float* __restrict__ L, const float* __restrict__ line_bias,
+                                                           int W, void* __restrict__ out, int B) {
+    constexpr int C = FaceCfg<V>::C;
+    extern __shared__ __align__(16) float s_row[];          // [W*15 | W*4] of the move being written
+    __shared__ uint64_t s_planes[C];
+    __shared__ float s_scale[C];
+    __shared__ float4 s_lut[16];
+    const int b = env_begin + blockIdx.x;
+    if (b >= B || (env_mask && !env_mask[b])) return;
+    const int src = offsets[b], n = offsets[b + 1] - src;
+    if (n <= 0) return;
+    if (threadIdx.x == 0) {
+        const Env e = load_env(view_of(const_cast<void*>(state), B), b);
+        uint64_t pl[C]; float p[2];
+        face_planes<V>(e, pl, p);
+#pragma unroll
+        for (int c = 0; c < C; c++) { s_planes[c] = pl[c]; s_scale[c] = (c >= C - 2) ? p[c - (C - 2)] : 1.f; }
+    }
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = lut_entry(threadIdx.x);
+    __syncthreads();
+    const long long row0 = (dst_offsets ? (long long)dst_offsets[b] : (long long)src) - row_base;
+    const int rowlen = 19 * W;
+    {
+        const int o = threadIdx.x;                                // W <= kQThreads (the reference's networks: W = 256)
+        const bool live = o < W;
+        float F[15][4], S[4];
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float bk = rank_bias[k * W + o];
+#pragma unroll
+                for (int r = 0; r < 15; r++) F[r][k] = bk;
+            }
+            const float lb = line_bias[o];
+            S[0] = S[1] = S[2] = S[3] = lb;
+#pragma unroll 1
+            for (int c = 0; c < C; c++) {
+                const uint64_t pl = s_planes[c];
+                const float sc = s_scale[c];
+#pragma unroll
+                for (int r = 0; r < 15; r++) {
+                    const int nib = (int)(pl >> (4 * r)) & 15;
+                    if (nib == 0) continue;                       // lut[0] = 0: an empty rank contributes nothing
+                    const float* t = T + ((size_t)(c * 16 + nib) * 4) * W + o;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) F[r][k] = fmaf(sc, __ldg(t + (size_t)k * W), F[r][k]);
+                    const float lw = sc * __ldg(L + (size_t)(c * 15 + r) * W + o);
+                    const float4 q = s_lut[nib];
+                    S[0] = fmaf(lw, q.x, S[0]); S[1] = fmaf(lw, q.y, S[1]); S[2] = fmaf(lw, q.z, S[2]); S[3] = fmaf(lw, q.w, S[3]);
+                }
+            }
+        }
+        const float* TA = T + (size_t)C * 16 * 4 * W;          // the move's own plane is input channel C
+        const float* LA = L + (size_t)C * 15 * W;
+#pragma unroll 1
+        for (int a = 0; a < n; a++) {
+            const uint64_t mv = __ldg(&actions[src + a]);
+            if (live) {
+                float s0 = S[0], s1 = S[1], s2 = S[2], s3 = S[3];
+#pragma unroll
+                for (int r = 0; r < 15; r++) {
+                    const int nib = (int)(mv >> (4 * r)) & 15;
+                    float m;
+                    if (nib) {
+                        const float* t = TA + ((size_t)nib * 4) * W + o;
+                        m = fmaxf(fmaxf(F[r][0] + __ldg(t), F[r][1] + __ldg(t + W)),
+                                  fmaxf(F[r][2] + __ldg(t + 2 * (size_t)W), F[r][3] + __ldg(t + 3 * (size_t)W)));
+                        const float lw = __ldg(LA + (size_t)r * W + o);
+                        const float4 q = s_lut[nib];
+                        s0 = fmaf(lw, q.x, s0); s1 = fmaf(lw, q.y, s1); s2 = fmaf(lw, q.z, s2); s3 = fmaf(lw, q.w, s3);
+                    } else m = fmaxf(fmaxf(F[r][0], F[r][1]), fmaxf(F[r][2], F[r][3]));
+                    s_row[o * 15 + r] = m;
+                }
+                *reinterpret_cast<float4*>(&s_row[15 * W + o * 4]) = make_float4(s0, s1, s2, s3);
+            }
+            {                                                     // the row is complete: all threads write it out
+                __syncthreads();
+                if (BF16) {
+                    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out) + (size_t)(row0 + a) * (rowlen / 2);
+                    for (int i = threadIdx.x; i < rowlen / 2; i += kQThreads)
+                        dst[i] = __floats2bfloat162_rn(s_row[2 * i], s_row[2 * i + 1]);
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(out) + (size_t)(row0 + a) * (rowlen / 4);
+                    const float4* srow = reinterpret_cast<const float4*>(s_row);
+                    for (int i = threadIdx.x; i < rowlen / 4; i += kQThreads) dst[i] = srow[i];
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_encode_actions(const uint64_t* __restrict__ actions, long long n,
                                                         float4* __restrict__ out) {
     long long nvec = n * 15;
@@ -1000,6 +1111,19 @@ static int launch_env(void* state, const StepArgs& a, const OutArgs& o, void* wo
     oo.static_tiles = (g_tile_order.load(std::memory_order_relaxed) == DDZ_TILES_AUTO && grid <= resident) ? 1 : 0;
     k_env<V, MODE><<<grid, kThreads, smem, st>>>(state, a, oo, ws, stats, B);
     DDZ_LAUNCH_CHECK("k_env");
+    return 0;
+}
+template <int V>
+static int launch_q_features(const void* state, const int32_t* offsets, const uint64_t* actions, const uint8_t* env_mask,
+                             const int32_t* dst_offsets, int env_begin, int env_count, long long row_base, const float* T,
+                             const float* rank_bias, const float* L, const float* line_bias, int W, void* out, int out_bf16,
+                             int B, cudaStream_t st) {
+    const size_t smem = (size_t)19 * W * sizeof(float);
+    if (out_bf16) k_q_features<V, true><<<env_count, kQThreads, smem, st>>>(state, offsets, actions, env_mask, dst_offsets, env_begin,
+                                                                           row_base, T, rank_bias, L, line_bias, W, out, B);
+    else k_q_features<V, false><<<env_count, kQThreads, smem, st>>>(state, offsets, actions, env_mask, dst_offsets, env_begin,
+                                                                    row_base, T, rank_bias, L, line_bias, W, out, B);
+    DDZ_LAUNCH_CHECK("k_q_features");
     return 0;
 }
 template <int MODE>
@@ -1533,6 +1657,23 @@ int ddz_encode_state_actions(const void* state, int variant, const int32_t* offs
     }
     DDZ_LAUNCH_CHECK("k_state_actions");
     return 0;
+}
+
+int ddz_q_features(const void* state, int variant, const int32_t* offsets, const uint64_t* actions_u64,
+                   const uint8_t* env_mask, const int32_t* dst_offsets, int env_begin, int env_count, int64_t row_base,
+                   const float* rank_tables, const float* rank_bias, const float* line_weights, const float* line_bias,
+                   int width, void* out, int out_bf16, int B, void* stream) {
+    if (!state || !offsets || !actions_u64 || !rank_tables || !rank_bias || !line_weights || !line_bias || !out || B <= 0 ||
+        env_begin < 0 || env_count <= 0 || env_begin + env_count > B || width <= 0 || width > kQThreads || (width & 3))
+        return DDZ_E_ARG;
+    const cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+        case 0: return launch_q_features<0>(state, offsets, actions_u64, env_mask, dst_offsets, env_begin, env_count, row_base, rank_tables, rank_bias, line_weights, line_bias, width, out, out_bf16, B, st);
+        case 1: return launch_q_features<1>(state, offsets, actions_u64, env_mask, dst_offsets, env_begin, env_count, row_base, rank_tables, rank_bias, line_weights, line_bias, width, out, out_bf16, B, st);
+        case 2: return launch_q_features<2>(state, offsets, actions_u64, env_mask, dst_offsets, env_begin, env_count, row_base, rank_tables, rank_bias, line_weights, line_bias, width, out, out_bf16, B, st);
+        case 3: return launch_q_features<3>(state, offsets, actions_u64, env_mask, dst_offsets, env_begin, env_count, row_base, rank_tables, rank_bias, line_weights, line_bias, width, out, out_bf16, B, st);
+    }
+    return DDZ_E_ARG;
 }
 
 int ddz_kth_moves(const uint64_t* hands, const uint64_t* lasts, const int32_t* idx, uint64_t* moves, int32_t* counts,

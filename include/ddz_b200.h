@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DDZ_ABI_VERSION 3   /* 3: ddz_mcts_moves, ddz_playout_pruned.  2: ddz_mpipe_*, ddz_set_tile_order, ddz_prob_form; cut lists are played
+#define DDZ_ABI_VERSION 3   /* 3: ddz_mcts_moves, ddz_playout_pruned, ddz_q_features.  2: ddz_mpipe_*, ddz_set_tile_order, ddz_prob_form; cut lists are played
                             * from their visible part */
 #define DDZ_MAX_LEGAL 512  /* upper bound of legal moves of one decision (worst known hand: 497) */
 
@@ -166,6 +166,19 @@ int ddz_kth_moves(const uint64_t* hands, const uint64_t* lasts, const int32_t* i
  * without re-deal would do, but with no lists or features written.  steps_taken int32[B] may be NULL. */
 int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32_t stepno0, const int32_t rewards[3],
                 int32_t* steps_taken, int64_t* stats, int B, void* stream);
+
+/* The first layer of the reference's Q-networks for every legal move, from the packed state and lists (net.py:65-139, the
+ * NetComplicated family: four (1,k) convolutions with stride (1,4), max-pool, the (15,1) "shunzi" convolution, net.py:91-97):
+ * out[row] = [W x 15 | W x 4], the matrix net.py:99 feeds fc1 -- WITHOUT building the [n, C+1, 15, 4] input of net.py:87-90.
+ * Every input plane is a function of one nibble per rank, so the convolutions are sums of table rows:
+ * rank_tables float32 [C+1][16][4][W] (T[c][nibble][k][o] = sum_{j<=k} W_k+1[o,c,0,j] * slot_j(nibble)), rank_bias [4][W],
+ * line_weights [C+1][15][W], line_bias [W]; W = width <= 256, a multiple of 4 (the reference: 256).  Rows and masks as in
+ * ddz_encode_state_actions; only the envs [env_begin, env_begin + env_count) are processed and row_base is subtracted from
+ * their row numbers (chunking).  out_bf16 != 0: rows are written as bfloat16.  Form-B builds read the form-B nibbles. */
+int ddz_q_features(const void* state, int variant, const int32_t* offsets, const uint64_t* actions_u64,
+                   const uint8_t* env_mask, const int32_t* dst_offsets, int env_begin, int env_count, int64_t row_base,
+                   const float* rank_tables, const float* rank_bias, const float* line_weights, const float* line_bias,
+                   int width, void* out, int out_bf16, int B, void* stream);
 
 /* The search bot's own move list and default policy (server/mcts/get_moves.py:36-69, which tree.py:33,86 calls for the
  * tree AND for every playout move): a list of more than 10 moves loses its rocket-kicker moves (:22-34,:56-57), the rest is
