@@ -74,6 +74,10 @@ def parse_args():
     ap.add_argument("--stats-every", type=int, default=64, help="env-steps between two statistics all-reduces (multi-GPU)")
     ap.add_argument("--clock-interval-ms", type=int, default=20, help="nvidia-smi polling interval of the clock sampler (0 = off)")
     ap.add_argument("--net-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="config 3: the consumer network")
+    ap.add_argument("--scoring", default="fused", choices=["fused", "module"],
+                    help="config 3: how the landlord's legal moves are scored -- fused: ddz_q_features (the network's first layer "
+                         "from the packed state and lists, no input tensor) + two library GEMMs; module: the torch module on the "
+                         "[n, C+1, 15, 4] input written by ddz_encode_state_actions")
     args = ap.parse_args()
     if args.envs is None:
         args.envs = {2: 4096, 3: 65536}.get(args.config, 131072)
@@ -681,7 +685,9 @@ def run_config3(args):
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = (args.net_precision == "tf32")
     net = QNetLike(CHANNELS, width=256, hidden=256).to(dev).eval()
-    if args.net_precision == "bf16":
+    if args.scoring == "fused":
+        policy = D.BatchedGreedyPolicy(net, fused=True, precision=args.net_precision)
+    elif args.net_precision == "bf16":
         inner = net
 
         class Autocast(torch.nn.Module):
@@ -689,7 +695,8 @@ def run_config3(args):
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     return inner.forward_state_action(x).float()
         net = Autocast()
-    policy = D.BatchedGreedyPolicy(net, chunk_actions=1 << 16)
+    if args.scoring == "module":
+        policy = D.BatchedGreedyPolicy(net, chunk_actions=1 << 16)
     sampler = ClockSampler(local, args.clock_interval_ms)
     sampler.start()
     perm, lord = D.random_deals(B, seed=SEED, pool_games=P)
@@ -708,7 +715,7 @@ def run_config3(args):
         if timed:
             ev[0].record()
         is_lord = env.get_role_ID() == 2
-        q = policy.q_values(env, is_lord)                  # ddz_encode_state_actions -> the torch network
+        q = policy.q_values(env, is_lord)                  # ddz_q_features + GEMMs, or ddz_encode_state_actions -> the module
         greedy = policy.select(env, q)                     # ddz_select_actions (segmented argmax)
         off = env.offsets
         cnt = off[1:] - off[:-1]
@@ -750,11 +757,18 @@ def run_config3(args):
             "config": {"workload": workload_text(args), "baseline_config": 3, "envs_per_gpu": B, "face_channels": CHANNELS,
                        "mean_legal_moves": nbar, "network": "QNetLike(9+1 channels, width 256, hidden 256) = NetCooperation's layer sizes (net.py:125-139), %s, "
                        "torch.manual_seed(0) random init (no checkpoint ships)" % args.net_precision,
+                       "scoring": ("fused: ddz_q_features computes the network's first layer (four rank convolutions, max-pool, line "
+                                   "convolution, net.py:91-97) for every legal move of the landlord from the packed state and move lists "
+                                   "-- the [n, C+1, 15, 4] input is never built --, fc1 / fc2 are two library GEMMs; same weights, same Q "
+                                   "values as the torch module within float32 rounding (tests/test_consumer_contract.py)")
+                       if args.scoring == "fused" else
+                       "module: the torch module on the [n, C+1, 15, 4] input written in place by ddz_encode_state_actions",
                        "network_and_selection_ms_per_step": net_ms, "env_kernel_ms_per_step": env_ms,
                        "actions_scored_per_step": scored[0] / K,
                        "games_finished": int(st[0]), "lord_win_rate": float(st[1]) / max(1, int(st[0])),
-                       "note": "the network is the reference's consumer (SURVEY 8 a16: contract only, not rewritten); the hot path "
-                               "contributes the env kernel, the in-place [n,C+1,15,4] encoder and the segmented argmax"},
+                       "note": "the network is the reference's consumer (SURVEY 8 a16: the contract is its torch module, which "
+                               "--scoring module runs unchanged); the hot path contributes the env kernel, the Q-scoring kernels "
+                               "(ddz_q_features or the in-place [n,C+1,15,4] encoder) and the segmented argmax"},
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": gbs, "peak": peak, "unit": "GB/s",
                          "frac": gbs / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
                          "note": "the env kernel alone (env_kernel_ms_per_step), one launch over %d envs between two network "

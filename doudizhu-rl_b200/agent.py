@@ -84,18 +84,18 @@ def q_tables(rank_convs, line_conv, dtype=torch.float32):
     Every plane of the network's input is a row of four 0/1 slots per rank that is a function of ONE nibble (a count);
     conv_k is a (1,k) kernel with stride (1,4), i.e. exactly one output per rank that sees slots 0..k-1 of that rank
     (net.py:69-72), so  conv_k(x)[o, r] = bias_k[o] + sum_c scale_c * T[c][nibble_c(r)][k][o]  with
-    T[c][v][k][o] = sum_{j<k} W_k[o, c, 0, j] * lut[v][j];  conv_shunzi (15,1) is  bias[o] + sum_{c,r} scale_c *
-    L[c][r][o] * lut[nibble_c(r)][j]  for each slot j.  Returns (T [C+1,16,4,W], rank_bias [4,W], L [C+1,15,W], line_bias [W])."""
+    T[c][v][o][k] = sum_{j<k} W_k[o, c, 0, j] * lut[v][j];  conv_shunzi (15,1) is  bias[o] + sum_{c,r} scale_c *
+    L[c][r][o] * lut[nibble_c(r)][j]  for each slot j.  Returns (T [C+1,16,W,4], rank_bias [W,4], L [C+1,15,W], line_bias [W])."""
     lut = _thermometer_lut().to(torch.float64)
     W = rank_convs[0].weight.shape[0]
     cin = rank_convs[0].weight.shape[1]
-    T = torch.zeros(cin, 16, 4, W, dtype=torch.float64)
-    bias = torch.zeros(4, W, dtype=torch.float64)
+    T = torch.zeros(cin, 16, W, 4, dtype=torch.float64)
+    bias = torch.zeros(W, 4, dtype=torch.float64)
     for k, conv in enumerate(rank_convs):                      # kernel (1, k+1)
         w = conv.weight.detach().to("cpu", torch.float64)      # [W, cin, 1, k+1]
         assert w.shape[2] == 1 and w.shape[3] == k + 1 and tuple(conv.stride) == (1, 4)
-        T[:, :, k, :] = torch.einsum("ocj,vj->cvo", w[:, :, 0, :], lut[:, :k + 1])
-        bias[k] = conv.bias.detach().to("cpu", torch.float64)
+        T[:, :, :, k] = torch.einsum("ocj,vj->cvo", w[:, :, 0, :], lut[:, :k + 1])
+        bias[:, k] = conv.bias.detach().to("cpu", torch.float64)
     lw = line_conv.weight.detach().to("cpu", torch.float64)    # [W, cin, 15, 1]
     assert lw.shape[2] == 15 and lw.shape[3] == 1
     L = lw[:, :, :, 0].permute(1, 2, 0).contiguous()           # [cin, 15, W]
@@ -138,7 +138,7 @@ class FusedQScorer:
         T, rb, L, lb = q_tables(convs, line)
         dev, dt = self.device, (torch.bfloat16 if self.precision == "bf16" else torch.float32)
         self.T, self.rank_bias, self.L, self.line_bias = T.to(dev), rb.to(dev), L.to(dev), lb.to(dev)
-        self.W = int(T.shape[-1])
+        self.W = int(T.shape[2])
         if self.W > 256 or self.W % 4:
             raise ValueError("ddz_q_features handles widths up to 256 that are multiples of 4 (net.py: 256)")
         if fc1.weight.shape[1] != 19 * self.W:

@@ -787,24 +787,29 @@ __global__ void __launch_bounds__(128) k_state_actions(const void* state, const 
 // the packed state and the packed move lists -- the [n, C+1, 15, 4] input of net.py:90 is never built.  Every input plane is,
 // per rank, four 0/1 slots that are a function of ONE nibble, and conv_k ((1,k) kernel, stride (1,4)) produces exactly one
 // output per rank from slots 0..k-1, so
-//     conv_k[o][r] = bias_k[o] + sum_c scale_c * T[c][nibble_c(r)][k][o]        (T built on the host: agent.q_tables)
+//     conv_k[o][r] = bias_k[o] + sum_c scale_c * T[c][nibble_c(r)][o][k]        (T built on the host: agent.q_tables)
 //     x_rank[o][r] = max_k conv_k[o][r]                                          (MaxPool2d((1,4)) over the concatenation)
 //     x_line[o][j] = bias[o] + sum_{c,r} scale_c * L[c][r][o] * lut[nibble_c(r)][j]      (conv_shunzi, (15,1) kernel)
-// One CTA per env, thread <-> output channel o: the C face planes are summed ONCE per env into registers (15 ranks x 4
-// convolutions + 4 line slots), each legal move then adds its own plane, takes the maximum and leaves through shared memory as
-// one row [W*15 | W*4] of the matrix fc1 multiplies (float32 or bfloat16).  The tables (<= 0.7 MB) live in L1 / L2.
+// One CTA per env, thread <-> output channel o.  The C face planes are summed ONCE per env into registers (15 ranks x 4
+// convolutions + 4 line slots; branch-free -- the table row of an empty rank is zero -- so the 15 ranks' loads of a plane are
+// in flight together).  The row of the "empty move" then sits in shared memory, twice; every legal move patches the few ranks
+// it (or the move that used the buffer before it) touches, and the row leaves as coalesced 16-byte stores while the next
+// move is patched into the other buffer: one barrier per move.  Rows are float32 or bfloat16, [W*15 | W*4] as net.py:93-97
+// lays them out.  The tables (<= 0.7 MB) live in L1 / L2.
 constexpr int kQThreads = 256;
-template <int V, bool BF16>
+// WC: the width as a compile-time constant (256, the reference's networks: every table offset becomes an immediate) or 0
+template <int V, bool BF16, int WC>
 __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, const int32_t* __restrict__ offsets,
                                                            const uint64_t* __restrict__ actions,
                                                            const uint8_t* __restrict__ env_mask,
                                                            const int32_t* __restrict__ dst_offsets, int env_begin,
-                                                           long long row_base, const float* __restrict__ T,
-                                                           const float* __restrict__ rank_bias,
+                                                           long long row_base, const float4* __restrict__ T,
+                                                           const float4* __restrict__ rank_bias,
                                                            const float* __restrict__ L, const float* __restrict__ line_bias,
-                                                           int W, void* __restrict__ out, int B) {
+                                                           int Wrt, void* __restrict__ out, int B) {
     constexpr int C = FaceCfg<V>::C;
-    extern __shared__ __align__(16) float s_row[];          // [W*15 | W*4] of the move being written
+    const int W = WC ? WC : Wrt;
+    extern __shared__ __align__(16) float s_rows[];         // two buffers of [W*15 | W*4]
     __shared__ uint64_t s_planes[C];
     __shared__ float s_scale[C];
     __shared__ float4 s_lut[16];
@@ -823,72 +828,87 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
     __syncthreads();
     const long long row0 = (dst_offsets ? (long long)dst_offsets[b] : (long long)src) - row_base;
     const int rowlen = 19 * W;
-    {
-        const int o = threadIdx.x;                                // W <= kQThreads (the reference's networks: W = 256)
-        const bool live = o < W;
-        float F[15][4], S[4];
-        if (live) {
+    const int o = threadIdx.x;                                // W <= kQThreads (the reference's networks: W = 256)
+    const bool live = o < W;
+    float4 F[15];                                             // F[r] = the four convolutions' sums over the face planes
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        const float4 bk = __ldg(&rank_bias[o]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float bk = rank_bias[k * W + o];
-#pragma unroll
-                for (int r = 0; r < 15; r++) F[r][k] = bk;
-            }
-            const float lb = line_bias[o];
-            S[0] = S[1] = S[2] = S[3] = lb;
+        for (int r = 0; r < 15; r++) F[r] = bk;
+        const float lb = __ldg(&line_bias[o]);
+        S = make_float4(lb, lb, lb, lb);
 #pragma unroll 1
-            for (int c = 0; c < C; c++) {
-                const uint64_t pl = s_planes[c];
-                const float sc = s_scale[c];
+        for (int c = 0; c < C; c++) {
+            const uint64_t pl = s_planes[c];
+            const float sc = s_scale[c];
+            // A plane holds at most four different non-empty nibbles (counts 1..4, or 9..12 in the form-B probability
+            // planes): its four table rows and its 15 line weights are loaded up front, all in flight together, and the
+            // ranks then pick among registers -- the nibble is the same for every thread, so the branches are uniform.
+            // (form-B builds mark the nibbles of ranks 0..12 of a probability plane with bit 3 -- rows 9..12 --, its two joker
+            // ranks stay unmarked: they hold 0 or 1 and use row 1)
+            const int hi = kProbForm ? ((int)((pl >> 3) & 1ull) << 3) : 0;
+            const float4* Tc = T + (c * 16 + hi) * W + o;
+            const float* Lc = L + c * 15 * W + o;
+            float4 t1 = __ldg(Tc + 1 * W), t2 = __ldg(Tc + 2 * W), t3 = __ldg(Tc + 3 * W), t4 = __ldg(Tc + 4 * W);
+            t1.x *= sc; t1.y *= sc; t1.z *= sc; t1.w *= sc; t2.x *= sc; t2.y *= sc; t2.z *= sc; t2.w *= sc;
+            t3.x *= sc; t3.y *= sc; t3.z *= sc; t3.w *= sc; t4.x *= sc; t4.y *= sc; t4.z *= sc; t4.w *= sc;
+            float4 tj = t1;
+            if (kProbForm && hi) { tj = __ldg(T + (c * 16 + 1) * W + o); tj.x *= sc; tj.y *= sc; tj.z *= sc; tj.w *= sc; }
+            float lw[15];
 #pragma unroll
-                for (int r = 0; r < 15; r++) {
-                    const int nib = (int)(pl >> (4 * r)) & 15;
-                    if (nib == 0) continue;                       // lut[0] = 0: an empty rank contributes nothing
-                    const float* t = T + ((size_t)(c * 16 + nib) * 4) * W + o;
+            for (int r = 0; r < 15; r++) lw[r] = __ldg(Lc + r * W);
+            const uint32_t plo = (uint32_t)pl, phi = (uint32_t)(pl >> 32);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) F[r][k] = fmaf(sc, __ldg(t + (size_t)k * W), F[r][k]);
-                    const float lw = sc * __ldg(L + (size_t)(c * 15 + r) * W + o);
-                    const float4 q = s_lut[nib];
-                    S[0] = fmaf(lw, q.x, S[0]); S[1] = fmaf(lw, q.y, S[1]); S[2] = fmaf(lw, q.z, S[2]); S[3] = fmaf(lw, q.w, S[3]);
-                }
+            for (int r = 0; r < 15; r++) {
+                const int nib = (int)(((r < 8 ? plo : phi) >> (4 * (r & 7))) & 7u);
+                if (nib == 0) continue;
+                const bool joker = kProbForm && r >= 13;
+                const float4 t = joker ? tj : (nib == 1 ? t1 : (nib == 2 ? t2 : (nib == 3 ? t3 : t4)));
+                F[r].x += t.x; F[r].y += t.y; F[r].z += t.z; F[r].w += t.w;
+                const float w = sc * lw[r];
+                const float4 q = s_lut[(joker ? 0 : hi) + nib];
+                S.x = fmaf(w, q.x, S.x); S.y = fmaf(w, q.y, S.y); S.z = fmaf(w, q.z, S.z); S.w = fmaf(w, q.w, S.w);
             }
         }
-        const float* TA = T + (size_t)C * 16 * 4 * W;          // the move's own plane is input channel C
-        const float* LA = L + (size_t)C * 15 * W;
-#pragma unroll 1
-        for (int a = 0; a < n; a++) {
-            const uint64_t mv = __ldg(&actions[src + a]);
-            if (live) {
-                float s0 = S[0], s1 = S[1], s2 = S[2], s3 = S[3];
+        // the row of a move that plays nothing, in both buffers
 #pragma unroll
-                for (int r = 0; r < 15; r++) {
-                    const int nib = (int)(mv >> (4 * r)) & 15;
-                    float m;
-                    if (nib) {
-                        const float* t = TA + ((size_t)nib * 4) * W + o;
-                        m = fmaxf(fmaxf(F[r][0] + __ldg(t), F[r][1] + __ldg(t + W)),
-                                  fmaxf(F[r][2] + __ldg(t + 2 * (size_t)W), F[r][3] + __ldg(t + 3 * (size_t)W)));
-                        const float lw = __ldg(LA + (size_t)r * W + o);
-                        const float4 q = s_lut[nib];
-                        s0 = fmaf(lw, q.x, s0); s1 = fmaf(lw, q.y, s1); s2 = fmaf(lw, q.z, s2); s3 = fmaf(lw, q.w, s3);
-                    } else m = fmaxf(fmaxf(F[r][0], F[r][1]), fmaxf(F[r][2], F[r][3]));
-                    s_row[o * 15 + r] = m;
-                }
-                *reinterpret_cast<float4*>(&s_row[15 * W + o * 4]) = make_float4(s0, s1, s2, s3);
+        for (int r = 0; r < 15; r++) {
+            const float m = fmaxf(fmaxf(F[r].x, F[r].y), fmaxf(F[r].z, F[r].w));
+            s_rows[o * 15 + r] = m; s_rows[rowlen + o * 15 + r] = m;
+        }
+    }
+    const float4* TA = T + C * 16 * W + o;                    // the move's own plane is input channel C
+    const float* LA = L + C * 15 * W + o;
+    uint64_t older = 0, old = 0;                               // the moves patched into this buffer / the other one before
+#pragma unroll 1
+    for (int a = 0; a < n; a++) {
+        const uint64_t mv = __ldg(&actions[src + a]);
+        float* row = s_rows + (a & 1) * rowlen;
+        if (live) {
+            float4 s = S;
+            const uint64_t touched = mv | older;              // ranks whose entry differs from what the buffer holds
+#pragma unroll
+            for (int r = 0; r < 15; r++) {
+                if (((touched >> (4 * r)) & 15) == 0) continue;            // uniform over the CTA
+                const int nib = (int)(mv >> (4 * r)) & 15;
+                const float4 t = __ldg(TA + nib * W);
+                row[o * 15 + r] = fmaxf(fmaxf(F[r].x + t.x, F[r].y + t.y), fmaxf(F[r].z + t.z, F[r].w + t.w));
+                const float lw = __ldg(LA + r * W);
+                const float4 q = s_lut[nib];
+                s.x = fmaf(lw, q.x, s.x); s.y = fmaf(lw, q.y, s.y); s.z = fmaf(lw, q.z, s.z); s.w = fmaf(lw, q.w, s.w);
             }
-            {                                                     // the row is complete: all threads write it out
-                __syncthreads();
-                if (BF16) {
-                    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out) + (size_t)(row0 + a) * (rowlen / 2);
-                    for (int i = threadIdx.x; i < rowlen / 2; i += kQThreads)
-                        dst[i] = __floats2bfloat162_rn(s_row[2 * i], s_row[2 * i + 1]);
-                } else {
-                    float4* dst = reinterpret_cast<float4*>(out) + (size_t)(row0 + a) * (rowlen / 4);
-                    const float4* srow = reinterpret_cast<const float4*>(s_row);
-                    for (int i = threadIdx.x; i < rowlen / 4; i += kQThreads) dst[i] = srow[i];
-                }
-                __syncthreads();
-            }
+            *reinterpret_cast<float4*>(&row[15 * W + o * 4]) = s;
+        }
+        older = old; old = mv;
+        __syncthreads();                                      // row a is complete; the other buffer has been written out
+        if (BF16) {
+            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out) + (size_t)(row0 + a) * (rowlen / 2);
+            for (int i = threadIdx.x; i < rowlen / 2; i += kQThreads) dst[i] = __floats2bfloat162_rn(row[2 * i], row[2 * i + 1]);
+        } else {
+            float4* dst = reinterpret_cast<float4*>(out) + (size_t)(row0 + a) * (rowlen / 4);
+            const float4* srow = reinterpret_cast<const float4*>(row);
+            for (int i = threadIdx.x; i < rowlen / 4; i += kQThreads) dst[i] = srow[i];
         }
     }
 }
@@ -1118,11 +1138,14 @@ static int launch_q_features(const void* state, const int32_t* offsets, const ui
                              const int32_t* dst_offsets, int env_begin, int env_count, long long row_base, const float* T,
                              const float* rank_bias, const float* L, const float* line_bias, int W, void* out, int out_bf16,
                              int B, cudaStream_t st) {
-    const size_t smem = (size_t)19 * W * sizeof(float);
-    if (out_bf16) k_q_features<V, true><<<env_count, kQThreads, smem, st>>>(state, offsets, actions, env_mask, dst_offsets, env_begin,
-                                                                           row_base, T, rank_bias, L, line_bias, W, out, B);
-    else k_q_features<V, false><<<env_count, kQThreads, smem, st>>>(state, offsets, actions, env_mask, dst_offsets, env_begin,
-                                                                    row_base, T, rank_bias, L, line_bias, W, out, B);
+    const size_t smem = (size_t)2 * 19 * W * sizeof(float);
+    const float4* T4 = reinterpret_cast<const float4*>(T);
+    const float4* rb4 = reinterpret_cast<const float4*>(rank_bias);
+#define DDZ_Q_LAUNCH(BF, WC_) k_q_features<V, BF, WC_><<<env_count, kQThreads, smem, st>>>(                        \
+        state, offsets, actions, env_mask, dst_offsets, env_begin, row_base, T4, rb4, L, line_bias, W, out, B)
+    if (W == 256) { if (out_bf16) DDZ_Q_LAUNCH(true, 256); else DDZ_Q_LAUNCH(false, 256); }
+    else          { if (out_bf16) DDZ_Q_LAUNCH(true, 0); else DDZ_Q_LAUNCH(false, 0); }
+#undef DDZ_Q_LAUNCH
     DDZ_LAUNCH_CHECK("k_q_features");
     return 0;
 }

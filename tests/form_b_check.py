@@ -37,6 +37,16 @@ for cls, variant in (("BatchedEnv", 0), ("BatchedEnvComplicated", 1), ("BatchedE
     x, _ = env.state_actions()
     want = np.concatenate([np.repeat(ref.observe()[3], np.diff(ref.observe()[0]), axis=0), ref.observe()[2][:, None]], 1)
     assert np.array_equal(x.cpu().numpy(), want), cls
+    # the fused Q-scorer reads the form-B nibbles (reversed rows for ranks 3..2 of the probability planes, jokers unchanged)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from qnet_like import QNetLike
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    for width in (32, 256):
+        net = QNetLike(env.C, width, 64, seed=3).eval().cuda()
+        torch.testing.assert_close(D.BatchedGreedyPolicy(net, fused=True).q_values(env), D.BatchedGreedyPolicy(net).q_values(env),
+                                   rtol=1e-4, atol=1e-5)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
     k60 = (np.random.default_rng(1).random((5, 60)) < 0.5).astype(np.int32)
     k60 = np.sort(k60.reshape(5, 15, 4), -1)[:, :, ::-1].reshape(5, 60).copy()   # thermometer rows
     k60.reshape(5, 15, 4)[:, 13:, 1:] = 0

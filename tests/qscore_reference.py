@@ -15,15 +15,15 @@ def features(nibbles, scales, T, rank_bias, L, line_bias):
     [W x 15 rank features (o * 15 + r) | W x 4 line features (o * 4 + j)], the layout of net.py:93-97's x"""
     T, rank_bias, L, line_bias = (np.asarray(a, np.float64) for a in (T, rank_bias, L, line_bias))
     n, cin, _ = nibbles.shape
-    W = T.shape[-1]
-    rank = np.broadcast_to(rank_bias[None, None], (n, 15, 4, W)).copy()          # [n, r, k, o]
+    W = T.shape[2]                                                                # T [C+1, 16, W, 4], rank_bias [W, 4]
+    rank = np.broadcast_to(rank_bias[None, None], (n, 15, W, 4)).copy()          # [n, r, o, k]
     line = np.broadcast_to(line_bias[None, :, None], (n, W, 4)).copy()           # [n, o, j]
     for c in range(cin):
-        t = T[c][nibbles[:, c, :]]                                                # [n, 15, 4, W]
+        t = T[c][nibbles[:, c, :]]                                                # [n, 15, W, 4]
         rank += scales[:, c, None, None, None] * t
         lw = L[c][None] * scales[:, c, None, None]                                # [n, 15, W]
         line += np.einsum("nro,nrj->noj", lw, LUT[nibbles[:, c, :]])
-    pooled = rank.max(axis=2)                                                     # MaxPool2d((1, 4)) over the four convs
+    pooled = rank.max(axis=3)                                                     # MaxPool2d((1, 4)) over the four convs
     return np.concatenate([pooled.transpose(0, 2, 1).reshape(n, -1), line.reshape(n, -1)], axis=1)
 
 
