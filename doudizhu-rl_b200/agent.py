@@ -86,20 +86,21 @@ def q_tables(rank_convs, line_conv, dtype=torch.float32):
     (net.py:69-72), so  conv_k(x)[o, r] = bias_k[o] + sum_c scale_c * T[c][nibble_c(r)][k][o]  with
     T[c][v][o][k] = sum_{j<k} W_k[o, c, 0, j] * lut[v][j];  conv_shunzi (15,1) is  bias[o] + sum_{c,r} scale_c *
     L[c][r][o] * lut[nibble_c(r)][j]  for each slot j.  Returns (T [C+1,16,W,4], rank_bias [W,4], L [C+1,15,W], line_bias [W])."""
-    lut = _thermometer_lut().to(torch.float64)
+    dev = rank_convs[0].weight.device                          # built where the weights live (a refresh after every update)
+    lut = _thermometer_lut().to(dev, torch.float64)
     W = rank_convs[0].weight.shape[0]
     cin = rank_convs[0].weight.shape[1]
-    T = torch.zeros(cin, 16, W, 4, dtype=torch.float64)
-    bias = torch.zeros(W, 4, dtype=torch.float64)
+    T = torch.zeros(cin, 16, W, 4, dtype=torch.float64, device=dev)
+    bias = torch.zeros(W, 4, dtype=torch.float64, device=dev)
     for k, conv in enumerate(rank_convs):                      # kernel (1, k+1)
-        w = conv.weight.detach().to("cpu", torch.float64)      # [W, cin, 1, k+1]
+        w = conv.weight.detach().to(torch.float64)             # [W, cin, 1, k+1]
         assert w.shape[2] == 1 and w.shape[3] == k + 1 and tuple(conv.stride) == (1, 4)
         T[:, :, :, k] = torch.einsum("ocj,vj->cvo", w[:, :, 0, :], lut[:, :k + 1])
-        bias[:, k] = conv.bias.detach().to("cpu", torch.float64)
-    lw = line_conv.weight.detach().to("cpu", torch.float64)    # [W, cin, 15, 1]
+        bias[:, k] = conv.bias.detach().to(torch.float64)
+    lw = line_conv.weight.detach().to(torch.float64)           # [W, cin, 15, 1]
     assert lw.shape[2] == 15 and lw.shape[3] == 1
     L = lw[:, :, :, 0].permute(1, 2, 0).contiguous()           # [cin, 15, W]
-    lb = line_conv.bias.detach().to("cpu", torch.float64)
+    lb = line_conv.bias.detach().to(torch.float64)
     return T.to(dtype).contiguous(), bias.to(dtype).contiguous(), L.to(dtype).contiguous(), lb.to(dtype).contiguous()
 
 

@@ -41,7 +41,9 @@ class BatchedDQN:
     and verbs (`perceive`, `e_greedy_action`, `greedy_action`, `update_epsilon`, `update_target`)."""
 
     def __init__(self, net_cls, face_channels, device, replay_size=REPLAY_SIZE, batch_size=BATCH_SIZE, gamma=GAMMA,
-                 lr=1e-4, decay=DECAY, update_target_every=UPDATE_TARGET_EVERY, seed=0):
+                 lr=1e-4, decay=DECAY, update_target_every=UPDATE_TARGET_EVERY, seed=0, fused=False, precision="fp32"):
+        """fused=True: the moves are scored by agent.FusedQScorer (ddz_q_features + two GEMMs, for the NetComplicated family of
+        net.py) instead of the module's forward; its tables are rebuilt from the weights after every update."""
         self.device = torch.device(device)
         self.epsilon = EPSILON_HIGH
         self.batch_size, self.gamma, self.decay, self.update_target_every = int(batch_size), float(gamma), decay, update_target_every
@@ -50,7 +52,7 @@ class BatchedDQN:
         self.target_net.load_state_dict(self.policy_net.state_dict())
         self.optimizer = torch.optim.Adam(self.policy_net.parameters(), lr)
         self.replay_buffer = ReplayBuffer(replay_size, face_channels, self.device)
-        self._policy = BatchedGreedyPolicy(self.policy_net, epsilon=0.0, seed=seed)
+        self._policy = BatchedGreedyPolicy(self.policy_net, epsilon=0.0, seed=seed, fused=fused, precision=precision)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed) + 1)
 
@@ -77,6 +79,8 @@ class BatchedDQN:
         for _ in range(updates):
             loss = td_step(self.policy_net, self.target_net, self.optimizer,
                            self.replay_buffer.sample(self.batch_size, self._gen), self.gamma)
+        if self._policy.scorer is not None:
+            self._policy.scorer.refresh()                      # the weights moved: rebuild the scoring tables
         return loss
 
     def update_epsilon(self, episode):

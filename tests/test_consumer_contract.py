@@ -134,3 +134,26 @@ def test_fused_q_scorer_reduced_precisions(D):
         q = pol.q_values(env)
         assert float((q - q32).abs().max()) < 1e-2, precision
         assert (pol.select(env, q) == exact.select(env, q32)).float().mean() > 0.97, precision
+
+
+@pytest.mark.gpu
+def test_fused_scoring_follows_the_weights_during_training(D):
+    """BatchedDQN(fused=True): after TD updates the scorer's tables are rebuilt, so its Q values stay those of the module"""
+    import functools
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        net_cls = functools.partial(QNetLike, 9, 256, 64)
+        game = D.BatchedGame(D.BatchedEnvCooperation, {"lord": net_cls},
+                             {"lord": functools.partial(D.BatchedDQN, fused=True, batch_size=64)}, num_envs=512, seed=3)
+        before = [p.detach().clone() for p in game.lord.policy_net.parameters()]
+        game.train(episodes=2)
+        assert any(not torch.equal(a, b) for a, b in zip(before, game.lord.policy_net.parameters()))    # it did learn
+        env = game.env
+        env.observe()
+        got = game.lord.q_values(env)
+        want = D.BatchedGreedyPolicy(game.lord.policy_net.eval()).q_values(env)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        assert game.lord._policy.scorer is not None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
