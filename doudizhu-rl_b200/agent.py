@@ -118,7 +118,7 @@ class FusedQScorer:
     """net(face, actions) of the NetComplicated family (net.py:65-139) for every legal move of a batched env, without the
     network's input tensor: ddz_q_features computes the first layer (four rank convolutions + max-pool + the line
     convolution, net.py:91-97) from the packed state and move lists through the tables of q_tables(), as rows of the matrix
-    fc1 multiplies; fc1 -> ReLU -> fc2 (net.py:99-101, dropout is the identity in eval mode) are two library GEMMs.
+    fc1 multiplies (rank-major; fc1's columns are permuted to match once per refresh); fc1 -> ReLU -> fc2 (net.py:99-101, dropout is the identity in eval mode) are two library GEMMs.
     precision: "fp32" (default: float32 rows, TF32 off), "tf32", "bf16" (rows written as bfloat16, fc1 in bfloat16)."""
 
     def __init__(self, net, face_channels, precision="fp32", device=None, chunk_rows=1 << 18):
@@ -144,7 +144,11 @@ class FusedQScorer:
             raise ValueError("ddz_q_features handles widths up to 256 that are multiples of 4 (net.py: 256)")
         if fc1.weight.shape[1] != 19 * self.W:
             raise ValueError("fc1 must take 19 * width inputs (net.py:77,138)")
-        self.w1t = fc1.weight.detach().t().contiguous().to(dev, dt)
+        # ddz_q_features lays a row out rank-major, [15][W] | [W][4]; net.py:93 flattens [W][15] | [W][4]: permute fc1's columns
+        w1 = fc1.weight.detach()
+        H, W = w1.shape[0], self.W
+        w1 = torch.cat((w1[:, :15 * W].reshape(H, W, 15).permute(0, 2, 1).reshape(H, 15 * W), w1[:, 15 * W:]), dim=1)
+        self.w1t = w1.t().contiguous().to(dev, dt)
         self.b1 = fc1.bias.detach().to(dev, dt)
         self.w2 = fc2.weight.detach().reshape(-1).to(dev, torch.float32)
         self.b2 = fc2.bias.detach().to(dev, torch.float32)

@@ -791,11 +791,13 @@ __global__ void __launch_bounds__(128) k_state_actions(const void* state, const 
 //     x_rank[o][r] = max_k conv_k[o][r]                                          (MaxPool2d((1,4)) over the concatenation)
 //     x_line[o][j] = bias[o] + sum_{c,r} scale_c * L[c][r][o] * lut[nibble_c(r)][j]      (conv_shunzi, (15,1) kernel)
 // One CTA per env, thread <-> output channel o.  The C face planes are summed ONCE per env into registers (15 ranks x 4
-// convolutions + 4 line slots; branch-free -- the table row of an empty rank is zero -- so the 15 ranks' loads of a plane are
-// in flight together).  The row of the "empty move" then sits in shared memory, twice; every legal move patches the few ranks
-// it (or the move that used the buffer before it) touches, and the row leaves as coalesced 16-byte stores while the next
-// move is patched into the other buffer: one barrier per move.  Rows are float32 or bfloat16, [W*15 | W*4] as net.py:93-97
-// lays them out.  The tables (<= 0.7 MB) live in L1 / L2.
+// convolutions + 4 line slots): a plane holds at most four different non-empty nibbles, so its four table rows (scaled) go
+// to the thread's own column of shared memory and its 15 line weights to registers, all loads in flight together, and the
+// ranks then pick by the nibble -- which is the same for every thread, so every branch is uniform.  Each legal move then adds
+// its own plane, takes the maximum and writes its row straight from registers: the row is laid out RANK-MAJOR,
+// [15][W] | [W][4], so a warp's 32 channels of one rank are one 128-byte line (float32; 64 bytes in bfloat16) -- no staging, no
+// barrier between moves.  (net.py:93-97 lays the same numbers out channel-major, o * 15 + r; the caller permutes fc1's
+// columns once, agent.FusedQScorer.refresh.)  The tables (<= 0.7 MB) live in L1 / L2.
 constexpr int kQThreads = 256;
 // WC: the width as a compile-time constant (256, the reference's networks: every table offset becomes an immediate) or 0
 template <int V, bool BF16, int WC>
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
                                                            int Wrt, void* __restrict__ out, int B) {
     constexpr int C = FaceCfg<V>::C;
     const int W = WC ? WC : Wrt;
-    extern __shared__ __align__(16) float s_rows[];         // two buffers of [W*15 | W*4]
+    extern __shared__ __align__(16) float4 s_t[];            // [5][kQThreads] a plane's scaled table rows, then s_m0
     __shared__ uint64_t s_planes[C];
     __shared__ float s_scale[C];
     __shared__ float4 s_lut[16];
@@ -828,88 +830,77 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
     __syncthreads();
     const long long row0 = (dst_offsets ? (long long)dst_offsets[b] : (long long)src) - row_base;
     const int rowlen = 19 * W;
+    float* const s_m0 = reinterpret_cast<float*>(s_t + 5 * kQThreads);      // [15][kQThreads]: the empty move's rank features
     const int o = threadIdx.x;                                // W <= kQThreads (the reference's networks: W = 256)
-    const bool live = o < W;
+    if (o >= W) return;                                       // no barrier below: idle threads may leave
     float4 F[15];                                             // F[r] = the four convolutions' sums over the face planes
-    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        const float4 bk = __ldg(&rank_bias[o]);
+    const float4 bk = __ldg(&rank_bias[o]);
 #pragma unroll
-        for (int r = 0; r < 15; r++) F[r] = bk;
-        const float lb = __ldg(&line_bias[o]);
-        S = make_float4(lb, lb, lb, lb);
+    for (int r = 0; r < 15; r++) F[r] = bk;
+    const float lb = __ldg(&line_bias[o]);
+    float4 S = make_float4(lb, lb, lb, lb);
 #pragma unroll 1
-        for (int c = 0; c < C; c++) {
-            const uint64_t pl = s_planes[c];
-            const float sc = s_scale[c];
-            // A plane holds at most four different non-empty nibbles (counts 1..4, or 9..12 in the form-B probability
-            // planes): its four table rows and its 15 line weights are loaded up front, all in flight together, and the
-            // ranks then pick among registers -- the nibble is the same for every thread, so the branches are uniform.
-            // (form-B builds mark the nibbles of ranks 0..12 of a probability plane with bit 3 -- rows 9..12 --, its two joker
-            // ranks stay unmarked: they hold 0 or 1 and use row 1)
-            const int hi = kProbForm ? ((int)((pl >> 3) & 1ull) << 3) : 0;
-            const float4* Tc = T + (c * 16 + hi) * W + o;
-            const float* Lc = L + c * 15 * W + o;
-            float4 t1 = __ldg(Tc + 1 * W), t2 = __ldg(Tc + 2 * W), t3 = __ldg(Tc + 3 * W), t4 = __ldg(Tc + 4 * W);
-            t1.x *= sc; t1.y *= sc; t1.z *= sc; t1.w *= sc; t2.x *= sc; t2.y *= sc; t2.z *= sc; t2.w *= sc;
-            t3.x *= sc; t3.y *= sc; t3.z *= sc; t3.w *= sc; t4.x *= sc; t4.y *= sc; t4.z *= sc; t4.w *= sc;
-            float4 tj = t1;
-            if (kProbForm && hi) { tj = __ldg(T + (c * 16 + 1) * W + o); tj.x *= sc; tj.y *= sc; tj.z *= sc; tj.w *= sc; }
-            float lw[15];
+    for (int c = 0; c < C; c++) {
+        const uint64_t pl = s_planes[c];
+        const float sc = s_scale[c];
+        // (form-B builds mark the nibbles of ranks 0..12 of a probability plane with bit 3 -- rows 9..12 --, its two joker
+        // ranks stay unmarked: they hold 0 or 1 and use row 1)
+        const int hi = kProbForm ? ((int)((pl >> 3) & 1ull) << 3) : 0;
+        const float4* Tc = T + (c * 16 + hi) * W + o;
+        const float* Lc = L + c * 15 * W + o;
+        const float4 t1 = __ldg(Tc + 1 * W), t2 = __ldg(Tc + 2 * W), t3 = __ldg(Tc + 3 * W), t4 = __ldg(Tc + 4 * W);
+        float4 tj = t1;
+        if (kProbForm && hi) tj = __ldg(T + (c * 16 + 1) * W + o);
+        float lw[15];
 #pragma unroll
-            for (int r = 0; r < 15; r++) lw[r] = __ldg(Lc + r * W);
-            const uint32_t plo = (uint32_t)pl, phi = (uint32_t)(pl >> 32);
-#pragma unroll
-            for (int r = 0; r < 15; r++) {
-                const int nib = (int)(((r < 8 ? plo : phi) >> (4 * (r & 7))) & 7u);
-                if (nib == 0) continue;
-                const bool joker = kProbForm && r >= 13;
-                const float4 t = joker ? tj : (nib == 1 ? t1 : (nib == 2 ? t2 : (nib == 3 ? t3 : t4)));
-                F[r].x += t.x; F[r].y += t.y; F[r].z += t.z; F[r].w += t.w;
-                const float w = sc * lw[r];
-                const float4 q = s_lut[(joker ? 0 : hi) + nib];
-                S.x = fmaf(w, q.x, S.x); S.y = fmaf(w, q.y, S.y); S.z = fmaf(w, q.z, S.z); S.w = fmaf(w, q.w, S.w);
-            }
-        }
-        // the row of a move that plays nothing, in both buffers
+        for (int r = 0; r < 15; r++) lw[r] = sc * __ldg(Lc + r * W);
+        // the thread's own column of s_t: written and read by this thread only, indexed by the (uniform) nibble
+        s_t[0 * kQThreads + o] = make_float4(sc * tj.x, sc * tj.y, sc * tj.z, sc * tj.w);
+        s_t[1 * kQThreads + o] = make_float4(sc * t1.x, sc * t1.y, sc * t1.z, sc * t1.w);
+        s_t[2 * kQThreads + o] = make_float4(sc * t2.x, sc * t2.y, sc * t2.z, sc * t2.w);
+        s_t[3 * kQThreads + o] = make_float4(sc * t3.x, sc * t3.y, sc * t3.z, sc * t3.w);
+        s_t[4 * kQThreads + o] = make_float4(sc * t4.x, sc * t4.y, sc * t4.z, sc * t4.w);
+        const uint32_t plo = (uint32_t)pl, phi = (uint32_t)(pl >> 32);
 #pragma unroll
         for (int r = 0; r < 15; r++) {
-            const float m = fmaxf(fmaxf(F[r].x, F[r].y), fmaxf(F[r].z, F[r].w));
-            s_rows[o * 15 + r] = m; s_rows[rowlen + o * 15 + r] = m;
+            const int nib = (int)(((r < 8 ? plo : phi) >> (4 * (r & 7))) & 7u);
+            if (nib == 0) continue;
+            const bool joker = kProbForm && r >= 13;       // row 0 of s_t: the unmarked row 1 (form-B joker ranks)
+            const float4 t = s_t[(joker ? 0 : nib) * kQThreads + o];
+            F[r].x += t.x; F[r].y += t.y; F[r].z += t.z; F[r].w += t.w;
+            const float4 q = s_lut[(joker ? 0 : hi) + nib];
+            S.x = fmaf(lw[r], q.x, S.x); S.y = fmaf(lw[r], q.y, S.y); S.z = fmaf(lw[r], q.z, S.z); S.w = fmaf(lw[r], q.w, S.w);
         }
     }
+#pragma unroll
+    for (int r = 0; r < 15; r++) s_m0[r * kQThreads + o] = fmaxf(fmaxf(F[r].x, F[r].y), fmaxf(F[r].z, F[r].w));
     const float4* TA = T + C * 16 * W + o;                    // the move's own plane is input channel C
     const float* LA = L + C * 15 * W + o;
-    uint64_t older = 0, old = 0;                               // the moves patched into this buffer / the other one before
 #pragma unroll 1
     for (int a = 0; a < n; a++) {
         const uint64_t mv = __ldg(&actions[src + a]);
-        float* row = s_rows + (a & 1) * rowlen;
-        if (live) {
-            float4 s = S;
-            const uint64_t touched = mv | older;              // ranks whose entry differs from what the buffer holds
+        const uint32_t mlo = (uint32_t)mv, mhi = (uint32_t)(mv >> 32);
+        float4 s = S;
+        float* const row32 = reinterpret_cast<float*>(out) + (size_t)(row0 + a) * rowlen + o;
+        __nv_bfloat16* const row16 = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)(row0 + a) * rowlen + o;
 #pragma unroll
-            for (int r = 0; r < 15; r++) {
-                if (((touched >> (4 * r)) & 15) == 0) continue;            // uniform over the CTA
-                const int nib = (int)(mv >> (4 * r)) & 15;
+        for (int r = 0; r < 15; r++) {
+            const int nib = (int)(((r < 8 ? mlo : mhi) >> (4 * (r & 7))) & 15u);      // uniform over the CTA
+            float m;
+            if (nib) {
                 const float4 t = __ldg(TA + nib * W);
-                row[o * 15 + r] = fmaxf(fmaxf(F[r].x + t.x, F[r].y + t.y), fmaxf(F[r].z + t.z, F[r].w + t.w));
+                m = fmaxf(fmaxf(F[r].x + t.x, F[r].y + t.y), fmaxf(F[r].z + t.z, F[r].w + t.w));
                 const float lw = __ldg(LA + r * W);
                 const float4 q = s_lut[nib];
                 s.x = fmaf(lw, q.x, s.x); s.y = fmaf(lw, q.y, s.y); s.z = fmaf(lw, q.z, s.z); s.w = fmaf(lw, q.w, s.w);
-            }
-            *reinterpret_cast<float4*>(&row[15 * W + o * 4]) = s;
+            } else m = s_m0[r * kQThreads + o];
+            if (BF16) row16[r * W] = __float2bfloat16_rn(m); else row32[r * W] = m;
         }
-        older = old; old = mv;
-        __syncthreads();                                      // row a is complete; the other buffer has been written out
         if (BF16) {
-            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out) + (size_t)(row0 + a) * (rowlen / 2);
-            for (int i = threadIdx.x; i < rowlen / 2; i += kQThreads) dst[i] = __floats2bfloat162_rn(row[2 * i], row[2 * i + 1]);
-        } else {
-            float4* dst = reinterpret_cast<float4*>(out) + (size_t)(row0 + a) * (rowlen / 4);
-            const float4* srow = reinterpret_cast<const float4*>(row);
-            for (int i = threadIdx.x; i < rowlen / 4; i += kQThreads) dst[i] = srow[i];
-        }
+            __nv_bfloat162 lo2 = __floats2bfloat162_rn(s.x, s.y), hi2 = __floats2bfloat162_rn(s.z, s.w);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo2); pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+            *reinterpret_cast<uint2*>(row16 - o + 15 * W + 4 * o) = pk;
+        } else *reinterpret_cast<float4*>(row32 - o + 15 * W + 4 * o) = s;
     }
 }
 
@@ -1138,7 +1129,7 @@ static int launch_q_features(const void* state, const int32_t* offsets, const ui
                              const int32_t* dst_offsets, int env_begin, int env_count, long long row_base, const float* T,
                              const float* rank_bias, const float* L, const float* line_bias, int W, void* out, int out_bf16,
                              int B, cudaStream_t st) {
-    const size_t smem = (size_t)2 * 19 * W * sizeof(float);
+    const size_t smem = (size_t)5 * kQThreads * sizeof(float4) + (size_t)15 * kQThreads * sizeof(float);   // 35 KB
     const float4* T4 = reinterpret_cast<const float4*>(T);
     const float4* rb4 = reinterpret_cast<const float4*>(rank_bias);
 #define DDZ_Q_LAUNCH(BF, WC_) k_q_features<V, BF, WC_><<<env_count, kQThreads, smem, st>>>(                        \

@@ -169,7 +169,9 @@ int ddz_playout(void* state, int max_steps, uint64_t seed, uint64_t env0, uint32
 
 /* The first layer of the reference's Q-networks for every legal move, from the packed state and lists (net.py:65-139, the
  * NetComplicated family: four (1,k) convolutions with stride (1,4), max-pool, the (15,1) "shunzi" convolution, net.py:91-97):
- * out[row] = [W x 15 | W x 4], the matrix net.py:99 feeds fc1 -- WITHOUT building the [n, C+1, 15, 4] input of net.py:87-90.
+ * out[row] = [15 x W | W x 4]: the numbers net.py:99 feeds fc1, the rank features RANK-MAJOR (index r * W + o where net.py:93
+ * has o * 15 + r: permute fc1's columns once), the line features as net.py has them (o * 4 + j) -- WITHOUT building the
+ * [n, C+1, 15, 4] input of net.py:87-90.
  * Every input plane is a function of one nibble per rank, so the convolutions are sums of table rows:
  * rank_tables float32 [C+1][16][W][4] (T[c][nibble][o][k] = sum_{j<=k} W_k+1[o,c,0,j] * slot_j(nibble); the row of nibble 0
  * must be zero), rank_bias [W][4], line_weights [C+1][15][W], line_bias [W], all 16-byte aligned; W = width <= 256, a
