@@ -911,6 +911,7 @@ int ddz_ref_mcts_moves(const int8_t hand[15], const int8_t last[15], int8_t* out
         while (j > 0 && values[order[j - 1]] > values[o]) { order[j] = order[j - 1]; j--; }
         order[j] = o;
     }
+    if (m == 0) return 0;                                      /* nothing left to rank (cannot happen: a bomb or the rocket stays) */
     int rounds = length / 3 + 1, n = 0;
     for (int k = 0; k < rounds; k++) {
         int lo = k < m ? k : m - 1, hi = m - 1 - k >= 0 ? m - 1 - k : 0;
