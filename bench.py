@@ -306,6 +306,22 @@ def verify_slice(D, torch, dev, rank, B):
     return "ok"
 
 
+def verify_timed_run(timed_state, B, rank, perm, lord, P):
+    """The timed run ITSELF, at full size: every env of this rank's slice was dealt, prefilled, warmed up and timed with moves
+    from its own Philox stream, so the oracle can replay all of it (ddz_ref_rollout_export, all host threads, about a second)
+    and the complete state of every env right after the timed region, and the counters, must be equal."""
+    import numpy as np
+    from oracle import ddz_oracle as O
+    fields, meta, stats, steps, listed = timed_state
+    n, ostats, f, m = O.rollout_export(B, steps, VARIANT, SEED, perm, lord, P, os.cpu_count() or 1, env0=rank * B)
+    if n != B * steps:
+        return "oracle replay failed on rank %d" % rank
+    st = stats.cpu().numpy()
+    same = (np.array_equal(fields.cpu().numpy().view(np.uint64), f) and np.array_equal(meta.cpu().numpy().view(np.uint32), m)
+            and np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 9]], ostats[[0, 1, 2, 3, 4, 5, 6, 9]]) and st[8] - listed == ostats[8])
+    return "ok" if same else "MISMATCH of the timed run's final state on rank %d" % rank
+
+
 def all_ranks_ok(D, torch, dev, world, verdict):
     import torch.distributed as dist
     bad = torch.tensor([0 if verdict == "ok" else 1], dtype=torch.int64, device=dev)
@@ -393,6 +409,10 @@ def run_config4(args):
     local_steps = int(dstats[4])
     assert local_steps == B * K, (local_steps, B * K)   # every env applied one move per step (finished ones re-dealt)
     nbar = float(dstats[8]) / local_steps
+    # what the timed run left behind, for verify_timed_run below (a 10 MB device copy, outside every timed region)
+    timed_state = None if args.no_verify else (
+        torch.cat([e._fields()[0] for e in ge.envs], dim=1).clone(), torch.cat([e._fields()[1] for e in ge.envs]).clone(),
+        ge.stats.clone(), int(ge.envs[0]._stepno), sum(int(e.num_actions) for e in ge.envs))
 
     # ---------------- for information: one chain of launches over all envs (no groups), graph replay and eager Python loop
     info = {}
@@ -484,6 +504,8 @@ def run_config4(args):
 
     # ---------------- after the timed regions: this rank's sample against the oracle
     verdict = "skipped" if args.no_verify else verify_slice(D, torch, dev, rank, B)
+    if verdict == "ok" and timed_state is not None:
+        verdict = verify_timed_run(timed_state, B, rank, perm, lord, P)
     if not args.no_verify:
         verdict = all_ranks_ok(D, torch, dev, world, verdict)
 
@@ -550,6 +572,10 @@ def run_config4(args):
                            "every %d steps" % REFILL},
             "gpu_launches": K * NG,
             "verify": verdict,
+            "verify_scope": "after the timed regions, on every rank: (1) a 512-env sample of its slice, every output of 48 steps "
+                            "against the oracle; (2) the timed run itself -- the complete state of ALL its envs and the counters "
+                            "right after the timed region against the oracle's replay of the same deals and Philox streams "
+                            "(prefill + warm-up + timed steps from the deal, ddz_ref_rollout_export)",
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -542,7 +542,7 @@ void ddz_ref_batch_export(const ddz_ref_env* envs, int B, uint64_t* f, uint32_t*
 /* ------------------------------------------------------------------ */
 typedef struct {
     int b0, b1, B, steps, warm, variant, pool_games;
-    uint64_t seed; const int8_t* perm; const int8_t* lord;
+    uint64_t seed, env0; const int8_t* perm; const int8_t* lord;
     int64_t stats[16]; uint64_t checksum; int64_t nsteps; double seconds;
     pthread_barrier_t* bar;
     uint64_t* out_fields; uint32_t* out_meta;   /* optional: the final state of every env (ddz_ref_rollout_export) */
@@ -579,7 +579,7 @@ static void* rollout_worker(void* arg) {
             ddz_ref_env_face(e, j->variant, face);                              /* a9 */
             ddz_ref_encode_actions(moves, N, af);                               /* a7 */
             j->stats[8] += N;
-            uint32_t k = ddz_ref_philox(j->seed, (uint64_t)b, (uint32_t)t) % (uint32_t)N;
+            uint32_t k = ddz_ref_philox(j->seed, j->env0 + (uint64_t)b, (uint32_t)t) % (uint32_t)N;
             int rr, dd, cc; float rw[3];
             int mc, ml, mv; ddz_ref_classify(moves + 15 * k, &mc, &ml, &mv);
             cs += ddz_ref_pack(moves + 15 * k) * 0x9E3779B97F4A7C15ULL + (uint64_t)N;
@@ -600,24 +600,24 @@ static void* rollout_worker(void* arg) {
     return 0;
 }
 
-static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, uint64_t env0, const int8_t* perm_pool,
                             const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
                             uint64_t* checksum, double* seconds, uint64_t* out_fields, uint32_t* out_meta);
 int64_t ddz_ref_rollout(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
                         const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
                         uint64_t* checksum, double* seconds) {
-    return rollout_impl(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads, stats, checksum,
+    return rollout_impl(B, warm_steps, steps, variant, seed, 0, perm_pool, lord_pool, pool_games, nthreads, stats, checksum,
                         seconds, 0, 0);
 }
 /* the same rollout from the deal, returning the final state of EVERY env in the device's export layout
  * (ddz_ref_batch_export): the full-size parity check -- one diverging move anywhere changes some env's state */
-int64_t ddz_ref_rollout_export(int B, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+int64_t ddz_ref_rollout_export(int B, int steps, int variant, uint64_t seed, uint64_t env0, const int8_t* perm_pool,
                                const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
                                uint64_t* fields9, uint32_t* meta) {
     if (!fields9 || !meta) return -1;
-    return rollout_impl(B, 0, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads, stats, 0, 0, fields9, meta);
+    return rollout_impl(B, 0, steps, variant, seed, env0, perm_pool, lord_pool, pool_games, nthreads, stats, 0, 0, fields9, meta);
 }
-static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, const int8_t* perm_pool,
+static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint64_t seed, uint64_t env0, const int8_t* perm_pool,
                             const int8_t* lord_pool, int pool_games, int nthreads, int64_t* stats,
                             uint64_t* checksum, double* seconds, uint64_t* out_fields, uint32_t* out_meta) {
     ensure();
@@ -633,7 +633,7 @@ static int64_t rollout_impl(int B, int warm_steps, int steps, int variant, uint6
         jobs[i].warm = warm_steps; jobs[i].bar = &bar;
         jobs[i].b0 = (int)((int64_t)B * i / nthreads); jobs[i].b1 = (int)((int64_t)B * (i + 1) / nthreads);
         jobs[i].B = B; jobs[i].steps = steps; jobs[i].variant = variant; jobs[i].pool_games = pool_games;
-        jobs[i].seed = seed; jobs[i].perm = perm_pool; jobs[i].lord = lord_pool;
+        jobs[i].seed = seed; jobs[i].env0 = env0; jobs[i].perm = perm_pool; jobs[i].lord = lord_pool;
         jobs[i].out_fields = out_fields; jobs[i].out_meta = out_meta;
         pthread_create(&th[i], 0, rollout_worker, &jobs[i]);
     }

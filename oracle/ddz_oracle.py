@@ -92,8 +92,8 @@ def lib():
         L.ddz_ref_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
                                       C.POINTER(C.c_double)]
         L.ddz_ref_rollout.restype = C.c_int64
-        L.ddz_ref_rollout_export.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, i8p, i8p, C.c_int, C.c_int, i64p, u64p,
-                                             u32p]
+        L.ddz_ref_rollout_export.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, i8p, i8p, C.c_int, C.c_int,
+                                             i64p, u64p, u32p]
         L.ddz_ref_rollout_export.restype = C.c_int64
         L.ddz_ref_get_moves_batch.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, i32p, u64p, C.POINTER(C.c_double)]
         L.ddz_ref_get_moves_batch.restype = C.c_int64
@@ -270,14 +270,15 @@ def rollout(B, warm_steps, steps, variant, seed, perm_pool, lord_pool, pool_game
     return int(n), float(sec.value), stats, int(cs.value)
 
 
-def rollout_export(B, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads):
-    """the rollout above from the deal, all envs: (env_steps, stats int64[16], fields uint64[9,B], meta uint32[B])"""
+def rollout_export(B, steps, variant, seed, perm_pool, lord_pool, pool_games, nthreads, env0=0):
+    """the rollout above from the deal, all envs (global env ids env0 .. env0 + B - 1): (env_steps, stats int64[16],
+    fields uint64[9,B], meta uint32[B])"""
     perm_pool = _i8(perm_pool)
     lp = None if lord_pool is None else _i8(lord_pool)
     stats = np.zeros(16, np.int64)
     f = np.zeros((9, int(B)), np.uint64)
     meta = np.zeros(int(B), np.uint32)
-    n = lib().ddz_ref_rollout_export(int(B), int(steps), int(variant), int(seed), _ptr(perm_pool, C.c_int8),
+    n = lib().ddz_ref_rollout_export(int(B), int(steps), int(variant), int(seed), int(env0), _ptr(perm_pool, C.c_int8),
                                      _ptr(lp, C.c_int8), int(pool_games), int(nthreads), _ptr(stats, C.c_int64),
                                      _ptr(f, C.c_uint64), _ptr(meta, C.c_uint32))
     if n < 0:
