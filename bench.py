@@ -646,7 +646,7 @@ def run_config5(args):
     e2e_ms = x0.elapsed_time(x1)
     assert int(off_h[n]) == total and int(gen.stats[7].item()) == 0
 
-    # ---------------- verification (outside the timed regions): a 512-pair sample of this rank against the oracle
+    # ---------------- verification (outside the timed regions): a 512-pair sample of this rank, list by list, against the oracle
     verdict = "skipped"
     if not args.no_verify:
         from oracle import ddz_oracle as O
@@ -658,6 +658,12 @@ def run_config5(args):
             if not np.array_equal(mv[off[i]:off[i + 1]], want):
                 verdict = "MISMATCH at pair %d on rank %d" % (i, rank)
                 break
+        if verdict == "ok":
+            # ... and ALL lists of this rank (the ones the e2e region brought back): lengths and an order-sensitive digest of every
+            # move against the oracle's generator
+            moves, counts, un, od = O.get_moves_digest(hands_np, lasts_np)
+            if moves != total or not np.array_equal(np.diff(off), counts) or O.lists_digest(mv, off) != (un, od):
+                verdict = "MISMATCH of the full-size digest on rank %d" % rank
         verdict = all_ranks_ok(D, torch, dev, world, verdict)
 
     total_ms = D.sharding.max_over_ranks(total_ms, dev)
