@@ -551,7 +551,7 @@ def run_config4(args):
                             "lord_win_rate": float(gstats[1].item()) / max(1, int(gstats[0].item())),
                             "window_trace": trace}, **info),
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": kern_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": kern_gbs / peak,
+                         "unit": "GB/s", "frac": kern_gbs / peak, "frac_of_nominal_8000_GBs": kern_gbs / 8000.0,
                          "frac_single_chain": (B * eb / (single * 1e-3) / 1e9 / peak) if single else None,
                          "traffic": ncu_traffic("config4_%dgroups%s" % (NG, "" if compressed else "_plain")),
                          "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
@@ -685,7 +685,8 @@ def run_config5(args):
                            "parallelism": "pair-shard x%d, no collective on the data path" % world,
                            "l2_policy": "each call writes %.0f MB of lists, more than the 126 MB L2; no flush" % (8 * total / 1e6)},
                 "roofline": {"bound": "hbm", "kernel": "k_legal_flat", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                             "frac": gbs / peak, "traffic": ncu_traffic("config5"), "peak_source": peak_src,
+                             "frac": gbs / peak, "frac_of_nominal_8000_GBs": gbs / 8000.0, "traffic": ncu_traffic("config5"),
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_pair": alg / n, "algorithmic_bytes_per_step": alg,
                              "note": "algorithmic bytes = 16 (hand, last) + 4 (offset) per pair + 8 per move; the kernel is "
                                      "issue-bound (integer work per move), far from the HBM roofline"},
@@ -802,7 +803,8 @@ def run_config3(args):
                                "--scoring module runs unchanged); the hot path contributes the env kernel, the Q-scoring kernels "
                                "(ddz_q_features or the in-place [n,C+1,15,4] encoder) and the segmented argmax"},
             "roofline": {"bound": "hbm", "kernel": "k_env<2,step+observe>", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                         "frac": gbs / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env": eb,
+                         "frac": gbs / peak, "frac_of_nominal_8000_GBs": gbs / 8000.0, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env": eb,
                          "note": "the env kernel alone (env_kernel_ms_per_step), one launch over %d envs between two network "
                                  "passes; the step as a whole is network-bound" % B},
             "e2e": {"value": B * K / (total_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
