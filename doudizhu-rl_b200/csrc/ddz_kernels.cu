@@ -842,6 +842,7 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
 #pragma unroll 1
     for (int c = 0; c < C; c++) {
         const uint64_t pl = s_planes[c];
+        if ((pl & 0x0777777777777777ull) == 0) continue;      // an empty plane (a pass, an untouched history) adds nothing
         const float sc = s_scale[c];
         // (form-B builds mark the nibbles of ranks 0..12 of a probability plane with bit 3 -- rows 9..12 --, its two joker
         // ranks stay unmarked: they hold 0 or 1 and use row 1)
