@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
                                                            int Wrt, void* __restrict__ out, int B) {
     constexpr int C = FaceCfg<V>::C;
     const int W = WC ? WC : Wrt;
-    extern __shared__ __align__(16) float4 s_t[];            // [5][kQThreads] a plane's scaled table rows, then s_m0
+    extern __shared__ __align__(16) float4 s_t[];            // [5][kQThreads] a plane's scaled table rows
     __shared__ uint64_t s_planes[C];
     __shared__ float s_scale[C];
     __shared__ float4 s_lut[16];
@@ -830,7 +830,6 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
     __syncthreads();
     const long long row0 = (dst_offsets ? (long long)dst_offsets[b] : (long long)src) - row_base;
     const int rowlen = 19 * W;
-    float* const s_m0 = reinterpret_cast<float*>(s_t + 5 * kQThreads);      // [15][kQThreads]: the empty move's rank features
     const int o = threadIdx.x;                                // W <= kQThreads (the reference's networks: W = 256)
     if (o >= W) return;                                       // no barrier below: idle threads may leave
     float4 F[15];                                             // F[r] = the four convolutions' sums over the face planes
@@ -873,8 +872,6 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
             S.x = fmaf(lw[r], q.x, S.x); S.y = fmaf(lw[r], q.y, S.y); S.z = fmaf(lw[r], q.z, S.z); S.w = fmaf(lw[r], q.w, S.w);
         }
     }
-#pragma unroll
-    for (int r = 0; r < 15; r++) s_m0[r * kQThreads + o] = fmaxf(fmaxf(F[r].x, F[r].y), fmaxf(F[r].z, F[r].w));
     const float4* TA = T + C * 16 * W + o;                    // the move's own plane is input channel C
     const float* LA = L + C * 15 * W + o;
 #pragma unroll 1
@@ -894,7 +891,7 @@ __global__ void __launch_bounds__(kQThreads) k_q_features(const void* state, con
                 const float lw = __ldg(LA + r * W);
                 const float4 q = s_lut[nib];
                 s.x = fmaf(lw, q.x, s.x); s.y = fmaf(lw, q.y, s.y); s.z = fmaf(lw, q.z, s.z); s.w = fmaf(lw, q.w, s.w);
-            } else m = s_m0[r * kQThreads + o];
+            } else m = fmaxf(fmaxf(F[r].x, F[r].y), fmaxf(F[r].z, F[r].w));
             if (BF16) row16[r * W] = __float2bfloat16_rn(m); else row32[r * W] = m;
         }
         if (BF16) {
@@ -1130,7 +1127,7 @@ static int launch_q_features(const void* state, const int32_t* offsets, const ui
                              const int32_t* dst_offsets, int env_begin, int env_count, long long row_base, const float* T,
                              const float* rank_bias, const float* L, const float* line_bias, int W, void* out, int out_bf16,
                              int B, cudaStream_t st) {
-    const size_t smem = (size_t)5 * kQThreads * sizeof(float4) + (size_t)15 * kQThreads * sizeof(float);   // 35 KB
+    const size_t smem = (size_t)5 * kQThreads * sizeof(float4);   // 20 KB
     const float4* T4 = reinterpret_cast<const float4*>(T);
     const float4* rb4 = reinterpret_cast<const float4*>(rank_bias);
 #define DDZ_Q_LAUNCH(BF, WC_) k_q_features<V, BF, WC_><<<env_count, kQThreads, smem, st>>>(                        \
