@@ -54,7 +54,7 @@ class BatchedGreedyPolicy:
     def select(self, env, q, stepno=None):
         """int32 [B] index into each env's legal list (dqn.py:60,70), -1 for finished envs."""
         choice = torch.empty(env.B, dtype=torch.int32, device=q.device)
-        q = q.contiguous()
+        q = q.contiguous() if q.numel() else torch.zeros(1, dtype=torch.float32, device=q.device)   # every env finished: no moves
         with torch.cuda.device(q.device):
             N.check(N.lib.ddz_select_actions(q.data_ptr(), env.offsets.data_ptr(), self.epsilon, self.seed, env.env0,
                                              env._stepno if stepno is None else int(stepno), choice.data_ptr(), env.B,

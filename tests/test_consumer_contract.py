@@ -157,3 +157,32 @@ def test_fused_scoring_follows_the_weights_during_training(D):
         assert game.lord._policy.scorer is not None
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
+@pytest.mark.gpu
+def test_fused_q_scorer_with_finished_envs(D):
+    """envs whose game is over have no legal moves: the scorer skips them (mixed batch) and returns an empty vector when
+    every env is finished"""
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        perm, lord = D.random_deals(600, seed=4)
+        env = D.BatchedEnvCooperation(600, seed=4)
+        env.prepare(torch.as_tensor(perm).cuda(), torch.as_tensor(lord).cuda())
+        net = QNetLike(9, 256, 64, seed=2).eval().cuda()
+        fused = D.BatchedGreedyPolicy(net, fused=True)
+        for _ in range(40):                                   # no re-deal: games end one by one
+            env.rollout_step()
+        done = env.is_done
+        assert 0 < int(done.sum()) < env.B
+        env.observe()
+        got, want = fused.q_values(env), D.BatchedGreedyPolicy(net).q_values(env)
+        assert got.shape[0] == env.num_actions
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        env.playout(max_steps=400)
+        env.observe()
+        assert bool(env.is_done.all()) and env.num_actions == 0
+        assert fused.q_values(env).numel() == 0
+        assert (fused.select(env, fused.q_values(env)) == -1).all()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
