@@ -23,6 +23,16 @@ def test_library_exports_every_declared_symbol():
     assert D.native.lib.ddz_face_channels(4) == D.native.E_ARG
     assert D.native.lib.ddz_state_bytes(1000) == 1000 * 76 and D.native.lib.ddz_state_bytes(0) == 0
     assert D.native.lib.ddz_workspace_bytes(4096) == 256 + 8 * 128
+    # argument checks come before any CUDA call (no compute without a GPU): null buffers, empty batches, a width the kernel
+    # does not handle
+    L, E = D.native.lib, D.native.E_ARG
+    assert L.ddz_mcts_moves(None, None, None, None, 4, None) == E and L.ddz_mcts_moves(1, 1, 1, 1, 0, None) == E
+    assert L.ddz_playout_pruned(None, 10, 0, 0, 0, None, None, None, 4, None) == E
+    assert L.ddz_playout(1, -1, 0, 0, 0, None, None, None, 4, None) == E
+    assert L.ddz_q_features(1, 2, 1, 1, None, None, 0, 4, 0, 1, 1, 1, 1, 260, 1, 0, 4, None) == E     # width > 256
+    assert L.ddz_q_features(1, 2, 1, 1, None, None, 0, 4, 0, 1, 1, 1, 1, 30, 1, 0, 4, None) == E      # not a multiple of 4
+    assert L.ddz_q_features(1, 2, 1, 1, None, None, 2, 4, 0, 1, 1, 1, 1, 256, 1, 0, 4, None) == E     # env range past B
+    assert L.ddz_q_features(1, 7, 1, 1, None, None, 0, 4, 0, 1, 1, 1, 1, 256, 1, 0, 4, None) == E     # no such face variant
 
 
 def test_sass_is_sm100a_only():
